@@ -1,0 +1,14 @@
+"""corticall_b200 -- B200 (sm_100a) implementation of Corticall's data-parallel k-mer hot path.
+
+The product is `libcorticall_cuda.so` (C ABI in include/corticall_cuda.h; CUDA sources in csrc/).  `host/`
+mirrors the reference's Java class-library surface for that path (CortexGraph, CortexRecord, CanonicalKmer,
+FindROIs, the Call helpers) on top of the C ABI.  There is no CPU fallback.
+"""
+from ._native import (CC_ALGO_AUTO, CC_ALGO_BSEARCH, CC_ALGO_MERGE, CortexJDKException, device_count, launch_count, lib,
+                      set_option)
+from .host.cortex import CortexColor, CortexGraph, CortexHeader, CortexRecord, packCanonical
+from .host.kmer import CanonicalKmer, CortexBinaryKmer, CortexByteKmer, SequenceUtils
+
+__all__ = ["CortexGraph", "CortexRecord", "CortexHeader", "CortexColor", "CanonicalKmer", "CortexByteKmer",
+           "CortexBinaryKmer", "SequenceUtils", "CortexJDKException", "packCanonical", "lib", "launch_count",
+           "set_option", "device_count", "CC_ALGO_AUTO", "CC_ALGO_BSEARCH", "CC_ALGO_MERGE"]

@@ -1,0 +1,909 @@
+// api.cu -- the extern "C" surface of libcorticall_cuda (include/corticall_cuda.h): handle lifecycle,
+// .ctx header parsing, host<->device marshalling around the kernels of scan.cu / lookup.cu.
+//
+// Reference behaviour mirrored here (S/ = public/java/src/uk/ac/ox/well/cortexjdk/):
+//   header parse + error texts   S/utils/io/graph/cortex/CortexGraph.java:66-168
+//   numRecords floors            S/utils/io/graph/cortex/CortexGraph.java:148-149
+//   getColorForSampleName        S/utils/io/graph/cortex/CortexGraph.java:335-354
+//   ROI header                   S/commands/discover/roi/FindROIs.java:85-105 + CortexGraphWriter.java:31-104
+//
+// There is no CPU implementation of any compute entry point in this library: without a CUDA device they
+// fail with CC_ERR_CUDA.
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <strings.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "cc_internal.hpp"
+
+namespace cc {
+
+// ------------------------------------------------------------------ errors / options / counters
+static thread_local std::string t_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+int fail(int status, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    return status;
+}
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    const char *base = strrchr(file, '/');
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, base ? base + 1 : file, line);
+    return CC_ERR_CUDA;
+}
+
+std::atomic<uint64_t> g_launches{0};
+
+Options &options() {
+    static Options o;
+    return o;
+}
+
+// ------------------------------------------------------------------ header (ctx_spec.md tables 1-3)
+namespace {
+
+struct Cursor {
+    const uint8_t *p;
+    uint64_t avail, pos = 0;
+    bool ok = true;
+    bool need(uint64_t n) {
+        if (!ok || pos + n > avail) { ok = false; return false; }
+        return true;
+    }
+    uint32_t u32() {
+        if (!need(4)) return 0;
+        uint32_t v;
+        memcpy(&v, p + pos, 4);
+        pos += 4;
+        return v;
+    }
+    uint64_t u64() {
+        if (!need(8)) return 0;
+        uint64_t v;
+        memcpy(&v, p + pos, 8);
+        pos += 8;
+        return v;
+    }
+    uint8_t u8() {
+        if (!need(1)) return 0;
+        return p[pos++];
+    }
+    // fixStringsWithEarlyTerminators (CortexGraph.java:50-64): cut at the first NUL
+    std::string str(uint64_t n) {
+        if (!need(n)) return std::string();
+        const char *b = reinterpret_cast<const char *>(p + pos);
+        pos += n;
+        return std::string(b, strnlen(b, n));
+    }
+};
+
+bool magic_ok(const uint8_t *p) { return strncasecmp(reinterpret_cast<const char *>(p), "CORTEX", 6) == 0; }
+
+}  // namespace
+
+int parse_header(const uint8_t *buf, uint64_t avail, uint64_t total_size, const char *path, Header &h) {
+    Cursor c{buf, avail};
+    if (avail < 6 || !magic_ok(buf))
+        return fail(CC_ERR_NOT_CORTEX, "The file '%s' does not appear to be a Cortex graph", path);
+    c.pos = 6;
+    h.version = c.u32();
+    if (!c.ok) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': truncated header", path);
+    if (h.version != 6) return fail(CC_ERR_BAD_VERSION, "The file '%s' is not a version 6 Cortex graph", path);
+    h.k = c.u32();
+    h.s = c.u32();
+    h.c = c.u32();
+    if (!c.ok || (uint64_t)h.c * 12 > avail)
+        return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': truncated header", path);
+    h.colors.assign(h.c, ColorMeta());
+    for (uint32_t i = 0; i < h.c; ++i) h.colors[i].info.mean_read_length = c.u32();
+    for (uint32_t i = 0; i < h.c; ++i) h.colors[i].info.total_sequence = c.u64();
+    for (uint32_t i = 0; i < h.c; ++i) {
+        const uint32_t L = c.u32();
+        h.colors[i].sample_name = c.str(L);
+    }
+    for (uint32_t i = 0; i < h.c; ++i) { c.need(16); c.pos += c.ok ? 16 : 0; }   // long double error rates: skipped like the reference
+    for (uint32_t i = 0; i < h.c; ++i) {
+        cc_color_info &ci = h.colors[i].info;
+        ci.tip_clipping = c.u8();
+        ci.low_covg_supernodes_removed = c.u8();
+        ci.low_covg_kmers_removed = c.u8();
+        ci.cleaned_against_graph = c.u8();
+        ci.low_cov_supernodes_threshold = c.u32();
+        ci.low_cov_kmer_threshold = c.u32();
+        const uint32_t G = c.u32();
+        h.colors[i].graph_name = c.str(G);
+    }
+    if (!c.need(6)) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': truncated header", path);
+    if (!magic_ok(buf + c.pos))
+        return fail(CC_ERR_BAD_TRAILER, "We didn't see a proper header terminator at the expected place in Cortex graph '%s'", path);
+    c.pos += 6;
+    h.data_offset = c.pos;
+    h.record_size = 8ull * h.s + 5ull * h.c;
+    if (h.record_size == 0) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': zero-sized records", path);
+    h.num_records = (total_size - h.data_offset) / h.record_size;       // floors: trailing partial record ignored
+    return CC_OK;
+}
+
+std::vector<uint8_t> make_roi_header(uint32_t k, uint32_t s, const std::string &name) {
+    static const uint8_t err[16] = {0, 0xd8, 0xa3, 0x70, 0x3d, 0x0a, 0xd7, 0xa3, 0xf8, 0x3f, 0, 0, 0, 0, 0, 0};   // CortexGraphWriter.java:76
+    std::vector<uint8_t> out;
+    auto u32 = [&](uint32_t v) { for (int i = 0; i < 4; ++i) out.push_back((uint8_t)(v >> (8 * i))); };
+    auto raw = [&](const void *p, size_t n) { out.insert(out.end(), (const uint8_t *)p, (const uint8_t *)p + n); };
+    raw("CORTEX", 6);
+    u32(6); u32(k); u32(s); u32(1);
+    u32(0);                 // mean read length
+    u32(0); u32(0);         // total sequence
+    u32((uint32_t)name.size()); raw(name.data(), name.size());
+    raw(err, 16);
+    u32(0);                 // four cleaning booleans
+    u32(0); u32(0);         // thresholds
+    u32(0);                 // cleaned-against graph name: empty
+    raw("CORTEX", 6);
+    return out;
+}
+
+namespace {
+
+// ------------------------------------------------------------------ handle plumbing
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CC_ERR_CUDA, "no CUDA device available (%s); libcorticall_cuda has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(CC_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    return CC_OK;
+}
+
+int init_handle(cc_graph *g, int device) {
+    g->device = device;
+    CC_CUDA(cudaSetDevice(device));
+    CC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    CC_CUDA(cudaEventCreate(&g->ev0));
+    CC_CUDA(cudaEventCreate(&g->ev1));
+    CC_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device));
+    return CC_OK;
+}
+
+int upload_body(cc_graph *g) {
+    const uint64_t bytes = g->h.num_records * g->h.record_size;
+    void *d = nullptr;
+    CC_CUDA(cudaMalloc(&d, bytes + 256));            // slack: tiles are fetched as 16-byte-aligned supersets
+    g->dev_alloc = d;
+    g->dev_body = static_cast<const uint8_t *>(d);
+    const uint8_t *src = g->host_image + g->h.data_offset;
+    const uint64_t chunk = 256ull << 20;
+    for (uint64_t off = 0; off < bytes; off += chunk) {
+        const uint64_t nb = std::min(chunk, bytes - off);
+        CC_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(d) + off, src + off, nb, cudaMemcpyHostToDevice, g->stream));
+    }
+    CC_CUDA(cudaMemsetAsync(static_cast<uint8_t *>(d) + bytes, 0, 256, g->stream));
+    CC_CUDA(cudaStreamSynchronize(g->stream));
+    return CC_OK;
+}
+
+void destroy(cc_graph *g) {
+    if (!g) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    g->scan_ws.release();
+    if (g->index.keys) cudaFree(g->index.keys);
+    if (g->index.table) cudaFree(g->index.table);
+    if (g->novel_buf) cudaFree(g->novel_buf);
+    if (g->novel_idx) cudaFree(g->novel_idx);
+    if (g->dev_alloc) cudaFree(g->dev_alloc);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->map_base) munmap(g->map_base, g->map_len);
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+    delete g;
+}
+
+int finish_open(std::unique_ptr<cc_graph, void (*)(cc_graph *)> &g, int device, cc_graph **out) {
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    if (int rc = init_handle(g.get(), device)) return rc;
+    if (int rc = upload_body(g.get())) return rc;
+    *out = g.release();
+    return CC_OK;
+}
+
+#define CC_REQUIRE(cond, ...)                                   \
+    do {                                                        \
+        if (!(cond)) return ::cc::fail(CC_ERR_ARG, __VA_ARGS__); \
+    } while (0)
+
+int check_colors(const cc_graph *g, int32_t child, const int32_t *parents, int nparents) {
+    // The reference indexes int[] coverages with these: out of range = ArrayIndexOutOfBoundsException
+    // (e.g. getColorForSampleName returned -1).
+    if (child < 0 || (uint32_t)child >= g->h.c)
+        return fail(CC_ERR_ARG, "child colour %d out of range (graph has %u colours)", child, g->h.c);
+    if (nparents < 0 || (nparents > 0 && !parents)) return fail(CC_ERR_ARG, "bad parent list");
+    for (int i = 0; i < nparents; ++i)
+        if (parents[i] < 0 || (uint32_t)parents[i] >= g->h.c)
+            return fail(CC_ERR_ARG, "parent colour %d out of range (graph has %u colours)", parents[i], g->h.c);
+    return CC_OK;
+}
+
+// Copies the parent list to the workspace (skipped when unchanged) and sizes the look-back state.
+int prepare_scan(cc_graph *g, uint64_t n_per_launch, const int32_t *parents, int nparents, cudaStream_t st) {
+    if (int rc = g->scan_ws.ensure(scan_tiles_for(n_per_launch, g->h.s, g->h.c), (uint32_t)nparents)) return rc;
+    if (nparents > 0) {
+        if (g->parents_cached.size() != (size_t)nparents || memcmp(g->parents_cached.data(), parents, 4 * (size_t)nparents) != 0) {
+            g->parents_cached.assign(parents, parents + nparents);
+            CC_CUDA(cudaMemcpyAsync(g->scan_ws.parents, g->parents_cached.data(), 4 * (size_t)nparents, cudaMemcpyHostToDevice, st));
+        }
+    }
+    return CC_OK;
+}
+
+int sync_stream(cc_graph *, cudaStream_t st) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    return CC_OK;
+}
+
+int ensure_index(cc_graph *g) {
+    if (!g->index.built) {
+        if (int rc = build_index(g, 0)) return rc;
+    }
+    if (!g->index.sorted)
+        return fail(CC_ERR_UNSORTED, "Records are not sorted (record %llu sorts before its predecessor)",
+                    (unsigned long long)g->index.unsorted_at);
+    return CC_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        CC_CUDA(cudaMalloc(&p, std::max<size_t>(n, 16)));
+        return CC_OK;
+    }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+}  // namespace
+}  // namespace cc
+
+using namespace cc;
+
+// ==================================================================== library
+extern "C" {
+
+const char *cc_last_error(void) { return t_error.c_str(); }
+const char *cc_version(void) { return "corticall_cuda 0.1 (sm_100a)"; }
+
+int cc_device_count(int *out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (out) *out = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CC_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
+    }
+    if (n == 0) return fail(CC_ERR_CUDA, "no CUDA device available (device count is 0)");
+    return CC_OK;
+}
+
+uint64_t cc_launch_count(void) { return g_launches.load(); }
+
+int cc_set_option(const char *name, int64_t value) {
+    if (!name) return fail(CC_ERR_ARG, "option name is null");
+    Options &o = options();
+    if (!strcmp(name, "scan_stages")) o.scan_stages = (int)value;
+    else if (!strcmp(name, "scan_tile_bytes")) o.scan_tile_bytes = (int)value;
+    else if (!strcmp(name, "scan_ctas_per_sm")) o.scan_ctas_per_sm = (int)value;
+    else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
+    else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
+    else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;
+    else return fail(CC_ERR_ARG, "unknown option '%s'", name);
+    return CC_OK;
+}
+
+// ==================================================================== lifecycle
+int cc_open(const char *path, int device, cc_graph **out) {
+    if (!path || !out) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(new cc_graph(), destroy);
+    g->path = path;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) {
+        if (errno == ENOENT) return fail(CC_ERR_IO, "Cortex graph file '%s' not found: %s", path, strerror(errno));
+        return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': %s", path, strerror(errno));
+    }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': %s", path, strerror(errno)); }
+    const uint64_t size = (uint64_t)sb.st_size;
+    if (size == 0) { close(fd); return fail(CC_ERR_NOT_CORTEX, "The file '%s' does not appear to be a Cortex graph", path); }
+    void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': mmap: %s", path, strerror(errno));
+    g->map_base = m;
+    g->map_len = size;
+    g->host_image = static_cast<const uint8_t *>(m);
+    g->host_size = size;
+    if (int rc = parse_header(g->host_image, size, size, path, g->h)) return rc;
+    return finish_open(g, device, out);
+}
+
+int cc_open_memory(const void *file_image, uint64_t size, int device, cc_graph **out) {
+    if (!file_image || !out) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(new cc_graph(), destroy);
+    g->path = "<memory>";
+    g->owned_image.assign(static_cast<const uint8_t *>(file_image), static_cast<const uint8_t *>(file_image) + size);
+    g->host_image = g->owned_image.data();
+    g->host_size = size;
+    if (int rc = parse_header(g->host_image, size, size, "<memory>", g->h)) return rc;
+    return finish_open(g, device, out);
+}
+
+int cc_open_device(const void *dev_body, uint32_t k, uint32_t s, uint32_t c, uint64_t n, uint64_t first_index, int device,
+                   cc_graph **out) {
+    if (!out || (!dev_body && n)) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (k == 0 || s != (k + 31) / 32) return fail(CC_ERR_ARG, "kmer_bits %u does not match kmer_size %u", s, k);
+    if (int rc = check_device(device)) return rc;
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(new cc_graph(), destroy);
+    g->path = "<device>";
+    g->h.version = 6; g->h.k = k; g->h.s = s; g->h.c = c;
+    g->h.record_size = 8ull * s + 5ull * c;
+    g->h.num_records = n;
+    g->h.colors.assign(c, ColorMeta());
+    for (uint32_t i = 0; i < c; ++i) g->h.colors[i].sample_name = std::to_string(i);
+    g->dev_body = static_cast<const uint8_t *>(dev_body);
+    g->first_index = first_index;
+    DeviceGuard guard(device);
+    if (int rc = init_handle(g.get(), device)) return rc;
+    *out = g.release();
+    return CC_OK;
+}
+
+void cc_dispose(cc_graph *g) { destroy(g); }
+
+// ==================================================================== header / colours
+int cc_header(const cc_graph *g, uint32_t *version, uint32_t *kmer_size, uint32_t *kmer_bits, uint32_t *num_colors,
+              uint64_t *num_records, uint64_t *data_offset, uint64_t *record_size) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    if (version) *version = g->h.version;
+    if (kmer_size) *kmer_size = g->h.k;
+    if (kmer_bits) *kmer_bits = g->h.s;
+    if (num_colors) *num_colors = g->h.c;
+    if (num_records) *num_records = g->h.num_records;
+    if (data_offset) *data_offset = g->h.data_offset;
+    if (record_size) *record_size = g->h.record_size;
+    return CC_OK;
+}
+
+static int copy_string(const std::string &s, char *buf, size_t cap) {
+    if (!buf || cap < s.size() + 1) return fail(CC_ERR_ARG, "buffer too small (%zu needed)", s.size() + 1);
+    memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    return CC_OK;
+}
+
+int cc_color_name(const cc_graph *g, uint32_t color, char *buf, size_t cap) {
+    if (!g || color >= g->h.c) return fail(CC_ERR_ARG, "colour %u out of range", color);
+    return copy_string(g->h.colors[color].sample_name, buf, cap);
+}
+int cc_color_graph_name(const cc_graph *g, uint32_t color, char *buf, size_t cap) {
+    if (!g || color >= g->h.c) return fail(CC_ERR_ARG, "colour %u out of range", color);
+    return copy_string(g->h.colors[color].graph_name, buf, cap);
+}
+int cc_color_info_get(const cc_graph *g, uint32_t color, cc_color_info *out) {
+    if (!g || !out || color >= g->h.c) return fail(CC_ERR_ARG, "colour %u out of range", color);
+    *out = g->h.colors[color].info;
+    return CC_OK;
+}
+
+int cc_color_for_sample_name(const cc_graph *g, const char *name, int32_t *out_color) {
+    if (!g || !name || !out_color) return fail(CC_ERR_ARG, "null argument");
+    int32_t color = -1;
+    int copies = 0;
+    for (uint32_t c = 0; c < g->h.c; ++c) {
+        if (strcasecmp(g->h.colors[c].sample_name.c_str(), name) == 0) { color = (int32_t)c; ++copies; }
+    }
+    if (color == -1) {       // Integer.valueOf(sampleName): optional sign, decimal digits only
+        const char *p = name;
+        if (*p == '+' || *p == '-') ++p;
+        bool digits = *p != 0;
+        for (const char *q = p; *q; ++q) digits &= (*q >= '0' && *q <= '9');
+        if (digits) { color = (int32_t)strtol(name, nullptr, 10); copies = 1; }
+    }
+    *out_color = (copies == 1) ? color : -1;
+    return CC_OK;
+}
+
+// ==================================================================== K1: record access / decode
+int cc_get_records(const cc_graph *g, uint64_t first, uint64_t count, void *out_raw) {
+    if (!g || (!out_raw && count)) return fail(CC_ERR_ARG, "null argument");
+    if (first > g->h.num_records || count > g->h.num_records - first)
+        return fail(CC_ERR_RANGE, "Record index is out of range (%llu+%llu vs 0-%lld)", (unsigned long long)first,
+                    (unsigned long long)count, (long long)g->h.num_records - 1);
+    const uint64_t S = g->h.record_size;
+    if (g->host_image) {
+        memcpy(out_raw, g->host_image + g->h.data_offset + first * S, count * S);
+        return CC_OK;
+    }
+    DeviceGuard guard(g->device);
+    CC_CUDA(cudaMemcpy(out_raw, g->dev_body + first * S, count * S, cudaMemcpyDeviceToHost));
+    return CC_OK;
+}
+
+int cc_decode_records_dev(cc_graph *g, uint64_t first, uint64_t count, uint64_t *dev_words, int32_t *dev_coverage,
+                          uint8_t *dev_edges, void *stream) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    if (first > g->h.num_records || count > g->h.num_records - first)
+        return fail(CC_ERR_RANGE, "Record index is out of range (%llu+%llu vs 0-%lld)", (unsigned long long)first,
+                    (unsigned long long)count, (long long)g->h.num_records - 1);
+    DeviceGuard guard(g->device);
+    return launch_decode_columns(g->dev_body + first * g->h.record_size, count, g->h.s, g->h.c, dev_words, dev_coverage, dev_edges,
+                                 g->scan_ws, g->sm_count, static_cast<cudaStream_t>(stream));
+}
+
+int cc_decode_records(cc_graph *g, uint64_t first, uint64_t count, uint64_t *out_words, int32_t *out_coverage, uint8_t *out_edges) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    DeviceGuard guard(g->device);
+    DevBuf w, c, e;
+    if (out_words) if (int rc = w.alloc(count * g->h.s * 8)) return rc;
+    if (out_coverage) if (int rc = c.alloc(count * g->h.c * 4)) return rc;
+    if (out_edges) if (int rc = e.alloc(count * g->h.c)) return rc;
+    if (int rc = cc_decode_records_dev(g, first, count, w.as<uint64_t>(), c.as<int32_t>(), e.as<uint8_t>(), g->stream)) return rc;
+    if (out_words) CC_CUDA(cudaMemcpyAsync(out_words, w.p, count * g->h.s * 8, cudaMemcpyDeviceToHost, g->stream));
+    if (out_coverage) CC_CUDA(cudaMemcpyAsync(out_coverage, c.p, count * g->h.c * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (out_edges) CC_CUDA(cudaMemcpyAsync(out_edges, e.p, count * g->h.c, cudaMemcpyDeviceToHost, g->stream));
+    return sync_stream(g, g->stream);
+}
+
+// ==================================================================== K1+K2: novelty scan
+int cc_find_novel_dev(cc_graph *g, int32_t child, const int32_t *parents, int nparents, void *dev_out_records,
+                      uint64_t *dev_out_index, uint64_t cap, uint64_t *dev_out_count, void *stream) {
+    if (!g || !dev_out_count || (cap && !dev_out_records)) return fail(CC_ERR_ARG, "null argument");
+    if (int rc = check_colors(g, child, parents, nparents)) return rc;
+    DeviceGuard guard(g->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = prepare_scan(g, g->h.num_records, parents, nparents, st)) return rc;
+    ScanArgs a{};
+    a.body = g->dev_body; a.n = g->h.num_records; a.index_base = g->first_index;
+    a.k = g->h.k; a.s = g->h.s; a.c = g->h.c;
+    a.child = child; a.nparents = nparents;
+    a.out_records = static_cast<uint8_t *>(dev_out_records); a.out_index = dev_out_index; a.cap = cap;
+    a.total_in = nullptr; a.total_out = dev_out_count;
+    return launch_scan_novel(a, g->scan_ws, g->sm_count, st);
+}
+
+int cc_find_novel(cc_graph *g, int32_t child, const int32_t *parents, int nparents, void *out_records, uint64_t *out_index,
+                  uint64_t cap, uint64_t *out_count) {
+    if (!g || !out_count) return fail(CC_ERR_ARG, "null argument");
+    if (int rc = check_colors(g, child, parents, nparents)) return rc;
+    DeviceGuard guard(g->device);
+    const uint64_t n = g->h.num_records, O = 8ull * g->h.s + 5;
+    const bool want_index = out_index != nullptr;
+    uint64_t want = std::min(cap, n);
+    if (!out_records) want = 0;
+    // Device staging sized for the expected (small) novel fraction; grown and re-run if it overflowed.
+    uint64_t dcap = std::min<uint64_t>(want, std::max<uint64_t>(65536, n / 32));
+    g->stats = cc_stats{};
+    const uint64_t launches0 = g_launches.load();
+    uint64_t total = 0;
+    float kernel_ms = 0.f;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (dcap > g->novel_cap) {
+            if (g->novel_buf) { cudaFree(g->novel_buf); g->novel_buf = nullptr; }
+            if (g->novel_idx) { cudaFree(g->novel_idx); g->novel_idx = nullptr; }
+            g->novel_cap = 0;
+            CC_CUDA(cudaMalloc(&g->novel_buf, dcap * O + 64));
+            CC_CUDA(cudaMalloc(&g->novel_idx, dcap * 8 + 64));
+            g->novel_cap = dcap;
+        }
+        if (int rc = g->scan_ws.ensure(0, 0)) return rc;
+        uint64_t *d_count = g->scan_ws.totals + 4;
+        CC_CUDA(cudaEventRecord(g->ev0, g->stream));
+        if (int rc = cc_find_novel_dev(g, child, parents, nparents, g->novel_buf, want_index ? static_cast<uint64_t *>(g->novel_idx) : nullptr, dcap, d_count, g->stream)) return rc;
+        CC_CUDA(cudaEventRecord(g->ev1, g->stream));
+        CC_CUDA(cudaMemcpyAsync(&total, d_count, 8, cudaMemcpyDeviceToHost, g->stream));
+        if (int rc = sync_stream(g, g->stream)) return rc;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+        kernel_ms += ms;
+        g->stats.d2h_bytes += 8;
+        const uint64_t need = std::min(total, want);
+        if (need <= dcap) break;
+        dcap = need;
+    }
+    const uint64_t got = std::min(total, want);
+    if (got) {
+        CC_CUDA(cudaMemcpyAsync(out_records, g->novel_buf, got * O, cudaMemcpyDeviceToHost, g->stream));
+        if (want_index) CC_CUDA(cudaMemcpyAsync(out_index, g->novel_idx, got * 8, cudaMemcpyDeviceToHost, g->stream));
+        if (int rc = sync_stream(g, g->stream)) return rc;
+        g->stats.d2h_bytes += got * O + (want_index ? got * 8 : 0);
+    }
+    *out_count = total;
+    g->stats.kernel_ms = kernel_ms;
+    g->stats.total_ms = kernel_ms;
+    g->stats.launches = (uint32_t)(g_launches.load() - launches0);
+    return CC_OK;
+}
+
+int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s, uint32_t c, uint64_t n, int32_t child,
+                       const int32_t *parents, int nparents, void *out_records, uint64_t *out_index, uint64_t cap,
+                       uint64_t *out_count, cc_stats *stats) {
+    if (!out_count || (!host_body && n)) return fail(CC_ERR_ARG, "null argument");
+    if (int rc = check_device(device)) return rc;
+    if (k == 0 || s != (k + 31) / 32) return fail(CC_ERR_ARG, "kmer_bits %u does not match kmer_size %u", s, k);
+    DeviceGuard guard(device);
+    // A transient handle over nothing: only its workspace, stream and header fields are used.
+    cc_graph *gp = nullptr;
+    if (int rc = cc_open_device(nullptr, k, s, c, 0, 0, device, &gp)) return rc;
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(gp, destroy);
+    g->h.num_records = n;
+    if (int rc = check_colors(g.get(), child, parents, nparents)) return rc;
+
+    const uint64_t S = g->h.record_size, O = 8ull * s + 5;
+    // chunk = whole records, a multiple of 32 records so that every chunk starts 16-byte aligned on the device
+    uint64_t chunk_rec = (((uint64_t)std::max(1, options().host_chunk_mb) << 20) / S) & ~31ull;
+    if (chunk_rec < 32) chunk_rec = 32;
+    const uint64_t nchunks = n ? (n + chunk_rec - 1) / chunk_rec : 0;
+    constexpr int NB = 3;
+    DevBuf buf[NB], dout, didx;
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t copied[NB] = {}, consumed[NB] = {}, t0 = nullptr, t1 = nullptr;
+    struct Cleanup {
+        cudaStream_t &s; cudaEvent_t *a, *b; cudaEvent_t &t0, &t1;
+        ~Cleanup() {
+            for (int i = 0; i < NB; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); }
+            if (t0) cudaEventDestroy(t0);
+            if (t1) cudaEventDestroy(t1);
+            if (s) cudaStreamDestroy(s);
+        }
+    } cleanup{copy_st, copied, consumed, t0, t1};
+    CC_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    CC_CUDA(cudaEventCreate(&t0));
+    CC_CUDA(cudaEventCreate(&t1));
+    for (int i = 0; i < NB; ++i) {
+        CC_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        CC_CUDA(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
+        if (i < (int)std::min<uint64_t>(nchunks, NB)) if (int rc = buf[i].alloc(chunk_rec * S + 256)) return rc;
+    }
+    const uint64_t want = out_records ? std::min(cap, n) : 0;
+    // device staging for the output: expected-small; the scan is re-run with a larger one if it overflows
+    uint64_t dcap = std::min<uint64_t>(want, std::max<uint64_t>(65536, n / 32));
+    uint64_t total = 0;
+    const uint64_t launches0 = g_launches.load();
+    uint64_t h2d = 0;
+    float total_ms = 0.f;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        DevBuf o, ix;
+        if (int rc = o.alloc(dcap * O + 64)) return rc;
+        if (out_index) if (int rc = ix.alloc(dcap * 8 + 64)) return rc;
+        if (int rc = prepare_scan(g.get(), chunk_rec, parents, nparents, g->stream)) return rc;
+        uint64_t *totals = g->scan_ws.totals;     // [0],[1] ping-pong
+        CC_CUDA(cudaMemsetAsync(totals, 0, 16, g->stream));
+        CC_CUDA(cudaEventRecord(t0, g->stream));
+        CC_CUDA(cudaStreamWaitEvent(copy_st, t0, 0));
+        for (uint64_t ci = 0; ci < nchunks; ++ci) {
+            const int b = (int)(ci % NB);
+            const uint64_t r0 = ci * chunk_rec, nr = std::min(chunk_rec, n - r0);
+            if (ci >= NB) CC_CUDA(cudaStreamWaitEvent(copy_st, consumed[b], 0));
+            CC_CUDA(cudaMemcpyAsync(buf[b].p, static_cast<const uint8_t *>(host_body) + r0 * S, nr * S, cudaMemcpyHostToDevice, copy_st));
+            CC_CUDA(cudaEventRecord(copied[b], copy_st));
+            CC_CUDA(cudaStreamWaitEvent(g->stream, copied[b], 0));
+            h2d += nr * S;
+            ScanArgs a{};
+            a.body = buf[b].as<uint8_t>(); a.n = nr; a.index_base = r0;
+            a.k = k; a.s = s; a.c = c; a.child = child; a.nparents = nparents;
+            a.out_records = o.as<uint8_t>(); a.out_index = out_index ? ix.as<uint64_t>() : nullptr; a.cap = dcap;
+            a.total_in = totals + (ci & 1); a.total_out = totals + ((ci + 1) & 1);
+            if (int rc = launch_scan_novel(a, g->scan_ws, g->sm_count, g->stream)) return rc;
+            CC_CUDA(cudaEventRecord(consumed[b], g->stream));
+        }
+        CC_CUDA(cudaMemcpyAsync(&total, totals + (nchunks & 1), 8, cudaMemcpyDeviceToHost, g->stream));
+        if (int rc = sync_stream(g.get(), g->stream)) return rc;
+        const uint64_t need = std::min(total, want);
+        if (need <= dcap) {
+            if (need) {
+                CC_CUDA(cudaMemcpyAsync(out_records, o.p, need * O, cudaMemcpyDeviceToHost, g->stream));
+                if (out_index) CC_CUDA(cudaMemcpyAsync(out_index, ix.p, need * 8, cudaMemcpyDeviceToHost, g->stream));
+            }
+            CC_CUDA(cudaEventRecord(t1, g->stream));
+            if (int rc = sync_stream(g.get(), g->stream)) return rc;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t0, t1);
+            total_ms += ms;
+            if (stats) {
+                stats->kernel_ms = 0.f;
+                stats->total_ms = total_ms;
+                stats->h2d_bytes = h2d;
+                stats->d2h_bytes = 8 + need * O + (out_index ? need * 8 : 0);
+                stats->launches = (uint32_t)(g_launches.load() - launches0);
+            }
+            break;
+        }
+        CC_CUDA(cudaEventRecord(t1, g->stream));
+        if (int rc = sync_stream(g.get(), g->stream)) return rc;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        total_ms += ms;
+        dcap = need;
+    }
+    *out_count = total;
+    return CC_OK;
+}
+
+int cc_write_roi_file(cc_graph *g, int32_t child, const int32_t *parents, int nparents, const char *out_path, uint64_t *out_count) {
+    if (!g || !out_path) return fail(CC_ERR_ARG, "null argument");
+    if (int rc = check_colors(g, child, parents, nparents)) return rc;
+    const uint64_t O = 8ull * g->h.s + 5;
+    // first pass with the default staging gives the count; cc_find_novel re-runs itself when it overflowed
+    std::vector<uint8_t> recs;
+    uint64_t total = 0;
+    uint64_t cap = std::max<uint64_t>(65536, g->h.num_records / 32);
+    cap = std::min(cap, g->h.num_records);
+    recs.resize(std::max<uint64_t>(cap, 1) * O);
+    if (int rc = cc_find_novel(g, child, parents, nparents, recs.data(), nullptr, cap, &total)) return rc;
+    if (total > cap) {
+        cap = total;
+        recs.resize(cap * O);
+        if (int rc = cc_find_novel(g, child, parents, nparents, recs.data(), nullptr, cap, &total)) return rc;
+    }
+    const std::vector<uint8_t> hdr = make_roi_header(g->h.k, g->h.s, g->h.colors[child].sample_name);
+    FILE *f = fopen(out_path, "wb");
+    if (!f) return fail(CC_ERR_IO, "Cortex graph file '%s' not found: %s", out_path, strerror(errno));
+    bool ok = fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size();
+    if (total) ok = ok && fwrite(recs.data(), 1, total * O, f) == total * O;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(CC_ERR_IO, "Error while writing Cortex graph file '%s': %s", out_path, strerror(errno));
+    if (out_count) *out_count = total;
+    return CC_OK;
+}
+
+// ==================================================================== K3: canonicalise + pack
+int cc_pack_canonical_dev(int device, const uint8_t *dev_seq, uint64_t len, uint32_t k, uint64_t *dev_words, uint8_t *dev_flags,
+                          void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (k == 0) return fail(CC_ERR_ARG, "k must be positive");
+    if (len < k) return CC_OK;
+    if (!dev_seq || !dev_words || !dev_flags) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_pack_windows(dev_seq, len, k, dev_words, dev_flags, 1, len - k + 1, static_cast<cudaStream_t>(stream));
+}
+
+int cc_pack_kmers_dev(int device, const uint8_t *dev_kmers, uint64_t nq, uint32_t k, uint64_t *dev_words, uint8_t *dev_flags,
+                      void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (k == 0) return fail(CC_ERR_ARG, "k must be positive");
+    if (nq == 0) return CC_OK;
+    if (!dev_kmers || !dev_words || !dev_flags) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_pack_windows(dev_kmers, nq * k, k, dev_words, dev_flags, k, nq, static_cast<cudaStream_t>(stream));
+}
+
+int cc_pack_canonical(int device, const uint8_t *seq, uint64_t len, uint32_t k, uint64_t *out_words, uint8_t *out_flags) {
+    if (int rc = check_device(device)) return rc;
+    if (k == 0) return fail(CC_ERR_ARG, "k must be positive");
+    if (len < k) return CC_OK;
+    if (!seq || !out_words || !out_flags) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    const uint64_t nw = len - k + 1, s = (k + 31) / 32;
+    DevBuf dseq, dw, df;
+    if (int rc = dseq.alloc(len + 64)) return rc;
+    if (int rc = dw.alloc(nw * s * 8)) return rc;
+    if (int rc = df.alloc(nw)) return rc;
+    CC_CUDA(cudaMemcpy(dseq.p, seq, len, cudaMemcpyHostToDevice));
+    if (int rc = launch_pack_windows(dseq.as<uint8_t>(), len, k, dw.as<uint64_t>(), df.as<uint8_t>(), 1, nw, nullptr)) return rc;
+    CC_CUDA(cudaMemcpy(out_words, dw.p, nw * s * 8, cudaMemcpyDeviceToHost));
+    CC_CUDA(cudaMemcpy(out_flags, df.p, nw, cudaMemcpyDeviceToHost));
+    return CC_OK;
+}
+
+// ==================================================================== K4: lookups
+int cc_build_index(cc_graph *g, int index_bits) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    DeviceGuard guard(g->device);
+    if (int rc = build_index(g, index_bits)) return rc;
+    if (!g->index.sorted)
+        return fail(CC_ERR_UNSORTED, "Records are not sorted (record %llu sorts before its predecessor)",
+                    (unsigned long long)g->index.unsorted_at);
+    return CC_OK;
+}
+
+int cc_find_ascii_dev(cc_graph *g, const uint8_t *dev_kmers, uint64_t nq, int64_t *dev_index, int algo, void *stream) {
+    if (!g || (nq && (!dev_kmers || !dev_index))) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    return launch_find_seq(g, dev_kmers, nq * g->h.k, g->h.k, nq, dev_index, algo, static_cast<cudaStream_t>(stream));
+}
+
+int cc_find_windows_dev(cc_graph *g, const uint8_t *dev_seq, uint64_t len, int64_t *dev_index, int algo, void *stream) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    if (len < g->h.k) return CC_OK;
+    if (!dev_seq || !dev_index) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    return launch_find_seq(g, dev_seq, len, 1, len - g->h.k + 1, dev_index, algo, static_cast<cudaStream_t>(stream));
+}
+
+int cc_find_packed_dev(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, int64_t *dev_index, int algo,
+                       void *stream) {
+    if (!g || (nq && (!dev_words || !dev_index))) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    return launch_find_packed(g, dev_words, dev_flags, nq, dev_index, algo, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+namespace {
+// Host-buffer lookups: the batch is streamed through the device in chunks on two alternating streams so that
+// (with page-locked caller buffers) the copies of one chunk overlap the search of the other.
+template <class Launch>
+int chunked_lookup(cc_graph *g, const uint8_t *in, uint64_t in_bytes_per_q, uint64_t in_extra_bytes, const uint8_t *flags,
+                   uint64_t nq, int64_t *out_index, Launch launch) {
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    g->stats = cc_stats{};
+    const uint64_t launches0 = g_launches.load();
+    const uint64_t chunk_q = std::max<uint64_t>(1, std::min<uint64_t>(nq, 1ull << 24));
+    cudaStream_t st[2] = {g->stream, nullptr};
+    CC_CUDA(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+    struct Kill { cudaStream_t s; ~Kill() { cudaStreamDestroy(s); } } kill{st[1]};
+    DevBuf din[2], dflag[2], dout[2];
+    const int nb = nq > chunk_q ? 2 : 1;
+    for (int b = 0; b < nb; ++b) {
+        if (int rc = din[b].alloc(chunk_q * in_bytes_per_q + in_extra_bytes + 64)) return rc;
+        if (flags) if (int rc = dflag[b].alloc(chunk_q)) return rc;
+        if (int rc = dout[b].alloc(chunk_q * 8)) return rc;
+    }
+    CC_CUDA(cudaEventRecord(g->ev0, g->stream));
+    CC_CUDA(cudaStreamWaitEvent(st[1], g->ev0, 0));
+    int b = 0;
+    for (uint64_t q0 = 0; q0 < nq; q0 += chunk_q, b ^= (nb - 1)) {
+        const uint64_t m = std::min(chunk_q, nq - q0);
+        const uint64_t nbytes = m * in_bytes_per_q + in_extra_bytes;
+        CC_CUDA(cudaMemcpyAsync(din[b].p, in + q0 * in_bytes_per_q, nbytes, cudaMemcpyHostToDevice, st[b]));
+        if (flags) CC_CUDA(cudaMemcpyAsync(dflag[b].p, flags + q0, m, cudaMemcpyHostToDevice, st[b]));
+        if (int rc = launch(din[b].as<uint8_t>(), flags ? dflag[b].as<uint8_t>() : nullptr, m, dout[b].as<int64_t>(), st[b])) return rc;
+        CC_CUDA(cudaMemcpyAsync(out_index + q0, dout[b].p, m * 8, cudaMemcpyDeviceToHost, st[b]));
+        g->stats.h2d_bytes += nbytes + (flags ? m : 0);
+        g->stats.d2h_bytes += m * 8;
+    }
+    if (nb == 2) {
+        cudaEvent_t done;
+        CC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        cudaEventRecord(done, st[1]);
+        cudaStreamWaitEvent(g->stream, done, 0);
+        cudaEventDestroy(done);
+    }
+    CC_CUDA(cudaEventRecord(g->ev1, g->stream));
+    if (int rc = sync_stream(g, g->stream)) return rc;
+    cudaEventElapsedTime(&g->stats.total_ms, g->ev0, g->ev1);
+    g->stats.launches = (uint32_t)(g_launches.load() - launches0);
+    return CC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int cc_find_ascii(cc_graph *g, const uint8_t *kmers, uint64_t nq, int64_t *out_index, int algo) {
+    if (!g || (nq && (!kmers || !out_index))) return fail(CC_ERR_ARG, "null argument");
+    if (nq == 0) return CC_OK;
+    const uint32_t k = g->h.k;
+    return chunked_lookup(g, kmers, k, 0, nullptr, nq, out_index,
+                          [&](const uint8_t *d, const uint8_t *, uint64_t m, int64_t *o, cudaStream_t st) {
+                              return launch_find_seq(g, d, m * k, k, m, o, algo, st);
+                          });
+}
+
+int cc_find_windows(cc_graph *g, const uint8_t *seq, uint64_t len, int64_t *out_index, int algo) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    const uint32_t k = g->h.k;
+    if (len < k) return CC_OK;
+    if (!seq || !out_index) return fail(CC_ERR_ARG, "null argument");
+    // windows are chunked with k-1 bytes of overlap: chunk of m windows needs m + k - 1 bytes
+    return chunked_lookup(g, seq, 1, k - 1, nullptr, len - k + 1, out_index,
+                          [&](const uint8_t *d, const uint8_t *, uint64_t m, int64_t *o, cudaStream_t st) {
+                              return launch_find_seq(g, d, m + k - 1, 1, m, o, algo, st);
+                          });
+}
+
+int cc_find_packed(cc_graph *g, const uint64_t *words, const uint8_t *flags, uint64_t nq, int64_t *out_index, int algo) {
+    if (!g || (nq && (!words || !out_index))) return fail(CC_ERR_ARG, "null argument");
+    if (nq == 0) return CC_OK;
+    return chunked_lookup(g, reinterpret_cast<const uint8_t *>(words), 8ull * g->h.s, 0, flags, nq, out_index,
+                          [&](const uint8_t *d, const uint8_t *f, uint64_t m, int64_t *o, cudaStream_t st) {
+                              return launch_find_packed(g, reinterpret_cast<const uint64_t *>(d), f, m, o, algo, st);
+                          });
+}
+
+int cc_contains_windows(cc_graph *g, const uint8_t *seq, uint64_t len, uint8_t *out_present) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    const uint32_t k = g->h.k;
+    if (len < k) return CC_OK;
+    if (!seq || !out_present) return fail(CC_ERR_ARG, "null argument");
+    const uint64_t nw = len - k + 1;
+    std::vector<int64_t> idx(nw);
+    if (int rc = cc_find_windows(g, seq, len, idx.data(), CC_ALGO_AUTO)) return rc;
+    for (uint64_t i = 0; i < nw; ++i) out_present[i] = idx[i] >= 0;
+    return CC_OK;
+}
+
+// ==================================================================== multi-GPU helpers
+int cc_bucket_by_owner_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
+                           const uint64_t *dev_splitters, int nshards, uint64_t *dev_counts, uint64_t *dev_sorted_words,
+                           uint32_t *dev_slots, void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (!dev_counts || (nq && (!dev_words || !dev_sorted_words || !dev_slots)) || (nshards > 1 && !dev_splitters))
+        return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_bucket_by_owner(dev_words, dev_flags, nq, s, dev_splitters, nshards, dev_counts, dev_sorted_words, dev_slots,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int cc_scatter_results_dev(int device, const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n, int64_t *dev_out, void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (n && (!dev_values || !dev_slots || !dev_out)) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_scatter_results(dev_values, dev_slots, n, dev_out, static_cast<cudaStream_t>(stream));
+}
+
+// ==================================================================== instrumentation
+int cc_last_stats(const cc_graph *g, cc_stats *out) {
+    if (!g || !out) return fail(CC_ERR_ARG, "null argument");
+    *out = g->stats;
+    return CC_OK;
+}
+
+int cc_device_body(const cc_graph *g, const void **dev_body, uint64_t *bytes) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    if (dev_body) *dev_body = g->dev_body;
+    if (bytes) *bytes = g->h.num_records * g->h.record_size;
+    return CC_OK;
+}
+
+int cc_device_keys(cc_graph *g, const uint64_t **dev_keys, uint64_t *n) {
+    if (!g) return fail(CC_ERR_ARG, "null graph");
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    if (dev_keys) *dev_keys = g->index.keys;
+    if (n) *n = g->h.num_records;
+    return CC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// cc_internal.hpp -- host-side internals of libcorticall_cuda (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/corticall_cuda.h"
+
+namespace cc {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+int fail(int status, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CC_CUDA(expr)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) return ::cc::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint32_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ options (cc_set_option)
+struct Options {
+    int scan_stages = 4;
+    int scan_tile_bytes = 32768;
+    int scan_ctas_per_sm = 2;
+    int index_bits = 0;          // 0 = auto
+    int lookup_block = 256;
+    int host_chunk_mb = 64;      // cc_find_novel_host chunk size
+};
+Options &options();
+
+// ------------------------------------------------------------------ header model (ctx_spec.md tables 1-3)
+struct ColorMeta {
+    std::string sample_name;
+    std::string graph_name;
+    cc_color_info info{};
+};
+struct Header {
+    uint32_t version = 0, k = 0, s = 0, c = 0;
+    uint64_t data_offset = 0, record_size = 0, num_records = 0;
+    std::vector<ColorMeta> colors;
+};
+// Parses a header image; returns cc_status and fills h (num_records computed from total_size).
+int parse_header(const uint8_t *buf, uint64_t avail, uint64_t total_size, const char *path_for_msg, Header &h);
+// FindROIs.makeCortexHeader + CortexGraphWriter.initialize: the 1-colour ROI header.
+std::vector<uint8_t> make_roi_header(uint32_t k, uint32_t s, const std::string &sample_name);
+
+// ------------------------------------------------------------------ device workspace for the scan
+struct ScanWorkspace {
+    uint64_t *tile_state = nullptr;   // look-back descriptors
+    uint64_t tile_state_cap = 0;
+    uint32_t *tile_counter = nullptr; // dynamic tile ticket
+    uint64_t *totals = nullptr;       // [0] in, [1] out (ping-pong for chunked scans)
+    int32_t *parents = nullptr;       // device copy of the parent colour list
+    uint32_t parents_cap = 0;
+    int *dev_error = nullptr;         // watchdog code
+    uint32_t epoch = 0;
+    uint32_t ticket_base = 0;         // tickets drawn so far from tile_counter (host mirror)
+    int ensure(uint64_t ntiles, uint32_t nparents);
+    void release();
+};
+
+// ------------------------------------------------------------------ lookup index
+struct LookupIndex {
+    uint64_t *keys = nullptr;     // [n*s] native words, word 0 first
+    uint32_t *table = nullptr;    // [2^bits + 1] lower bounds
+    int bits = 0;
+    bool built = false;
+    bool sorted = true;
+    uint64_t unsorted_at = 0;
+};
+
+}  // namespace cc
+
+struct cc_graph {
+    int device = 0;
+    cc::Header h;
+    std::string path;
+    // host image (mmap or caller copy) -- only for cc_get_records and the upload
+    const uint8_t *host_image = nullptr;
+    uint64_t host_size = 0;
+    void *map_base = nullptr;
+    uint64_t map_len = 0;
+    std::vector<uint8_t> owned_image;
+    // device body
+    const uint8_t *dev_body = nullptr;   // record 0
+    void *dev_alloc = nullptr;           // owned allocation (null when wrapping a caller buffer)
+    uint64_t first_index = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cc::ScanWorkspace scan_ws;
+    cc::LookupIndex index;
+    cc_stats stats{};
+    int sm_count = 148;
+    // staging for the host-output novelty scan (grown on demand, kept across calls)
+    void *novel_buf = nullptr;
+    void *novel_idx = nullptr;
+    uint64_t novel_cap = 0;
+    std::vector<int32_t> parents_cached;   // what scan_ws.parents currently holds
+};
+
+namespace cc {
+
+// ------------------------------------------------------------------ kernel launchers (defined in the .cu files)
+struct ScanArgs {
+    const uint8_t *body;   // device, record 0 of this launch
+    uint64_t n;            // records in this launch
+    uint64_t index_base;   // global index of record 0 (for out_index)
+    uint32_t k, s, c;
+    int32_t child;
+    int nparents;          // device list in ws.parents
+    uint8_t *out_records;  // device
+    uint64_t *out_index;   // device or null
+    uint64_t cap;
+    const uint64_t *total_in;   // device or null (=0)
+    uint64_t *total_out;        // device
+};
+int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaStream_t st);
+// Number of tiles launch_scan_novel / launch_decode_columns will cut n records into (current options).
+uint64_t scan_tiles_for(uint64_t n, uint32_t s, uint32_t c);
+int launch_decode_columns(const uint8_t *dev_body, uint64_t n, uint32_t s, uint32_t c,
+                          uint64_t *dev_words, int32_t *dev_cov, uint8_t *dev_edges, ScanWorkspace &ws, int sm_count,
+                          cudaStream_t st);
+
+int build_index(cc_graph *g, int bits);
+int launch_pack_windows(const uint8_t *dev_seq, uint64_t len, uint32_t k, uint64_t *dev_words, uint8_t *dev_flags,
+                        uint64_t row_stride /*1 for sliding windows, k for independent rows*/, uint64_t nq, cudaStream_t st);
+int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, int64_t *dev_index,
+                       int algo, cudaStream_t st);
+int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t len, uint64_t row_stride, uint64_t nq, int64_t *dev_index,
+                    int algo, cudaStream_t st);
+int launch_bucket_by_owner(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
+                           const uint64_t *dev_splitters, int nshards, uint64_t *dev_counts, uint64_t *dev_sorted_words,
+                           uint32_t *dev_slots, cudaStream_t st);
+int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n, int64_t *dev_out, cudaStream_t st);
+
+}  // namespace cc

@@ -1,0 +1,202 @@
+/*
+ * corticall_cuda.h -- C ABI of libcorticall_cuda, the B200 (sm_100a) implementation of Corticall's
+ * data-parallel k-mer hot path.  This is the drop-in boundary: a JNI shim (csrc/jni_shim.cpp, see
+ * INTEGRATION.md) binds exactly these entry points behind the reference's Java classes.
+ *
+ * Reference interfaces replaced (S/ = public/java/src/uk/ac/ox/well/cortexjdk/ in mcveanlab/Corticall):
+ *   S/utils/io/graph/DeBruijnGraph.java:16-53           the graph interface CortexGraph implements
+ *   S/utils/io/graph/cortex/CortexGraph.java:40-48      constructors              -> cc_open / cc_open_memory
+ *   S/utils/io/graph/cortex/CortexGraph.java:66-168     loadCortexGraph (header)  -> cc_header / cc_color_*
+ *   S/utils/io/graph/cortex/CortexGraph.java:183-237    getRecord / getNextRecord -> cc_get_records / cc_decode_records
+ *   S/utils/io/graph/cortex/CortexGraph.java:272-321    findRecord (all overloads)-> cc_find_ascii / cc_find_windows / cc_find_packed
+ *   S/utils/io/graph/cortex/CortexGraph.java:335-366    getColorForSampleName(s)  -> cc_color_for_sample_name
+ *   S/commands/discover/roi/FindROIs.java:31-105        the novel-k-mer step      -> cc_find_novel / cc_write_roi_file
+ *   S/utils/io/graph/cortex/CortexGraphWriter.java:31-138  output layout of that step
+ *   S/utils/sequence/SequenceUtils.java:206-225, S/utils/io/graph/cortex/CortexRecord.java:313-334,
+ *   S/utils/kmer/CanonicalKmer.java:13-37, S/utils/kmer/CortexBinaryKmer.java:15-17
+ *                                                        canonicalise + 2-bit pack -> cc_pack_canonical
+ *   S/commands/discover/call/Call.java:2348-2381,2425-2451  loadRois / loadChildWalk / getRegions
+ *                                                        -> cc_find_windows (child walk), cc_contains_windows (ROI membership)
+ *
+ * Conventions
+ *   - every function returns a cc_status (0 = OK); cc_last_error() gives a thread-local message that
+ *     carries the text of the CortexJDKException the reference would throw;
+ *   - plain pointers and sizes only; all buffers are caller-owned; "_dev" variants take DEVICE pointers
+ *     and a cudaStream_t (as void*) and are asynchronous on that stream; the others take HOST pointers
+ *     and are synchronous (host<->device copies are inside the call);
+ *   - k-mer words: `s = ceil(k/32)` uint64 per k-mer, NATIVE byte order, word 0 most significant, bases
+ *     right-aligned, A=0 C=1 G=2 T=3 -- i.e. exactly the on-disk words read little-endian.  The Java
+ *     long[] of CortexRecord is Long.reverseBytes() of each word (CortexGraph.java:208-209);
+ *   - coverage is returned as int32 (Java int: values >= 2^31 wrap negative, BinaryUtils.java:6-17);
+ *   - record index results are int64, -1 = the reference's `null`;
+ *   - one caller thread per cc_graph; there is NO CPU fallback: without a CUDA device every compute
+ *     entry point fails with CC_ERR_CUDA.
+ */
+#ifndef CORTICALL_CUDA_H
+#define CORTICALL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CC_API __attribute__((visibility("default")))
+#else
+#define CC_API
+#endif
+
+typedef enum {
+    CC_OK = 0,
+    CC_ERR_NOT_CORTEX = 1,   /* CortexGraph.java:74-76   "does not appear to be a Cortex graph"      */
+    CC_ERR_BAD_VERSION = 2,  /* CortexGraph.java:82-84   "is not a version 6 Cortex graph"           */
+    CC_ERR_BAD_TRAILER = 3,  /* CortexGraph.java:140-142 "didn't see a proper header terminator"     */
+    CC_ERR_IO = 4,           /* CortexGraph.java:163-167 file not found / parse error                */
+    CC_ERR_UNSORTED = 5,     /* CortexGraph.java:295-301 "Records are not sorted"                    */
+    CC_ERR_RANGE = 6,        /* CortexGraph.java:173-175 record index out of range                   */
+    CC_ERR_CUDA = 7,         /* no device / CUDA runtime failure                                     */
+    CC_ERR_NCCL = 8,         /* reserved for the multi-GPU exchange                                  */
+    CC_ERR_ARG = 9,          /* bad argument (colour out of range = Java ArrayIndexOutOfBounds)      */
+    CC_ERR_UNSUPPORTED = 10  /* shape outside what the kernels cover                 */
+} cc_status;
+
+typedef struct cc_graph cc_graph;   /* opaque: host mapping, device buffers, index, stream */
+
+/* Per-colour header block (ctx_spec.md tables 1-3; CortexColor.java). */
+typedef struct {
+    uint32_t mean_read_length;
+    uint64_t total_sequence;             /* little-endian per the spec (the Java reader mis-parses it) */
+    uint8_t  tip_clipping, low_covg_supernodes_removed, low_covg_kmers_removed, cleaned_against_graph;
+    uint32_t low_cov_supernodes_threshold, low_cov_kmer_threshold;
+} cc_color_info;
+
+/* Scan / lookup statistics of the last call on a handle (device time from CUDA events). */
+typedef struct {
+    float    kernel_ms;        /* device time of the kernels of the last call                 */
+    float    total_ms;         /* device time of the whole call incl. copies (host variants)  */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t launches;         /* kernels launched by the last call                           */
+} cc_stats;
+
+/* ---------------------------------------------------------------- library */
+CC_API const char *cc_last_error(void);                 /* thread-local, never NULL */
+CC_API const char *cc_version(void);
+CC_API int cc_device_count(int *out);                   /* CC_ERR_CUDA when no driver / device */
+
+/* ---------------------------------------------------------------- lifecycle (CortexGraph ctors, :40-48,:66-168) */
+/* Parse header, map the file, upload the record body to `device`. */
+CC_API int cc_open(const char *path, int device, cc_graph **out);
+/* Same from an in-memory image of a whole .ctx file (header + body). */
+CC_API int cc_open_memory(const void *file_image, uint64_t size, int device, cc_graph **out);
+/* Wrap a DEVICE-resident record array (on-disk record layout, n records of 8s+5c bytes, caller keeps it
+ * alive; must lie in an allocation readable up to the next 16-byte boundary).  Used for shards of a
+ * k-mer-range-partitioned graph and by the benchmark.  `first_index` is added to every record index the
+ * handle reports (the shard's offset in the global array). */
+CC_API int cc_open_device(const void *dev_body, uint32_t k, uint32_t s, uint32_t c, uint64_t n,
+                          uint64_t first_index, int device, cc_graph **out);
+/* Frees device memory and the mapping.  NOT CortexGraph.close(): the Java close() only closes the
+ * RandomAccessFile and the graph stays usable (CortexGraph.java:253-255,264-270). */
+CC_API void cc_dispose(cc_graph *g);
+
+/* ---------------------------------------------------------------- header / colours */
+CC_API int cc_header(const cc_graph *g, uint32_t *version, uint32_t *kmer_size, uint32_t *kmer_bits,
+                     uint32_t *num_colors, uint64_t *num_records, uint64_t *data_offset, uint64_t *record_size);
+CC_API int cc_color_name(const cc_graph *g, uint32_t color, char *buf, size_t cap);          /* getSampleName */
+CC_API int cc_color_graph_name(const cc_graph *g, uint32_t color, char *buf, size_t cap);    /* getCleanedAgainstGraphName */
+CC_API int cc_color_info_get(const cc_graph *g, uint32_t color, cc_color_info *out);
+/* CortexGraph.getColorForSampleName :335-354: case-insensitive name, else integer literal; -1 unless exactly one. */
+CC_API int cc_color_for_sample_name(const cc_graph *g, const char *name, int32_t *out_color);
+
+/* ---------------------------------------------------------------- K1: record access / streaming decode */
+/* Raw on-disk bytes of records [first, first+count) -> count*S bytes (getRecord(i) for the Java side). */
+CC_API int cc_get_records(const cc_graph *g, uint64_t first, uint64_t count, void *out_raw);
+/* Device decode of records [first, first+count) into columns (any of the outputs may be NULL):
+ * words[count*s] (native), coverage[count*c] (int32), edges[count*c]. */
+CC_API int cc_decode_records(cc_graph *g, uint64_t first, uint64_t count,
+                             uint64_t *out_words, int32_t *out_coverage, uint8_t *out_edges);
+CC_API int cc_decode_records_dev(cc_graph *g, uint64_t first, uint64_t count,
+                                 uint64_t *dev_words, int32_t *dev_coverage, uint8_t *dev_edges, void *stream);
+
+/* ---------------------------------------------------------------- K1+K2: the novel-k-mer step (FindROIs) */
+/* FindROIs.isNovel :72-82 over every record, in file order: coverage[child] > 0 (signed) and
+ * coverage[p] == 0 for every listed parent.  Output records have the 1-colour layout
+ * CortexGraphWriter.addRecord :106-138 emits: s words verbatim, child coverage u32 LE, child edge byte
+ * (8s+5 bytes each).  *out_count receives the TOTAL number of novel records even when it exceeds cap
+ * (only the first cap are stored).  out_index (optional) receives each one's input record index. */
+CC_API int cc_find_novel(cc_graph *g, int32_t child, const int32_t *parents, int nparents,
+                         void *out_records, uint64_t *out_index, uint64_t cap, uint64_t *out_count);
+CC_API int cc_find_novel_dev(cc_graph *g, int32_t child, const int32_t *parents, int nparents,
+                             void *dev_out_records, uint64_t *dev_out_index, uint64_t cap,
+                             uint64_t *dev_out_count, void *stream);
+/* Same scan over a HOST-resident record array streamed through the device in chunks (copies overlap the
+ * kernel); nothing stays resident.  This is the end-to-end form of FindROIs for a graph that lives on
+ * disk / in page cache.  host_body should be page-locked for full PCIe speed. */
+CC_API int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s, uint32_t c, uint64_t n,
+                              int32_t child, const int32_t *parents, int nparents,
+                              void *out_records, uint64_t *out_index, uint64_t cap, uint64_t *out_count,
+                              cc_stats *stats);
+/* FindROIs.execute :31-70 end to end: scan + write `out_path` (header of FindROIs.makeCortexHeader :85-105). */
+CC_API int cc_write_roi_file(cc_graph *g, int32_t child, const int32_t *parents, int nparents,
+                             const char *out_path, uint64_t *out_count);
+
+/* ---------------------------------------------------------------- K3: canonicalise + 2-bit pack */
+/* Every k-window of seq (nw = len-k+1, 0 if len<k): canonical orientation by the reference's ASCII rule
+ * (SequenceUtils.java:206-225), packed like CortexRecord.encodeBinaryKmer :313-334.
+ * flags[i]: bit0 = reverse complement chosen, bit1 = window holds a byte outside ACGTacgt (Java throws;
+ * words are 0), bit2 = window holds lowercase (packs, but can never equal a record under findRecord). */
+CC_API int cc_pack_canonical(int device, const uint8_t *seq, uint64_t len, uint32_t k,
+                             uint64_t *out_words, uint8_t *out_flags);
+CC_API int cc_pack_canonical_dev(int device, const uint8_t *dev_seq, uint64_t len, uint32_t k,
+                                 uint64_t *dev_words, uint8_t *dev_flags, void *stream);
+/* nq independent k-byte k-mers, row-major (no shared windows). */
+CC_API int cc_pack_kmers_dev(int device, const uint8_t *dev_kmers, uint64_t nq, uint32_t k,
+                             uint64_t *dev_words, uint8_t *dev_flags, void *stream);
+
+/* ---------------------------------------------------------------- K4: batched lookups (findRecord) */
+/* algo: 0 = auto (prefix-bucketed search), 1 = plain binary search over the key column,
+ *       2 = sorted-merge (radix-sort the batch, one monotone pass over the key column). */
+enum { CC_ALGO_AUTO = 0, CC_ALGO_BSEARCH = 1, CC_ALGO_MERGE = 2 };
+/* Build (or rebuild) the lookup index: key column + prefix table; validates ascending order
+ * (CC_ERR_UNSORTED).  Called lazily by the first lookup.  index_bits = 0 picks a default. */
+CC_API int cc_build_index(cc_graph *g, int index_bits);
+/* nq k-byte ASCII queries, row-major: canonicalise, search; out_index[i] = record index or -1. */
+CC_API int cc_find_ascii(cc_graph *g, const uint8_t *kmers, uint64_t nq, int64_t *out_index, int algo);
+CC_API int cc_find_ascii_dev(cc_graph *g, const uint8_t *dev_kmers, uint64_t nq, int64_t *dev_index, int algo, void *stream);
+/* Every k-window of seq (Call.loadChildWalk :2358-2381): out_index[i] for window i. */
+CC_API int cc_find_windows(cc_graph *g, const uint8_t *seq, uint64_t len, int64_t *out_index, int algo);
+CC_API int cc_find_windows_dev(cc_graph *g, const uint8_t *dev_seq, uint64_t len, int64_t *dev_index, int algo, void *stream);
+/* Canonical packed queries (nq*s native words).  flags (optional, from cc_pack_canonical): queries with
+ * bit1 or bit2 set miss. */
+CC_API int cc_find_packed(cc_graph *g, const uint64_t *words, const uint8_t *flags, uint64_t nq, int64_t *out_index, int algo);
+CC_API int cc_find_packed_dev(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq,
+                              int64_t *dev_index, int algo, void *stream);
+/* ROI membership (`rois.contains(new CanonicalKmer(window))`, Call.java:191-197,2425-2451): 1/0 per window. */
+CC_API int cc_contains_windows(cc_graph *g, const uint8_t *seq, uint64_t len, uint8_t *out_present);
+
+/* ---------------------------------------------------------------- multi-GPU helpers (k-mer-range shards) */
+/* Owner shard of each canonical packed query given nshards-1 splitter keys (first key of shards 1..):
+ * counts per owner, and queries/slots grouped by owner (stable).  Used before the all-to-all. */
+CC_API int cc_bucket_by_owner_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
+                                  const uint64_t *dev_splitters, int nshards,
+                                  uint64_t *dev_counts /* nshards */, uint64_t *dev_sorted_words, uint32_t *dev_slots,
+                                  void *stream);
+/* dev_out[slots[i]] = values[i] (the return leg after the reverse all-to-all). */
+CC_API int cc_scatter_results_dev(int device, const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n,
+                                  int64_t *dev_out, void *stream);
+
+/* ---------------------------------------------------------------- instrumentation */
+CC_API int cc_last_stats(const cc_graph *g, cc_stats *out);
+/* Total kernels this library has launched in this process (bench.py's gpu_launches). */
+CC_API uint64_t cc_launch_count(void);
+/* Device pointer / size of the resident body and key column (benchmarks, tests). */
+CC_API int cc_device_body(const cc_graph *g, const void **dev_body, uint64_t *bytes);
+CC_API int cc_device_keys(cc_graph *g, const uint64_t **dev_keys, uint64_t *n);
+/* Tuning knobs: "scan_stages", "scan_tile_bytes", "scan_ctas_per_sm", "index_bits", "lookup_block". */
+CC_API int cc_set_option(const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,329 @@
+"""Parity of the CUDA path (through the C ABI of libcorticall_cuda) against the CPU oracle and the reference's
+golden vectors.  Mirrors T/utils/kmer/CortexGraphTest.java (recordsAreCorrect, numRecordsTest, testGetRecord,
+testSortedFindRecord, testFindNonExistentRecord) on the device-backed CortexGraph, then widens to the shapes
+BASELINE.json names.  Integer / byte work: every comparison is bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import corticall_b200 as cb                      # noqa: E402
+from corticall_b200 import _native as N          # noqa: E402
+from oracle import orc                           # noqa: E402  (the checker)
+from tools import synth                          # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def graph(fixture_ctx):
+    g = cb.CortexGraph(fixture_ctx)
+    yield g
+    g.dispose()
+
+
+def t2words(body_words):
+    return [w for w in body_words]
+
+
+# ------------------------------------------------------------------ the reference's own tests, on the GPU graph
+
+def test_header(graph):
+    assert (graph.getVersion(), graph.getKmerSize(), graph.getKmerBits(), graph.getNumColors()) == (6, 31, 1, 2)
+    assert graph.getNumRecords() == 66                                   # numRecordsTest :147-152
+    assert graph.getColor(0).getSampleName() == "one" and graph.getColor(1).getSampleName() == "two"   # :139-145
+    assert graph.getColorForSampleName("ONE") == 0 and graph.getColorForSampleName("1") == 1
+    assert graph.getColorForSampleName("nope") == -1
+    assert graph.getColorsForSampleNames(["two", "one", "x"]) == [1, 0, -1]
+    assert graph.getColor(0).getMeanReadLength() == 63 and graph.getColor(0).getCleanedAgainstGraphName() == "undefined"
+
+
+def test_records_are_correct(graph, kats):                               # recordsAreCorrect :186-198
+    n = 0
+    for cr, row in zip(graph, kats["fixture_records"]):
+        assert cr.getKmerAsString() == row["kmer"]
+        assert cr.getCoverages() == row["coverage"]
+        assert cr.getEdgeAsStrings() == row["edges"]
+        assert cr.toString() == "%s %d %d %s %s" % (row["kmer"], *row["coverage"], *row["edges"])
+        n += 1
+    assert n == 66
+    assert sum(1 for _ in graph) == 66                                   # re-iteration works (TraversalEngineTest :35-45)
+
+
+def test_get_record_backwards(graph, kats):                              # testGetRecord :255-265
+    for i in range(10, -1, -1):
+        assert graph.getRecord(i).getKmerAsString() == kats["fixture_records"][i]["kmer"]
+    assert graph.getRecord(66) is None
+    with pytest.raises(cb.CortexJDKException):
+        graph.getRecord(-1)
+
+
+def test_encode_binary_kmer(graph):                                      # testEncodeBinaryKmer :267-280
+    for i in range(10, -1, -1):
+        cr = graph.getRecord(i)
+        assert cb.CortexRecord.encodeBinaryKmer(cr.getKmerAsBytes()) == cr.getBinaryKmer()
+        assert cb.CortexRecord.decodeBinaryKmer(cr.getBinaryKmer(), 31, 1) == cr.getKmerAsBytes()
+
+
+def test_sorted_find_record(graph, kats):                                # testSortedFindRecord :310-320
+    for row in kats["fixture_records"]:
+        cr = graph.findRecord(row["kmer"])
+        assert cr is not None and cr.getKmerAsString() == row["kmer"] and cr.getCoverages() == row["coverage"]
+        rc = cb.SequenceUtils.reverseComplement(row["kmer"])
+        assert graph.findRecord(rc) == cr
+        assert graph.findRecord(cb.CanonicalKmer(rc)) == cr and graph.findRecord(cb.CortexByteKmer(row["kmer"])) == cr
+
+
+def test_find_non_existent_record(graph, kats):                          # testFindNonExistentRecord :322-331
+    assert graph.findRecord(kats["missing_query"]) is None
+    assert graph.findRecord(kats["fixture_records"][5]["kmer"].lower()) is None
+    assert graph.findRecord("A" * 30) is None
+
+
+def test_all_fasta_windows_hit(graph, fixture_ctx, fixture_fa):          # BASELINE.json configs[0]
+    og = orc.Graph(fixture_ctx)
+    seen = set()
+    for seq in fixture_fa:
+        for algo in (cb.CC_ALGO_AUTO, cb.CC_ALGO_BSEARCH, cb.CC_ALGO_MERGE):
+            idx = graph.findWindows(seq, algo)
+            assert idx.tolist() == og.find_windows(seq).tolist() and (idx >= 0).all()
+        seen.update(idx.tolist())
+        assert graph.containsWindows(seq).all()
+    assert seen == set(range(66))
+
+
+def test_novelty_fixture(graph, fixture_ctx, tmp_path):
+    og = orc.Graph(fixture_ctx)
+    for child, parents, n in ((0, [1], 19), (1, [0], 47), (0, [], 19), (0, [0], 0), (0, [1, 1], 19)):
+        cnt, recs, idx = graph.findNovel(child, parents)
+        want, widx = og.find_rois(child, parents)
+        assert cnt == n and recs.tobytes() == want and idx.tolist() == widx.tolist()
+    # FindROIs.execute end to end: the file on disk is header + records, and reads back as a sorted 1-colour graph
+    out = tmp_path / "rois.ctx"
+    assert graph.writeRois(0, [1], out) == 19
+    want, _ = og.find_rois(0, [1])
+    assert out.read_bytes() == orc.roi_header(31, 1, "one") + want
+    roi = cb.CortexGraph(out)
+    assert roi.getNumColors() == 1 and roi.getNumRecords() == 19 and roi.getSampleName(0) == "one"
+    ks = [cr.getKmerAsString() for cr in roi]
+    assert ks == sorted(ks)
+    assert roi.findRecord(ks[7]).getKmerAsString() == ks[7]
+    roi.dispose()
+    with pytest.raises(cb.CortexJDKException):
+        graph.findNovel(2, [0])                                          # colour out of range (Java: ArrayIndexOutOfBounds)
+    with pytest.raises(cb.CortexJDKException):
+        graph.findNovel(0, [-1])
+
+
+# ------------------------------------------------------------------ synthetic graphs of the named shapes vs the oracle
+
+SHAPES = [  # k, c, n
+    (31, 4, 20000),      # config #4's record shape (28 B, 4-byte aligned)
+    (47, 4, 50000),      # config #2/#3 (36 B)
+    (63, 21, 6000),      # config #5 (121 B, odd)
+    (31, 1, 5000),       # 13 B
+    (5, 3, 300),
+    (95, 2, 3000),       # 3 words
+    (127, 5, 2000),      # 4 words
+    (33, 7, 4097),
+    (47, 4, 31), (47, 4, 32), (47, 4, 33), (47, 4, 3), (31, 2, 1),
+]
+
+
+@pytest.mark.parametrize("k,c,n", SHAPES)
+def test_scan_and_lookup_vs_oracle(k, c, n):
+    ctx = synth.make_ctx_file(4321 + k + n, n, k, c, novel_permille=15, adv_period=97, trailing=b"\x01\x02\x03")
+    g = cb.CortexGraph(ctx)
+    og = orc.Graph(ctx)
+    assert g.getNumRecords() == n == og.h.num_records
+    # K1 decode: all columns
+    words, cov, edges = g.decodeRecords(0, n)
+    raw = g.getRawRecords(0, n)
+    s = g.getKmerBits()
+    assert (raw[:, :8 * s].copy().view("<u8") == words).all()
+    assert (raw[:, 8 * s:8 * s + 4 * c].copy().view("<i4") == cov).all()
+    assert (raw[:, 8 * s + 4 * c:] == edges).all()
+    for i in sorted({0, n // 3, n - 1}):
+        bk, ocov, oed = og.get_record(i)
+        assert words[i].byteswap().view(np.int64).tolist() == bk.tolist() and cov[i].tolist() == ocov.tolist()
+    if n > 40:
+        w2, c2, e2 = g.decodeRecords(7, 33)                              # unaligned sub-range
+        assert (w2 == words[7:40]).all() and (c2 == cov[7:40]).all() and (e2 == edges[7:40]).all()
+    # K1+K2: several colour choices
+    choices = [(0, list(range(1, c))), (0, []), (c - 1, [0]), (0, [c - 1, c - 1])]
+    for child, parents in choices:
+        cnt, recs, idx = g.findNovel(child, parents)
+        want, widx = og.find_rois(child, parents)
+        assert cnt == len(widx) and recs.tobytes() == want and idx.tolist() == widx.tolist(), (child, parents)
+    # capped output: count is still the total, only `cap` stored
+    cnt, recs, idx = g.findNovel(0, [], cap=5)
+    want, widx = og.find_rois(0, [])
+    assert cnt == len(widx) and recs.tobytes() == want[:min(5, cnt) * (8 * s + 5)]
+    # K3+K4 lookups (hits on both strands, misses, N, lower case), all three algorithms
+    tw = [torch.from_numpy(words[:, w].copy().view(np.int64)) for w in range(s)]
+    q_ascii, canon, valid = synth.make_queries(99, tw, k, 4000, corrupt_permille=30)
+    qa = q_ascii.numpy()
+    if n >= 3:
+        want_idx = og.find_batch(qa)
+    else:
+        # N <= 2: the reference's search loop never runs and only its LRU answers; the GPU path
+        # returns the exact match.  Compare with the oracle's answer once every record is cached (after iteration).
+        for i in range(n):
+            og.get_record(i)
+        want_idx = og.find_batch(qa)
+    for algo in (cb.CC_ALGO_AUTO, cb.CC_ALGO_BSEARCH, cb.CC_ALGO_MERGE):
+        got = g.findRecordIndices(qa, algo)
+        assert got.tolist() == want_idx.tolist(), algo
+    assert (want_idx[~valid.numpy()] == -1).all()
+    # packed queries
+    pw = np.stack([cw.numpy().view(np.uint64) for cw in canon], axis=1)
+    flags = np.where(valid.numpy(), 0, 2).astype(np.uint8)
+    got = g.findPacked(pw, flags)
+    assert got.tolist() == want_idx.tolist()
+    g.dispose()
+
+
+@pytest.mark.parametrize("k", [5, 21, 31, 32, 33, 47, 63, 64, 65, 95, 128])
+def test_pack_canonical_vs_oracle(k):
+    seq = synth.random_genome(11 + k, 20000, n_permille=2).numpy().copy()
+    seq[300:420] += 32                                                   # a lower-case run
+    seq[5000] = ord(".")
+    seq[7000:7003] = [ord("n"), 200, 0]
+    for ln in (len(seq), 9001, k, k + 1, k - 1):
+        sub = seq[:ln]
+        w, f = cb.packCanonical(sub, k)
+        ow, of = orc.pack_windows(sub, k)
+        assert w.shape == ow.shape and (w == ow).all() and (f == of).all()
+    # unaligned start of the sequence buffer
+    w, f = cb.packCanonical(seq[3:4000], k)
+    ow, of = orc.pack_windows(seq[3:4000], k)
+    assert (w == ow).all() and (f == of).all()
+
+
+def test_lowest_orientation_property_gpu():
+    """SequenceUtilsTest :59-72 on the GPU packer: canonical == min(fw, rc) for random k in {21,31,41,51}."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for k in (21, 31, 41, 51):
+        seq = synth.random_genome(k, 10000 + k - 1).numpy()
+        w, f = cb.packCanonical(seq, k)
+        sb = seq.tobytes()
+        for i in range(0, 10000, 97):
+            fw = sb[i:i + k]
+            rc = fw.translate(comp)[::-1]
+            exp = min(fw, rc)
+            assert cb.CortexRecord.decodeBinaryKmer([int(x) for x in w[i].byteswap().view(np.int64)], k, (k + 31) // 32) == exp
+            assert bool(f[i] & 1) == (exp != fw)
+
+
+@pytest.mark.parametrize("mis", [0, 1, 4, 7, 8, 13, 15])
+@pytest.mark.parametrize("k,c", [(47, 4), (63, 21), (31, 1)])
+def test_misaligned_device_body(mis, k, c):
+    """A device body at any byte offset (a shard cut out of a larger buffer): tiles are fetched as aligned supersets."""
+    n = 30011
+    body, words = synth.make_graph_body(77 + mis, n, k, c, novel_permille=30, adv_period=101)
+    S = body.shape[1]
+    buf = torch.zeros(n * S + 64, dtype=torch.uint8, device="cuda")
+    buf[16 + mis:16 + mis + n * S] = body.reshape(-1).cuda()
+    g = cb.CortexGraph.fromDevice(buf.data_ptr() + 16 + mis, k, c, n, firstIndex=1000, keepalive=buf)
+    cnt, recs, idx = g.findNovel(0, list(range(1, c)))
+    wcnt, wrecs, widx = orc.find_rois_body(body.numpy().reshape(-1), n, k, (k + 31) // 32, c, 0, list(range(1, c)))
+    assert cnt == wcnt and recs.tobytes() == wrecs.tobytes() and (idx == widx + 1000).all()
+    w, cv, e = g.decodeRecords(0, n)
+    assert (w == np.stack([x.numpy().view(np.uint64) for x in words], axis=1)).all()
+    # lookups report indices rebased by firstIndex
+    q = synth.words_to_ascii([x[:50] for x in words], k).numpy()
+    assert g.findRecordIndices(q).tolist() == list(range(1000, 1050))
+    g.dispose()
+
+
+def test_host_streamed_scan():
+    """cc_find_novel_host: the record array stays on the host and is streamed through the device in chunks."""
+    k, c, n = 47, 4, 300_000
+    body, _ = synth.make_graph_body(5, n, k, c, novel_permille=8, adv_period=1009)
+    flat = body.numpy().reshape(-1)
+    N.set_option("host_chunk_mb", 1)                                     # many chunks -> exercises the carry between launches
+    try:
+        par = np.array([1, 2, 3], dtype=np.int32)
+        out = np.empty((n, 21), dtype=np.uint8); idx = np.empty(n, dtype=np.uint64)
+        cnt = C.c_uint64(); st = N.Stats()
+        N.check(N.lib().cc_find_novel_host(0, flat.ctypes.data, k, 2, c, n, 0, par.ctypes.data, 3, out.ctypes.data,
+                                           idx.ctypes.data, n, C.byref(cnt), C.byref(st)))
+    finally:
+        N.set_option("host_chunk_mb", 64)
+    wcnt, wrecs, widx = orc.find_rois_body(flat, n, k, 2, c, 0, [1, 2, 3])
+    assert cnt.value == wcnt and out[:wcnt].tobytes() == wrecs.tobytes() and (idx[:wcnt] == widx).all()
+    assert st.h2d_bytes == n * 36 and st.launches >= 10
+
+
+def test_unsorted_graph_is_rejected():
+    ctx = bytearray(synth.make_ctx_file(3, 900, 15, 1, adv_period=0))
+    g0 = orc.Graph(bytes(ctx))
+    S, off = g0.h.record_size, g0.h.data_offset
+    a, b = bytes(ctx[off + 10 * S:off + 11 * S]), bytes(ctx[off + 500 * S:off + 501 * S])
+    ctx[off + 10 * S:off + 11 * S], ctx[off + 500 * S:off + 501 * S] = b, a
+    g = cb.CortexGraph(bytes(ctx))
+    with pytest.raises(cb.CortexJDKException) as ei:                     # CortexGraph.java:295-301
+        g.findRecord("ACGTACGTACGTACG")
+    assert ei.value.status == N.CC_ERR_UNSORTED and "not sorted" in str(ei.value)
+    # the scan does not need sorted input (FindROIs just iterates)
+    cnt, _, _ = g.findNovel(0, [])
+    assert cnt == orc.Graph(bytes(ctx)).find_rois(0, [])[1].size
+    g.dispose()
+
+
+def test_empty_graph():
+    ctx = synth.header_bytes(31, 3)
+    g = cb.CortexGraph(ctx)
+    assert g.getNumRecords() == 0 and list(g) == []
+    cnt, recs, idx = g.findNovel(0, [1, 2])
+    assert cnt == 0 and len(recs) == 0
+    assert g.findRecord("A" * 31) is None
+    assert g.findWindows("ACGT" * 20).tolist() == [-1] * 50
+    g.dispose()
+
+
+def test_dense_novel_output():
+    """Every record novel (the staging buffer must grow and the ordered write-out must hold at 100 % density)."""
+    k, c, n = 31, 2, 150_000
+    body, _ = synth.make_graph_body(9, n, k, c, adv_period=0)
+    body[:, 8 + 4:8 + 8] = 0                                             # parent coverage := 0
+    body[:, 8] |= 1                                                      # child coverage > 0
+    ctx = synth.header_bytes(k, c) + body.numpy().tobytes()
+    g = cb.CortexGraph(ctx)
+    cnt, recs, idx = g.findNovel(0, [1])
+    want, widx = orc.Graph(ctx).find_rois(0, [1])
+    assert cnt == n and recs.tobytes() == want and idx.tolist() == widx.tolist()
+    g.dispose()
+
+
+def test_full_size_config2_scan():
+    """BASELINE.json configs[1] at full size (2.5e7 records, k=47, 4 colours, 0.9 GB), generated on the device:
+    bit-exact against the oracle run over the same bytes, plus size-independent properties."""
+    k, c, n = 47, 4, 25_000_000
+    body, words = synth.make_graph_body(20261018, n, k, c, device="cuda")
+    g = cb.CortexGraph.fromDevice(body.data_ptr(), k, c, n, keepalive=body)
+    cnt, recs, idx = g.findNovel(0, [1, 2, 3])
+    # properties: sorted unique indices; every emitted record equals the source record's projection
+    assert (np.diff(idx.astype(np.int64)) > 0).all()
+    host = body.cpu().numpy()
+    assert (recs[:, :16] == host[idx.astype(np.int64), :16]).all()
+    assert (recs[:, 16:20] == host[idx.astype(np.int64), 16:20]).all() and (recs[:, 20] == host[idx.astype(np.int64), 32]).all()
+    # independent predicate evaluated with torch on the device
+    cov = body[:, 16:32].contiguous().view(torch.int32)
+    mask = (cov[:, 0] > 0) & (cov[:, 1] == 0) & (cov[:, 2] == 0) & (cov[:, 3] == 0)
+    assert int(mask.sum()) == cnt and torch.equal(torch.nonzero(mask).flatten().cpu(), torch.from_numpy(idx.astype(np.int64)))
+    # the oracle over the full array
+    wcnt, wrecs, widx = orc.find_rois_body(host.reshape(-1), n, k, 2, c, 0, [1, 2, 3], cap=cnt + 10)
+    assert wcnt == cnt and wrecs.tobytes() == recs.tobytes() and (widx == idx).all()
+    # idempotence: scanning the ROI set again with no parents returns it unchanged
+    roi_ctx = orc.roi_header(k, 2, "child") + recs.tobytes()
+    rg = cb.CortexGraph(roi_ctx)
+    c2, r2, _ = rg.findNovel(0, [])
+    assert c2 == cnt and r2.tobytes() == recs.tobytes()
+    # and every ROI k-mer is found in the big graph at its recorded index
+    got = g.findPacked(recs[:, :16].copy().view("<u8"))
+    assert (got == idx.astype(np.int64)).all()
+    rg.dispose(); g.dispose()
