@@ -333,6 +333,9 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
     else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
     else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;
+    else if (!strcmp(name, "scan_debug")) o.scan_debug = (int)value;
+    else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;
+    else if (!strcmp(name, "scan_chunk_tiles")) o.scan_chunk_tiles = (int)value;
     else return fail(CC_ERR_ARG, "unknown option '%s'", name);
     return CC_OK;
 }
@@ -392,6 +395,9 @@ int cc_open_device(const void *dev_body, uint32_t k, uint32_t s, uint32_t c, uin
     g->first_index = first_index;
     DeviceGuard guard(device);
     if (int rc = init_handle(g.get(), device)) return rc;
+    // The caller's buffer may still be being written on another stream (the handle's own stream is
+    // non-blocking): settle the device once here so that every later call sees the finished array.
+    CC_CUDA(cudaDeviceSynchronize());
     *out = g.release();
     return CC_OK;
 }
@@ -503,7 +509,7 @@ int cc_find_novel_dev(cc_graph *g, int32_t child, const int32_t *parents, int np
     ScanArgs a{};
     a.body = g->dev_body; a.n = g->h.num_records; a.index_base = g->first_index;
     a.k = g->h.k; a.s = g->h.s; a.c = g->h.c;
-    a.child = child; a.nparents = nparents;
+    a.child = child; a.nparents = nparents; a.parent_list = parents;
     a.out_records = static_cast<uint8_t *>(dev_out_records); a.out_index = dev_out_index; a.cap = cap;
     a.total_in = nullptr; a.total_out = dev_out_count;
     return launch_scan_novel(a, g->scan_ws, g->sm_count, st);
@@ -628,7 +634,7 @@ int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s
             h2d += nr * S;
             ScanArgs a{};
             a.body = buf[b].as<uint8_t>(); a.n = nr; a.index_base = r0;
-            a.k = k; a.s = s; a.c = c; a.child = child; a.nparents = nparents;
+            a.k = k; a.s = s; a.c = c; a.child = child; a.nparents = nparents; a.parent_list = parents;
             a.out_records = o.as<uint8_t>(); a.out_index = out_index ? ix.as<uint64_t>() : nullptr; a.cap = dcap;
             a.total_in = totals + (ci & 1); a.total_out = totals + ((ci + 1) & 1);
             if (int rc = launch_scan_novel(a, g->scan_ws, g->sm_count, g->stream)) return rc;

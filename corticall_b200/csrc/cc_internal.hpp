@@ -28,12 +28,15 @@ inline void count_launch(uint32_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 // ------------------------------------------------------------------ options (cc_set_option)
 struct Options {
-    int scan_stages = 4;
+    int scan_stages = 3;
     int scan_tile_bytes = 32768;
     int scan_ctas_per_sm = 2;
     int index_bits = 0;          // 0 = auto
     int lookup_block = 256;
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
+    int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
+    int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)
+    int scan_debug = 0;          // diagnosis only: bit0 = skip the look-back (WRONG output positions)
 };
 Options &options();
 
@@ -117,6 +120,7 @@ struct ScanArgs {
     uint32_t k, s, c;
     int32_t child;
     int nparents;          // device list in ws.parents
+    const int32_t *parent_list;   // host copy of the same list
     uint8_t *out_records;  // device
     uint64_t *out_index;   // device or null
     uint64_t cap;

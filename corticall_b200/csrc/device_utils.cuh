@@ -59,11 +59,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_fail(err, code);
+    // try_wait suspends the warp in hardware for a bounded time, so the fast path is a handful of
+    // instructions; the wall-clock watchdog is consulted only every 4096 failed probes.
+#pragma unroll 1
+    for (uint32_t spins = 0; spins < 4096u; ++spins) {
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    const uint64_t t0 = globaltimer_ns();
+    while (true) {
+#pragma unroll 1
+        for (uint32_t spins = 0; spins < 4096u; ++spins) {
+            if (mbar_try_wait(bar, parity)) return;
+        }
+        if (globaltimer_ns() - t0 > kWatchdogNs) watchdog_fail(err, code);
     }
 }
 

@@ -26,10 +26,14 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;     // + 1 producer warp
+constexpr int kScanWarp = kConsumerWarps;            // warp 8: intra-tile scan + decoupled look-back
+constexpr int kProducerWarp = kConsumerWarps + 1;    // warp 9: tile tickets + bulk copies
+constexpr int kThreads = kConsumerThreads + 64;
 constexpr int kMaxIters = 8;                        // tile_records <= kMaxIters * kConsumerThreads
 constexpr int kMaxStages = 8;
-constexpr uint32_t kCtrlBytes = 1024;
+constexpr int kSlots = kMaxIters * kConsumerWarps;  // (iteration, warp) count slots per tile
+constexpr uint32_t kCtrlBytes = 2048;
+constexpr int kFastParents = 4;                     // parent offsets kept in registers up to this many
 
 constexpr uint64_t kFlagAgg = 1ull << 62;
 constexpr uint64_t kFlagPrefix = 2ull << 62;
@@ -51,6 +55,8 @@ struct ScanKParams {
     uint64_t n, index_base;
     uint32_t s, c, cov_off, edge_off, O;
     int32_t child, nparents;
+    uint32_t child_off;                 // cov_off + 4*child
+    uint32_t parent_off[kFastParents];  // cov_off + 4*parent (first kFastParents parents)
     const int32_t *parents;
     uint8_t *out;
     uint64_t *out_index;
@@ -61,7 +67,15 @@ struct ScanKParams {
     uint32_t *tile_counter;
     uint32_t ticket_base;
     uint32_t epoch;
+    uint32_t debug;
     int *err;
+    // general kernel only: run iff *run_if == run_expect (run_if == null: always).  When skipped, block 0 still
+    // draws the launch's tickets so the host's mirror of the ticket counter stays exact.
+    const uint32_t *run_if;
+    uint32_t run_expect, skip_tickets;
+    // fast kernel only
+    uint32_t chunk_log2, num_chunks, stg_stride, stg_cap, Ow;
+    uint32_t *overflow;
     TileGeom g;
 };
 
@@ -80,50 +94,47 @@ struct DecodeKParams {
 
 // Shared-memory control block (first kCtrlBytes of dynamic smem).
 struct Ctrl {
-    uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
+    uint64_t full[kMaxStages];      // producer -> everyone: tile bytes have landed (tx-count barrier)
+    uint64_t empty[kMaxStages];     // consumer warps -> producer: stage may be overwritten
+    uint64_t counted[2];            // consumer warps -> scan warp: per-warp novel counts of the tile are in cnt[slot]
+    uint64_t based[2];              // scan warp -> consumer warps: pre[slot] and tile_base[slot] are valid
     int32_t tile_id[kMaxStages];
-    uint32_t cnt[kMaxIters * kConsumerWarps];
-    uint32_t pre[kMaxIters * kConsumerWarps];
-    uint64_t tile_base;
+    uint32_t cnt[2][kSlots];
+    uint32_t pre[2][kSlots];
+    uint64_t tile_base[2];
 };
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block too large");
 
 // ------------------------------------------------------------------ producer: the TMA side of the ring
-__device__ __forceinline__ void producer_loop(Ctrl *ctrl, uint8_t *stage0, const uint8_t *body, uint64_t n,
-                                              const TileGeom &g, uint32_t *tile_counter, uint32_t ticket_base, int *err) {
+// One thread.  Tiles are handed out by a global ticket (so every predecessor of a tile is already owned by a
+// running CTA: the look-back can never wait on an unscheduled CTA); the ticket of the NEXT tile is requested
+// before waiting for a free stage so the atomic's round trip overlaps the wait and the copy issue.
+__device__ __forceinline__ void producer_loop(uint64_t *full, uint64_t *empty, int32_t *tile_id, uint8_t *stage0,
+                                              const uint8_t *body, uint64_t n, const TileGeom &g, uint32_t *tile_counter,
+                                              uint32_t ticket_base, int *err) {
     const uint64_t policy = make_evict_first_policy();
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(body) & 15u);
     const uint8_t *abase = body - mis;
+    uint32_t t_next = atomicAdd(tile_counter, 1u) - ticket_base;
     for (uint32_t it = 0;; ++it) {
         const uint32_t st = it % g.stages;
         const uint32_t ph = (it / g.stages) & 1u;
-        mbar_wait(&ctrl->empty[st], ph ^ 1u, err, DEV_TIMEOUT_EMPTY);
-        const uint32_t t = atomicAdd(tile_counter, 1u) - ticket_base;
+        const uint32_t t = t_next;
+        if (t < g.num_tiles) t_next = atomicAdd(tile_counter, 1u) - ticket_base;   // exactly one ticket >= num_tiles per CTA
+        mbar_wait(&empty[st], ph ^ 1u, err, DEV_TIMEOUT_EMPTY);
         if (t >= g.num_tiles) {
-            ctrl->tile_id[st] = -1;
-            mbar_arrive(&ctrl->full[st]);           // sentinel: consumers see tile_id < 0 and leave
+            tile_id[st] = -1;
+            mbar_arrive(&full[st]);                 // sentinel: consumers see tile_id < 0 and leave
             break;
         }
-        ctrl->tile_id[st] = (int32_t)t;
+        tile_id[st] = (int32_t)t;
         const uint64_t rec0 = (uint64_t)t * g.tile_records;
         const uint64_t left = n - rec0;
         const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
         const uint32_t bytes = (nrec * g.S + mis + 15u) & ~15u;
-        mbar_arrive_expect_tx(&ctrl->full[st], bytes);
-        bulk_g2s(stage0 + (size_t)st * g.stage_bytes, abase + rec0 * g.S, bytes, &ctrl->full[st], policy);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        bulk_g2s(stage0 + (size_t)st * g.stage_bytes, abase + rec0 * g.S, bytes, &full[st], policy);
     }
-}
-
-__device__ __forceinline__ void ring_init(Ctrl *ctrl, uint32_t stages) {
-    if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < stages; ++i) {
-            mbar_init(&ctrl->full[i], 1);
-            mbar_init(&ctrl->empty[i], kConsumerWarps);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------ decoupled look-back (one warp)
@@ -131,8 +142,8 @@ __device__ __forceinline__ uint64_t pack_desc(uint64_t flag, uint32_t epoch, uin
     return flag | ((uint64_t)(epoch & kEpochMask) << 40) | (value & kValueMask);
 }
 
-// Returns the exclusive prefix of `tile` (novel records in all earlier tiles + base) and publishes this
-// tile's inclusive prefix.  Called by all 32 lanes of one warp.
+// Publishes this tile's aggregate, returns its exclusive prefix (novel records in all earlier tiles + base) and
+// publishes its inclusive prefix.  Called by all 32 lanes of one warp.
 __device__ __forceinline__ uint64_t lookback(uint64_t *state, uint32_t tile, uint64_t agg, uint32_t epoch,
                                              const uint64_t *total_in, int *err) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -182,116 +193,427 @@ __device__ __forceinline__ uint64_t lookback(uint64_t *state, uint32_t tile, uin
 }
 
 // ------------------------------------------------------------------ K1+K2: novelty scan
-template <bool ALIGNED4>
+// Warp roles: 0..7 consumers, 8 scan, 9 producer.  Per tile:
+//   consumers  wait full[stage]; evaluate FindROIs.isNovel for their records (ballot masks stay in registers);
+//              post per-(iteration,warp) counts; arrive counted[slot];
+//   scan warp  wait counted[slot]; exclusive scan of the counts; PUBLISH THE TILE AGGREGATE at once; look back
+//              for the exclusive prefix; arrive based[slot];
+//   consumers  (after having evaluated the NEXT tile) wait based[slot]; copy their novel records to
+//              out[(base + rank) * O]; release the stage.
+// The aggregate of a tile is therefore published as soon as its bytes have been seen, independent of how long
+// earlier tiles of the same CTA wait for their own prefixes -- that keeps the look-back chain short.
+template <bool ALIGNED4, int NP>   // NP = number of parents when <= kFastParents, else -1 (list in shared memory)
 __global__ void __launch_bounds__(kThreads, 2) scan_novel_kernel(const __grid_constant__ ScanKParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (p.run_if != nullptr && *reinterpret_cast<const volatile uint32_t *>(p.run_if) != p.run_expect) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.tile_counter, p.skip_tickets);
+        return;
+    }
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(smem);
-    int32_t *parents_s = reinterpret_cast<int32_t *>(smem + kCtrlBytes);
-    const uint32_t parents_bytes = ((uint32_t)p.nparents * 4u + 127u) & ~127u;
+    uint32_t *parents_s = reinterpret_cast<uint32_t *>(smem + kCtrlBytes);     // byte offsets cov_off + 4*parent
+    const uint32_t parents_bytes = NP >= 0 ? 0u : (((uint32_t)p.nparents * 4u + 127u) & ~127u);
     uint8_t *stage0 = smem + kCtrlBytes + parents_bytes;
 
     const TileGeom &g = p.g;
-    for (int i = threadIdx.x; i < p.nparents; i += kThreads) parents_s[i] = p.parents[i];
-    ring_init(ctrl, g.stages);
+    if (NP < 0)
+        for (int i = threadIdx.x; i < p.nparents; i += kThreads) parents_s[i] = p.cov_off + 4u * (uint32_t)p.parents[i];
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < g.stages; ++i) {
+            mbar_init(&ctrl->full[i], 1);
+            mbar_init(&ctrl->empty[i], kConsumerWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&ctrl->counted[i], kConsumerWarps);
+            mbar_init(&ctrl->based[i], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (warp == kConsumerWarps) {
-        if (lane == 0) producer_loop(ctrl, stage0, p.body, p.n, g, p.tile_counter, p.ticket_base, p.err);
+    if (warp == kProducerWarp) {
+        if (lane == 0)
+            producer_loop(ctrl->full, ctrl->empty, ctrl->tile_id, stage0, p.body, p.n, g, p.tile_counter, p.ticket_base, p.err);
         return;
     }
-
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.body) & 15u);
-    const uint32_t S = g.S;
     const uint32_t nslots = g.iters * kConsumerWarps;
 
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t st = it % g.stages;
-        const uint32_t ph = (it / g.stages) & 1u;
-        mbar_wait(&ctrl->full[st], ph, p.err, DEV_TIMEOUT_FULL);
-        const int32_t tile = ctrl->tile_id[st];
-        if (tile < 0) break;
-        const uint64_t rec0 = (uint64_t)tile * g.tile_records;
-        const uint64_t left = p.n - rec0;
-        const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
-        const uint8_t *tile_s = stage0 + (size_t)st * g.stage_bytes + mis;
-
-        // ---- predicate (FindROIs.isNovel): coverage[child] > 0 (signed) && all listed parents == 0
-        uint32_t masks[kMaxIters];
-#pragma unroll
-        for (int j = 0; j < kMaxIters; ++j) {
-            masks[j] = 0;
-            if (j < (int)g.iters) {
-                const uint32_t r = (uint32_t)j * kConsumerThreads + threadIdx.x;
-                bool novel = false;
-                if (r < nrec) {
-                    const uint8_t *cov = tile_s + r * S + p.cov_off;
-                    uint32_t any_parent = 0;
-                    for (int i = 0; i < p.nparents; ++i) any_parent |= lds_u32<ALIGNED4>(cov + 4 * parents_s[i]);
-                    const int32_t child_cov = (int32_t)lds_u32<ALIGNED4>(cov + 4 * p.child);
-                    novel = (child_cov > 0) && (any_parent == 0);
-                }
-                masks[j] = __ballot_sync(0xffffffffu, novel);
-                if (lane == 0) ctrl->cnt[j * kConsumerWarps + warp] = __popc(masks[j]);
-            }
-        }
-        named_bar_sync(1, kConsumerThreads);
-
-        // ---- intra-tile exclusive scan of the (iteration, warp) counts + look-back, by warp 0
-        if (warp == 0) {
-            const uint32_t a = lane < nslots ? ctrl->cnt[lane] : 0u;
-            const uint32_t b = lane + 32 < nslots ? ctrl->cnt[lane + 32] : 0u;
+    if (warp == kScanWarp) {
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u, slot = it & 1u, sph = (it >> 1) & 1u;
+            mbar_wait(&ctrl->full[st], ph, p.err, DEV_TIMEOUT_FULL);
+            const int32_t tile = ctrl->tile_id[st];
+            if (tile < 0) break;
+            mbar_wait(&ctrl->counted[slot], sph, p.err, DEV_TIMEOUT_FULL);
+            const uint32_t a = lane < nslots ? ctrl->cnt[slot][lane] : 0u;
+            const uint32_t b = lane + 32 < nslots ? ctrl->cnt[slot][lane + 32] : 0u;
             uint32_t ia = a, ib = b;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
-                uint32_t tb = __shfl_up_sync(0xffffffffu, ib, o);
+                const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
+                const uint32_t tb = __shfl_up_sync(0xffffffffu, ib, o);
                 if ((int)lane >= o) { ia += ta; ib += tb; }
             }
             const uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
             const uint32_t tot_b = __shfl_sync(0xffffffffu, ib, 31);
-            if (lane < nslots) ctrl->pre[lane] = ia - a;
-            if (lane + 32 < nslots) ctrl->pre[lane + 32] = tot_a + ib - b;
+            if (lane < nslots) ctrl->pre[slot][lane] = ia - a;
+            if (lane + 32 < nslots) ctrl->pre[slot][lane + 32] = tot_a + ib - b;
             const uint64_t agg = (uint64_t)tot_a + tot_b;
-            const uint64_t excl = lookback(p.tile_state, (uint32_t)tile, agg, p.epoch, p.total_in, p.err);
+            const uint64_t excl = (p.debug & 1u) ? 0ull : lookback(p.tile_state, (uint32_t)tile, agg, p.epoch, p.total_in, p.err);
             if (lane == 0) {
-                ctrl->tile_base = excl;
+                ctrl->tile_base[slot] = excl;
                 if ((uint32_t)tile == g.num_tiles - 1) *p.total_out = excl + agg;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->based[slot]);
         }
-        named_bar_sync(1, kConsumerThreads);
+        return;
+    }
 
-        // ---- ordered write-out: each warp copies its novel records' output bytes (8s words verbatim,
-        //      child coverage, child edge) as one contiguous byte run, 32 consecutive bytes per instruction.
-        const uint64_t tile_base = ctrl->tile_base;
+    // ---- consumer warps
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.body) & 15u);
+    const uint32_t S = g.S;
+    uint32_t poff[kFastParents > 0 ? kFastParents : 1];
 #pragma unroll
-        for (int j = 0; j < kMaxIters; ++j) {
-            if (j < (int)g.iters && masks[j] != 0) {
-                const uint32_t m = masks[j];
-                const uint64_t wbase = tile_base + ctrl->pre[j * kConsumerWarps + warp];
-                const uint32_t cnt = __popc(m);
-                const uint32_t rbase = (uint32_t)j * kConsumerThreads + warp * 32u;
-                const uint32_t total = cnt * p.O;
-                for (uint32_t b = lane; b < total; b += 32) {
-                    const uint32_t q = b / p.O;
-                    const uint32_t ob = b - q * p.O;
-                    if (wbase + q < p.cap) {
-                        const uint32_t src_lane = __fns(m, 0, q + 1);
-                        const uint8_t *rec = tile_s + (rbase + src_lane) * S;
-                        uint32_t off;
-                        if (ob < p.cov_off) off = ob;
-                        else if (ob < p.cov_off + 4) off = p.cov_off + 4 * p.child + (ob - p.cov_off);
-                        else off = p.edge_off + p.child;
-                        p.out[(wbase + q) * p.O + ob] = rec[off];
+    for (int i = 0; i < kFastParents; ++i) poff[i] = p.parent_off[i];
+    const uint32_t lane_lt = (1u << lane) - 1u;
+
+    uint32_t masks_prev[kMaxIters];
+#pragma unroll
+    for (int j = 0; j < kMaxIters; ++j) masks_prev[j] = 0;
+    int32_t tile_prev = -1;
+    uint32_t st_prev = 0;
+
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u, slot = it & 1u;
+        mbar_wait(&ctrl->full[st], ph, p.err, DEV_TIMEOUT_FULL);
+        const int32_t tile = ctrl->tile_id[st];
+        uint32_t masks_cur[kMaxIters];
+#pragma unroll
+        for (int j = 0; j < kMaxIters; ++j) masks_cur[j] = 0;
+        if (tile >= 0) {
+            // ---- predicate (FindROIs.isNovel :72-82): coverage[child] > 0 (signed) && every listed parent == 0
+            const uint64_t rec0 = (uint64_t)tile * g.tile_records;
+            const uint64_t left = p.n - rec0;
+            const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
+            const uint8_t *tile_s = stage0 + (size_t)st * g.stage_bytes + mis;
+#pragma unroll
+            for (int j = 0; j < kMaxIters; ++j) {
+                if (j < (int)g.iters) {
+                    const uint32_t r = (uint32_t)j * kConsumerThreads + threadIdx.x;
+                    bool novel = false;
+                    if (r < nrec && !(p.debug & 2u)) {
+                        const uint8_t *rec = tile_s + r * S;
+                        uint32_t any_parent = 0;
+                        if (NP >= 0) {
+#pragma unroll
+                            for (int i = 0; i < (NP > 0 ? NP : 0); ++i) any_parent |= lds_u32<ALIGNED4>(rec + poff[i]);
+                        } else {
+                            for (int i = 0; i < p.nparents; ++i) any_parent |= lds_u32<ALIGNED4>(rec + parents_s[i]);
+                        }
+                        const int32_t child_cov = (int32_t)lds_u32<ALIGNED4>(rec + p.child_off);
+                        novel = (child_cov > 0) && (any_parent == 0);
+                    }
+                    masks_cur[j] = __ballot_sync(0xffffffffu, novel);
+                    if (lane == 0) ctrl->cnt[slot][j * kConsumerWarps + warp] = __popc(masks_cur[j]);
+                }
+            }
+            if (lane == 0) mbar_arrive(&ctrl->counted[slot]);       // release: orders the cnt stores of this lane
+        }
+        if (tile_prev >= 0) {
+            // ---- ordered write-out of the PREVIOUS tile (its prefix has had a whole tile's time to resolve)
+            const uint32_t pslot = slot ^ 1u, psph = ((it - 1) >> 1) & 1u;
+            if (!(p.debug & 8u)) mbar_wait(&ctrl->based[pslot], psph, p.err, DEV_TIMEOUT_LOOKBACK);
+            const uint64_t tile_base = ctrl->tile_base[pslot];
+            const uint64_t rec0 = (uint64_t)tile_prev * g.tile_records;
+            const uint8_t *tile_s = stage0 + (size_t)st_prev * g.stage_bytes + mis;
+#pragma unroll
+            for (int j = 0; j < kMaxIters; ++j) {
+                const uint32_t m = masks_prev[j];
+                if (j < (int)g.iters && m != 0) {
+                    if ((m >> lane) & 1u) {
+                        const uint64_t pos = tile_base + ctrl->pre[pslot][j * kConsumerWarps + warp] + __popc(m & lane_lt);
+                        if (pos < p.cap) {
+                            const uint32_t r = (uint32_t)j * kConsumerThreads + threadIdx.x;
+                            const uint8_t *rec = tile_s + r * S;
+                            uint8_t *dst = p.out + pos * p.O;
+                            // CortexGraphWriter.addRecord :106-138: s words verbatim, child coverage (LE), child edge byte
+                            for (uint32_t b = 0; b < p.cov_off; ++b) dst[b] = rec[b];
+#pragma unroll
+                            for (uint32_t b = 0; b < 4; ++b) dst[p.cov_off + b] = rec[p.child_off + b];
+                            dst[p.cov_off + 4] = rec[p.edge_off + p.child];
+                            if (p.out_index) p.out_index[pos] = p.index_base + rec0 + r;
+                        }
                     }
                 }
-                if (p.out_index && ((m >> lane) & 1u)) {
-                    const uint64_t pos = wbase + __popc(m & ((1u << lane) - 1u));
-                    if (pos < p.cap) p.out_index[pos] = p.index_base + rec0 + rbase + lane;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->empty[st_prev]);
+        }
+        if (tile < 0) break;
+#pragma unroll
+        for (int j = 0; j < kMaxIters; ++j) masks_prev[j] = masks_cur[j];
+        tile_prev = tile;
+        st_prev = st;
+    }
+}
+
+// ------------------------------------------------------------------ K1+K2, fast path: chunked scan, deferred look-back
+// The per-tile look-back above costs every tile a global round trip with all consumer warps parked behind it.
+// Novel k-mers are rare (well under 1 % of a trio graph), so this kernel defers everything that needs another
+// CTA: a CTA claims CHUNKS of 2^chunk_log2 consecutive tiles; each consumer warp owns a contiguous slice of every
+// tile and appends its novel records to a private shared-memory list, posting one count per (tile, warp) -- the
+// eight consumer warps never synchronise with each other or with any other CTA while they stream.  At the end of
+// a chunk the scan warp sums the counts, publishes the CHUNK aggregate, looks back over chunk descriptors for the
+// exclusive prefix and copies the staged runs to out[] in (tile, warp) = input order, while the consumers are
+// already filling the other staging buffer with the next chunk.  A chunk whose staging list overflows (dense
+// novelty) raises *overflow = epoch; the general kernel is launched right behind this one and runs only then.
+constexpr int kMaxChunkTiles = 16;
+constexpr uint32_t kStageBufBytes = 2048;          // staging bytes per consumer warp per segment parity
+
+struct FastCtrl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t seg_done[2];           // consumer warps -> scan warp: segment (chunk) fully evaluated and staged
+    uint64_t seg_free[2];           // scan warp -> consumer warps: staging buffer / counts of that parity are free
+    int32_t tile_id[kMaxStages];
+    int32_t seg_chunk[2];           // chunk index of the segment, -1 = no more work
+    uint32_t ovfw[2][kConsumerWarps];
+    uint32_t cnt[2][kMaxChunkTiles * kConsumerWarps];
+};
+static_assert(sizeof(FastCtrl) <= kCtrlBytes, "control block too large");
+
+__device__ __forceinline__ void producer_loop_chunks(FastCtrl *ctrl, uint8_t *stage0, const ScanKParams &p) {
+    const TileGeom &g = p.g;
+    const uint64_t policy = make_evict_first_policy();
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.body) & 15u);
+    const uint8_t *abase = p.body - mis;
+    uint32_t c_next = atomicAdd(p.tile_counter, 1u) - p.ticket_base;
+    uint32_t it = 0;
+    while (true) {
+        const uint32_t c = c_next;
+        if (c >= p.num_chunks) {                     // exactly one ticket >= num_chunks per CTA
+            const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
+            mbar_wait(&ctrl->empty[st], ph ^ 1u, p.err, DEV_TIMEOUT_EMPTY);
+            ctrl->tile_id[st] = -1;
+            mbar_arrive(&ctrl->full[st]);
+            break;
+        }
+        c_next = atomicAdd(p.tile_counter, 1u) - p.ticket_base;      // round trip overlaps the whole chunk
+        const uint32_t t0 = c << p.chunk_log2;
+        const uint32_t t1 = min(t0 + (1u << p.chunk_log2), g.num_tiles);
+        for (uint32_t t = t0; t < t1; ++t, ++it) {
+            const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
+            mbar_wait(&ctrl->empty[st], ph ^ 1u, p.err, DEV_TIMEOUT_EMPTY);
+            ctrl->tile_id[st] = (int32_t)t;
+            const uint64_t rec0 = (uint64_t)t * g.tile_records;
+            const uint64_t left = p.n - rec0;
+            const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
+            const uint32_t bytes = (nrec * g.S + mis + 15u) & ~15u;
+            mbar_arrive_expect_tx(&ctrl->full[st], bytes);
+            bulk_g2s(stage0 + (size_t)st * g.stage_bytes, abase + rec0 * g.S, bytes, &ctrl->full[st], policy);
+        }
+    }
+}
+
+template <bool ALIGNED4, int NP>
+__global__ void __launch_bounds__(kThreads, 2) scan_novel_fast_kernel(const __grid_constant__ ScanKParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    FastCtrl *ctrl = reinterpret_cast<FastCtrl *>(smem);
+    uint32_t *parents_s = reinterpret_cast<uint32_t *>(smem + kCtrlBytes);
+    const uint32_t parents_bytes = NP >= 0 ? 0u : (((uint32_t)p.nparents * 4u + 127u) & ~127u);
+    uint8_t *stg0 = smem + kCtrlBytes + parents_bytes;                          // [2][kConsumerWarps][stg_cap] entries
+    const uint32_t stg_warp_bytes = p.stg_cap * p.stg_stride;
+    const uint32_t stg_bytes = (2u * kConsumerWarps * stg_warp_bytes + 127u) & ~127u;
+    uint8_t *stage0 = stg0 + stg_bytes;
+
+    const TileGeom &g = p.g;
+    if (NP < 0)
+        for (int i = threadIdx.x; i < p.nparents; i += kThreads) parents_s[i] = p.cov_off + 4u * (uint32_t)p.parents[i];
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < g.stages; ++i) {
+            mbar_init(&ctrl->full[i], 1);
+            mbar_init(&ctrl->empty[i], kConsumerWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&ctrl->seg_done[i], kConsumerWarps);
+            mbar_init(&ctrl->seg_free[i], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (warp == kProducerWarp) {
+        if (lane == 0) producer_loop_chunks(ctrl, stage0, p);
+        return;
+    }
+    const uint32_t T = 1u << p.chunk_log2;
+
+    if (warp == kScanWarp) {
+        for (uint32_t seg = 0;; ++seg) {
+            const uint32_t par = seg & 1u, k = seg >> 1;
+            mbar_wait(&ctrl->seg_done[par], k & 1u, p.err, DEV_TIMEOUT_FULL);
+            const int32_t chunk = ctrl->seg_chunk[par];
+            if (chunk < 0) break;
+            const uint32_t t0 = (uint32_t)chunk << p.chunk_log2;
+            const uint32_t ntile = min(T, g.num_tiles - t0);
+            const uint32_t nent = ntile * kConsumerWarps;
+            uint32_t cv[4];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t e = (uint32_t)i * 32u + lane;
+                cv[i] = e < nent ? ctrl->cnt[par][e] : 0u;
+                sum += cv[i];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const bool ovf = __any_sync(0xffffffffu, lane < kConsumerWarps && ctrl->ovfw[par][lane & 7u] != 0u);
+            const uint64_t total = sum;
+            const uint64_t excl = lookback(p.tile_state, (uint32_t)chunk, total, p.epoch, p.total_in, p.err);
+            if (ovf) {
+                if (lane == 0) atomicExch(p.overflow, p.epoch);
+            } else if (sum != 0) {
+                // ---- copy the staged runs out in (tile, warp) order = input order.  Entry e = t*8 + w is held by
+                // lane e%32 in cv[e/32]; every lane copies its own (at most four, usually empty) runs, so the
+                // copy is a few dozen independent byte moves per lane instead of a serial walk over the runs.
+                const uint64_t chunk_rec0 = (uint64_t)t0 * g.tile_records;
+                uint32_t row_carry = 0;             // records in entries of earlier i (row-major prefix)
+                uint32_t col_carry = 0;             // records of warp (lane&7) in tiles of earlier i
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t v = cv[i];
+                    // exclusive prefix over entries in order (lanes ascending)
+                    uint32_t inc = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if ((int)lane >= o) inc += t;
+                    }
+                    const uint32_t row_total = __shfl_sync(0xffffffffu, inc, 31);
+                    // records of the same consumer warp (same lane&7) in the earlier tiles of this group of four
+                    const uint32_t u8 = __shfl_up_sync(0xffffffffu, v, 8);
+                    const uint32_t u16 = __shfl_up_sync(0xffffffffu, v, 16);
+                    const uint32_t u24 = __shfl_up_sync(0xffffffffu, v, 24);
+                    const uint32_t col_pre = (lane >= 8 ? u8 : 0u) + (lane >= 16 ? u16 : 0u) + (lane >= 24 ? u24 : 0u);
+                    uint32_t col_total = v + __shfl_xor_sync(0xffffffffu, v, 8);
+                    col_total += __shfl_xor_sync(0xffffffffu, col_total, 16);
+                    if (v != 0) {
+                        const uint64_t pos0 = excl + row_carry + (inc - v);
+                        const uint32_t w = lane & (kConsumerWarps - 1u);
+                        const uint8_t *sp = stg0 + (size_t)(par * kConsumerWarps + w) * stg_warp_bytes +
+                                            (size_t)(col_carry + col_pre) * p.stg_stride;
+                        for (uint32_t q = 0; q < v; ++q) {
+                            const uint64_t pos = pos0 + q;
+                            if (pos < p.cap) {
+                                uint8_t *dst = p.out + pos * p.O;
+                                const uint8_t *src = sp + q * p.stg_stride;
+                                for (uint32_t b = 0; b < p.O; ++b) dst[b] = src[b];
+                                if (p.out_index)
+                                    p.out_index[pos] = p.index_base + chunk_rec0 + *reinterpret_cast<const uint32_t *>(src + p.Ow);
+                            }
+                        }
+                    }
+                    row_carry += row_total;
+                    col_carry += col_total;
+                }
+            }
+            if ((uint32_t)chunk == p.num_chunks - 1 && lane == 0) *p.total_out = excl + total;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->seg_free[par]);
+        }
+        return;
+    }
+
+    // ---- consumer warps: warp w owns records [w*rpw, (w+1)*rpw) of every tile
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.body) & 15u);
+    const uint32_t S = g.S;
+    const uint32_t rpw = g.tile_records / kConsumerWarps;            // multiple of 32
+    uint32_t poff[kFastParents > 0 ? kFastParents : 1];
+#pragma unroll
+    for (int i = 0; i < kFastParents; ++i) poff[i] = p.parent_off[i];
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    const uint32_t words4 = p.cov_off >> 2;                          // 4-byte words of the k-mer (2 per 64-bit word)
+
+    uint32_t seg = 0, fill = 0, ovf = 0;
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
+        mbar_wait(&ctrl->full[st], ph, p.err, DEV_TIMEOUT_FULL);
+        const int32_t tile = ctrl->tile_id[st];
+        const uint32_t par = seg & 1u, k = seg >> 1;
+        if (tile < 0) {
+            if (k >= 1) mbar_wait(&ctrl->seg_free[par], (k - 1u) & 1u, p.err, DEV_TIMEOUT_LOOKBACK);
+            if (warp == 0 && lane == 0) ctrl->seg_chunk[par] = -1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->seg_done[par]);
+            break;
+        }
+        const uint32_t tin = (uint32_t)tile & (T - 1u);
+        if (tin == 0) {
+            // a new chunk: its staging buffer was last used two chunks ago; wait until the scan warp drained it
+            if (k >= 1) mbar_wait(&ctrl->seg_free[par], (k - 1u) & 1u, p.err, DEV_TIMEOUT_LOOKBACK);
+            fill = 0;
+            ovf = 0;
+            if (warp == 0 && lane == 0) ctrl->seg_chunk[par] = tile >> p.chunk_log2;
+        }
+        const uint64_t rec0 = (uint64_t)tile * g.tile_records;
+        const uint64_t left = p.n - rec0;
+        const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
+        const uint8_t *tile_s = stage0 + (size_t)st * g.stage_bytes + mis;
+        uint8_t *stg = stg0 + (size_t)(par * kConsumerWarps + warp) * stg_warp_bytes;
+        uint32_t tile_cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxIters; ++j) {
+            if (j * 32 < (int)rpw) {
+                const uint32_t r = warp * rpw + (uint32_t)j * 32u + lane;
+                const uint8_t *rec = tile_s + r * S;
+                bool novel = false;
+                if (r < nrec && !(p.debug & 2u)) {
+                    // FindROIs.isNovel :72-82: coverage[child] > 0 (signed) && every listed parent == 0
+                    uint32_t any_parent = 0;
+                    if (NP >= 0) {
+#pragma unroll
+                        for (int i = 0; i < (NP > 0 ? NP : 0); ++i) any_parent |= lds_u32<ALIGNED4>(rec + poff[i]);
+                    } else {
+                        for (int i = 0; i < p.nparents; ++i) any_parent |= lds_u32<ALIGNED4>(rec + parents_s[i]);
+                    }
+                    const int32_t child_cov = (int32_t)lds_u32<ALIGNED4>(rec + p.child_off);
+                    novel = (child_cov > 0) && (any_parent == 0);
+                    if (p.debug & 32u) novel = novel && (child_cov == 0x7fffffff);      // diagnosis: loads kept, nothing novel
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, novel);
+                if (m != 0) {
+                    const uint32_t c = __popc(m);
+                    if (fill + c <= p.stg_cap) {
+                        if (novel) {
+                            // staged entry = the output record (s words verbatim, child coverage LE, child edge byte:
+                            // CortexGraphWriter.addRecord :106-138), padded to Ow, then the chunk-relative record number
+                            uint8_t *dst = stg + (size_t)(fill + __popc(m & lane_lt)) * p.stg_stride;
+                            for (uint32_t w4 = 0; w4 < words4; ++w4)
+                                *reinterpret_cast<uint32_t *>(dst + 4u * w4) = lds_u32<ALIGNED4>(rec + 4u * w4);
+                            *reinterpret_cast<uint32_t *>(dst + p.cov_off) = lds_u32<ALIGNED4>(rec + p.child_off);
+                            dst[p.cov_off + 4u] = rec[p.edge_off + p.child];
+                            *reinterpret_cast<uint32_t *>(dst + p.Ow) = tin * g.tile_records + r;
+                        }
+                    } else {
+                        ovf = 1;
+                    }
+                    fill += c;
+                    tile_cnt += c;
                 }
             }
         }
+        if (lane == 0) ctrl->cnt[par][tin * kConsumerWarps + warp] = tile_cnt;
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->empty[st]);
+        if (tin == T - 1u || (uint32_t)tile == g.num_tiles - 1u) {
+            if (lane == 0) {
+                ctrl->ovfw[par][warp] = ovf;
+                mbar_arrive(&ctrl->seg_done[par]);       // release: orders this warp's staging + count stores (after __syncwarp)
+            }
+            ++seg;
+        }
     }
 }
 
@@ -302,13 +624,22 @@ __global__ void __launch_bounds__(kThreads, 2) decode_columns_kernel(const __gri
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(smem);
     uint8_t *stage0 = smem + kCtrlBytes;
     const TileGeom &g = p.g;
-    ring_init(ctrl, g.stages);
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < g.stages; ++i) {
+            mbar_init(&ctrl->full[i], 1);
+            mbar_init(&ctrl->empty[i], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (warp == kConsumerWarps) {
-        if (lane == 0) producer_loop(ctrl, stage0, p.body, p.n, g, p.tile_counter, p.ticket_base, p.err);
+    if (warp == kProducerWarp) {
+        if (lane == 0)
+            producer_loop(ctrl->full, ctrl->empty, ctrl->tile_id, stage0, p.body, p.n, g, p.tile_counter, p.ticket_base, p.err);
         return;
     }
+    if (warp == kScanWarp) return;                  // no compaction in the column decode
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.body) & 15u);
     const uint32_t S = g.S;
 
@@ -437,6 +768,58 @@ void ScanWorkspace::release() {
     *this = ScanWorkspace();
 }
 
+namespace {
+
+struct FastGeom {
+    TileGeom g;
+    uint32_t chunk_log2 = 0, num_chunks = 0, stg_stride = 0, stg_cap = 0, Ow = 0, stg_bytes = 0;
+    bool ok = false;
+};
+
+// Geometry of the fast kernel: tiles of a multiple of 256 records (8 warps x 32 lanes), a staging area, >= 2 stages.
+FastGeom pick_fast_geometry(uint64_t n, uint32_t S, uint32_t O, uint32_t extra_smem, int max_smem_optin, int ctas_per_sm) {
+    FastGeom f;
+    const Options &o = options();
+    if (!o.scan_fast || S == 0) return f;
+    uint32_t R = ((uint32_t)std::max(4096, o.scan_tile_bytes) / S) & ~255u;
+    if (R < 256) R = 256;
+    if (R > (uint32_t)(kMaxIters * kConsumerThreads)) R = kMaxIters * kConsumerThreads;
+    const uint32_t stage_bytes = (R * S + 32u + 127u) & ~127u;
+    f.Ow = (O + 3u) & ~3u;
+    f.stg_stride = f.Ow + 4u;
+    f.stg_cap = kStageBufBytes / f.stg_stride;
+    if (f.stg_cap < 4) return f;
+    f.stg_bytes = (2u * kConsumerWarps * f.stg_cap * f.stg_stride + 127u) & ~127u;
+    int stages = std::min(std::max(o.scan_stages, 2), kMaxStages);
+    const int64_t budget = (int64_t)max_smem_optin / std::max(ctas_per_sm, 1) - 1024 - kCtrlBytes - extra_smem - f.stg_bytes;
+    while (stages > 2 && (int64_t)stages * stage_bytes > budget) --stages;
+    if ((int64_t)stages * stage_bytes > budget) return f;
+    if (((uint64_t)R * S + 31u) >= (1u << 20)) return f;
+    const uint64_t ntiles = (n + R - 1) / R;
+    if (ntiles >= (1ull << 31)) return f;
+    int lg = 0;
+    while ((1 << (lg + 1)) <= std::min(std::max(o.scan_chunk_tiles, 1), kMaxChunkTiles)) ++lg;
+    f.chunk_log2 = (uint32_t)lg;
+    f.num_chunks = (uint32_t)((ntiles + (1ull << lg) - 1) >> lg);
+    f.g.S = S; f.g.tile_records = R; f.g.num_tiles = (uint32_t)ntiles; f.g.stages = (uint32_t)stages;
+    f.g.stage_bytes = stage_bytes; f.g.iters = R / kConsumerThreads;
+    f.ok = true;
+    return f;
+}
+
+int next_epoch(ScanWorkspace &ws, cudaStream_t st) {
+    // A fresh epoch makes every descriptor of earlier launches read as "invalid" without a memset.
+    ws.epoch = (ws.epoch + 1) & kEpochMask;
+    if (ws.epoch == 0) {
+        CC_CUDA(cudaMemsetAsync(ws.tile_state, 0, ws.tile_state_cap * sizeof(uint64_t), st));
+        CC_CUDA(cudaMemsetAsync(ws.totals + 16, 0, 8, st));     // the overflow flag holds an epoch too
+        ws.epoch = 1;
+    }
+    return CC_OK;
+}
+
+}  // namespace
+
 // ws.parents must already hold the parent list; ws.ensure() must have been called for this n.
 int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaStream_t st) {
     if (a.n == 0) {
@@ -449,33 +832,70 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
     if (int rc = device_limits(lim)) return rc;
     const Options &o = options();
     const uint32_t S = 8u * a.s + 5u * a.c;
-    const uint32_t parents_bytes = ((uint32_t)a.nparents * 4u + 127u) & ~127u;
-    int ctas = std::max(1, std::min(o.scan_ctas_per_sm, 4));
+    const bool fastp = a.nparents <= kFastParents;
+    const uint32_t parents_bytes = fastp ? 0u : (((uint32_t)a.nparents * 4u + 127u) & ~127u);
+    const int ctas = std::max(1, std::min(o.scan_ctas_per_sm, 4));
     ScanKParams p{};
-    if (int rc = pick_geometry(a.n, S, parents_bytes, lim.smem_optin, ctas, p.g)) return rc;
-    if (p.g.num_tiles > ws.tile_state_cap) return fail(CC_ERR_ARG, "scan workspace too small");
-    // A fresh epoch makes every descriptor of earlier launches read as "invalid" without a memset.
-    ws.epoch = (ws.epoch + 1) & kEpochMask;
-    if (ws.epoch == 0) {
-        CC_CUDA(cudaMemsetAsync(ws.tile_state, 0, ws.tile_state_cap * sizeof(uint64_t), st));
-        ws.epoch = 1;
-    }
     p.body = a.body; p.n = a.n; p.index_base = a.index_base;
     p.s = a.s; p.c = a.c; p.cov_off = 8u * a.s; p.edge_off = 8u * a.s + 4u * a.c; p.O = 8u * a.s + 5u;
     p.child = a.child; p.nparents = a.nparents; p.parents = ws.parents;
+    p.child_off = p.cov_off + 4u * (uint32_t)a.child;
+    for (int i = 0; i < kFastParents; ++i)
+        p.parent_off[i] = (fastp && i < a.nparents) ? p.cov_off + 4u * (uint32_t)a.parent_list[i] : p.child_off;
     p.out = a.out_records; p.out_index = a.out_index; p.cap = a.cap;
     p.total_in = a.total_in; p.total_out = a.total_out;
     p.tile_state = ws.tile_state; p.tile_counter = ws.tile_counter;
-    p.epoch = ws.epoch; p.err = ws.dev_error;
-
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, p.g.num_tiles);
-    // every launch draws exactly num_tiles + grid tickets from the workspace's counter
-    p.ticket_base = ws.ticket_base;
-    ws.ticket_base += p.g.num_tiles + grid;
-
-    const size_t smem = kCtrlBytes + parents_bytes + (size_t)p.g.stages * p.g.stage_bytes;
+    p.err = ws.dev_error; p.debug = (uint32_t)o.scan_debug;
+    p.overflow = reinterpret_cast<uint32_t *>(ws.totals + 16);
     const bool aligned4 = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.body) & 3u) == 0);
-    auto kern = aligned4 ? scan_novel_kernel<true> : scan_novel_kernel<false>;
+    const int np_slot = fastp ? a.nparents : kFastParents + 1;
+    using Kern = void (*)(const ScanKParams);
+
+    // ---- fast kernel (chunked, deferred look-back)
+    bool guarded = false;
+    uint32_t fast_epoch = 0;
+    const FastGeom f = pick_fast_geometry(a.n, S, p.O, parents_bytes, lim.smem_optin, ctas);
+    if (f.ok && f.num_chunks <= ws.tile_state_cap) {
+        if (int rc = next_epoch(ws, st)) return rc;
+        ScanKParams q = p;
+        q.g = f.g; q.epoch = ws.epoch;
+        q.chunk_log2 = f.chunk_log2; q.num_chunks = f.num_chunks; q.stg_stride = f.stg_stride; q.stg_cap = f.stg_cap; q.Ow = f.Ow;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, f.num_chunks);
+        q.ticket_base = ws.ticket_base;
+        ws.ticket_base += f.num_chunks + grid;      // every CTA draws its chunks plus one terminal ticket
+        const size_t smem = kCtrlBytes + parents_bytes + f.stg_bytes + (size_t)f.g.stages * f.g.stage_bytes;
+        static const Kern ftable[2][kFastParents + 2] = {
+            {scan_novel_fast_kernel<false, 0>, scan_novel_fast_kernel<false, 1>, scan_novel_fast_kernel<false, 2>,
+             scan_novel_fast_kernel<false, 3>, scan_novel_fast_kernel<false, 4>, scan_novel_fast_kernel<false, -1>},
+            {scan_novel_fast_kernel<true, 0>, scan_novel_fast_kernel<true, 1>, scan_novel_fast_kernel<true, 2>,
+             scan_novel_fast_kernel<true, 3>, scan_novel_fast_kernel<true, 4>, scan_novel_fast_kernel<true, -1>}};
+        Kern kern = ftable[aligned4 ? 1 : 0][np_slot];
+        CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, st>>>(q);
+        count_launch();
+        CC_CUDA(cudaGetLastError());
+        guarded = true;
+        fast_epoch = ws.epoch;
+    }
+
+    // ---- general kernel (per-tile look-back, any density): alone, or behind the fast kernel and run only on overflow
+    if (int rc = pick_geometry(a.n, S, parents_bytes, lim.smem_optin, ctas, p.g)) return rc;
+    if (p.g.num_tiles > ws.tile_state_cap) return fail(CC_ERR_ARG, "scan workspace too small");
+    if (int rc = next_epoch(ws, st)) return rc;
+    p.epoch = ws.epoch;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, p.g.num_tiles);
+    p.ticket_base = ws.ticket_base;
+    ws.ticket_base += p.g.num_tiles + grid;         // drawn by the CTAs, or added by block 0 when the launch is skipped
+    p.run_if = guarded ? p.overflow : nullptr;
+    p.run_expect = fast_epoch;
+    p.skip_tickets = p.g.num_tiles + grid;
+    const size_t smem = kCtrlBytes + parents_bytes + (size_t)p.g.stages * p.g.stage_bytes;
+    static const Kern table[2][kFastParents + 2] = {
+        {scan_novel_kernel<false, 0>, scan_novel_kernel<false, 1>, scan_novel_kernel<false, 2>, scan_novel_kernel<false, 3>,
+         scan_novel_kernel<false, 4>, scan_novel_kernel<false, -1>},
+        {scan_novel_kernel<true, 0>, scan_novel_kernel<true, 1>, scan_novel_kernel<true, 2>, scan_novel_kernel<true, 3>,
+         scan_novel_kernel<true, 4>, scan_novel_kernel<true, -1>}};
+    Kern kern = table[aligned4 ? 1 : 0][np_slot];
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(p);
     count_launch();

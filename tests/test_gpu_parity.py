@@ -304,6 +304,7 @@ def test_full_size_config2_scan():
     bit-exact against the oracle run over the same bytes, plus size-independent properties."""
     k, c, n = 47, 4, 25_000_000
     body, words = synth.make_graph_body(20261018, n, k, c, device="cuda")
+    torch.cuda.synchronize()
     g = cb.CortexGraph.fromDevice(body.data_ptr(), k, c, n, keepalive=body)
     cnt, recs, idx = g.findNovel(0, [1, 2, 3])
     # properties: sorted unique indices; every emitted record equals the source record's projection
