@@ -1,0 +1,162 @@
+"""CPU-side checks (no GPU needed): the C-ABI library loads and exports every symbol include/corticall_cuda.h
+declares, header parsing / error statuses mirror the reference's exceptions (CortexGraph.java:74-76,82-84,140-142,
+163-167), compute entry points refuse to run without a device (no CPU fallback), and the host value types
+(CanonicalKmer, CortexByteKmer, CortexBinaryKmer, CortexRecord, SequenceUtils) match the reference's golden vectors."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import corticall_b200 as cb
+from corticall_b200 import _native as N
+from corticall_b200.host.kmer import _java_array_hash, decodeBinaryKmer, encodeBinaryKmer, native_words
+from oracle import orc
+from tools import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = cb.device_count() > 0
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "corticall_cuda.h")).read()
+    return sorted(set(re.findall(r"CC_API\s+[\w\s\*]+?\b(cc_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 35
+    L = N.lib()
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(N.SIGNATURES) == names                       # the ctypes table binds exactly the header
+    assert b"sm_100a" in L.cc_version()
+
+
+def test_no_cpu_fallback(fixture_ctx):
+    if HAS_GPU:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(cb.CortexJDKException) as ei:
+        cb.CortexGraph(fixture_ctx)
+    assert ei.value.status == N.CC_ERR_CUDA and "no CPU fallback" in str(ei.value)
+    seq = np.frombuffer(b"ACGT" * 20, dtype=np.uint8)
+    words = np.zeros((50, 1), dtype=np.uint64); flags = np.zeros(50, dtype=np.uint8)
+    assert N.lib().cc_pack_canonical(0, seq.ctypes.data, seq.size, 31, words.ctypes.data, flags.ctypes.data) == N.CC_ERR_CUDA
+    cnt = C.c_uint64()
+    par = np.array([1], dtype=np.int32)
+    rc = N.lib().cc_find_novel_host(0, seq.ctypes.data, 31, 1, 2, 1, 0, par.ctypes.data, 1, None, None, 0, C.byref(cnt), None)
+    assert rc == N.CC_ERR_CUDA
+
+
+def open_status(image: bytes):
+    h = N._P()
+    buf = np.frombuffer(image, dtype=np.uint8)
+    rc = N.lib().cc_open_memory(buf.ctypes.data, buf.size, 0, C.byref(h))
+    if rc == 0:
+        N.lib().cc_dispose(h)
+    return rc, N.last_error()
+
+
+def test_header_errors_mirror_the_reference(fixture_ctx, tmp_path):
+    rc, msg = open_status(b"NOTCTX" + fixture_ctx[6:])
+    assert rc == N.CC_ERR_NOT_CORTEX and "does not appear to be a Cortex graph" in msg
+    rc, msg = open_status(fixture_ctx[:6] + b"\x05\0\0\0" + fixture_ctx[10:])
+    assert rc == N.CC_ERR_BAD_VERSION and "is not a version 6 Cortex graph" in msg
+    rc, msg = open_status(fixture_ctx[:142] + b"XORTEX" + fixture_ctx[148:])
+    assert rc == N.CC_ERR_BAD_TRAILER and "proper header terminator" in msg
+    rc, msg = open_status(fixture_ctx[:60])
+    assert rc == N.CC_ERR_IO
+    rc, _ = open_status(b"cortex" + fixture_ctx[6:])           # equalsIgnoreCase: header accepted, fails only for lack of a device
+    assert rc == (0 if HAS_GPU else N.CC_ERR_CUDA)
+    h = N._P()
+    rc = N.lib().cc_open(str(tmp_path / "missing.ctx").encode(), 0, C.byref(h))
+    assert rc == N.CC_ERR_IO and "not found" in N.last_error()
+    assert N.lib().cc_set_option(b"no_such_option", 1) == N.CC_ERR_ARG
+
+
+# ------------------------------------------------------------------ host value types vs the reference's vectors
+
+def test_complement_and_reverse_complement(kats):               # SequenceUtilsTest :19-57
+    for a, b in zip(kats["complement_in"], kats["complement_out"]):
+        assert cb.SequenceUtils.complement(ord(a)) == ord(b)
+    for seq, exp in kats["reverse_complement"]:
+        assert cb.SequenceUtils.reverseComplement(seq) == exp
+        assert cb.SequenceUtils.reverseComplement(seq.encode()) == exp.encode()
+
+
+def test_lowest_orientation_matches_oracle_and_property():      # SequenceUtilsTest :59-72
+    rng = random.Random(0)
+    comp = str.maketrans("ACGT", "TGCA")
+    for k in (21, 31, 41, 51):
+        for _ in range(500):
+            fw = "".join(rng.choice("ACGT") for _ in range(k))
+            rc = fw.translate(comp)[::-1]
+            assert cb.SequenceUtils.alphanumericallyLowestOrientation(fw) == min(fw, rc)
+    for q in (b"NACGT", b"TTTTN", b"acgTT", b"AC.GT", b"AAAAA", b"ACGT", bytes([200, 65, 67, 71, 84])):
+        assert cb.SequenceUtils.alphanumericallyLowestOrientation(q) == orc.lowest_orientation(q)[0]
+
+
+def test_canonical_kmer(kats):                                   # CanonicalKmerTest :8-14
+    a, b = (cb.CanonicalKmer(x) for x in kats["hash_collision_pair"])
+    assert a.hashCode() == b.hashCode() and a != b
+    ck = cb.CanonicalKmer("TTTTT")
+    assert ck.getKmerAsString() == "AAAAA" and ck.isFlipped() and ck.length() == 5
+    assert cb.CanonicalKmer("AAAAC") == "AAAAC" and not cb.CanonicalKmer("AAAAC").isFlipped()
+    assert cb.CanonicalKmer("ACGTT").getSubKmer(1, 3).getKmerAsString() == "ACG"   # CGT -> canonical ACG
+    assert [k.getKmerAsString() for k in cb.SequenceUtils.kmerizeSequence("ACGTAC", 3)] == ["ACG", "ACG", "GTA", "GTA"]
+    assert len({cb.CanonicalKmer("ACGTA"), cb.CanonicalKmer("TACGT")}) == 1          # set membership (Call.java:191-197)
+
+
+def test_byte_kmer_compare_is_signed():                          # CortexByteKmer.java:41-49
+    a, b = cb.CortexByteKmer(bytes([200, 65])), cb.CortexByteKmer(b"AA")
+    assert a.compareTo(b) == -1 and b.compareTo(a) == 1 and a.compareTo(a) == 0
+    assert orc.lib().orc_byte_kmer_compare(np.frombuffer(a.getKmer(), np.uint8).ctypes.data,
+                                           np.frombuffer(b.getKmer(), np.uint8).ctypes.data, 2) == -1
+    assert hash(cb.CortexByteKmer("ACGT")) == _java_array_hash(b"ACGT")
+
+
+def test_encode_decode_binary_kmer(fixture_ctx, kats):           # CortexGraphTest.testEncodeBinaryKmer :267-280
+    og = orc.Graph(fixture_ctx)
+    for i, row in enumerate(kats["fixture_records"]):
+        bk, _, _ = og.get_record(i)
+        assert encodeBinaryKmer(row["kmer"].encode()) == bk.tolist()          # == the record's long[] (byte-swapped disk word)
+        assert decodeBinaryKmer(bk.tolist(), 31, 1) == row["kmer"].encode()
+    rng = random.Random(3)
+    for k in (1, 5, 31, 32, 33, 47, 63, 64, 65, 95, 128):
+        km = "".join(rng.choice("ACGT") for _ in range(k)).encode()
+        enc = np.zeros((k + 31) // 32, dtype=np.int64)
+        assert orc.lib().orc_encode_binary_kmer(np.frombuffer(km, np.uint8).ctypes.data, k, enc.ctypes.data) == 0
+        assert encodeBinaryKmer(km) == enc.tolist()
+        assert decodeBinaryKmer(enc.tolist(), k, len(enc)) == km
+        assert [int.from_bytes(int(x).to_bytes(8, "big", signed=True), "little") for x in enc] == native_words(km)
+    with pytest.raises(RuntimeError):
+        encodeBinaryKmer(b"ACGTN")
+    assert cb.CortexBinaryKmer(b"TTTT").getBinaryKmer() == encodeBinaryKmer(b"AAAA")   # (byte[]) ctor canonicalises
+
+
+def test_cortex_record_string_round_trip(kats):                  # CortexGraphTest.constructRecordsFromString :200-253
+    for row in kats["fixture_records"]:
+        text = "%s %d %d %s %s" % (row["kmer"], *row["coverage"], *row["edges"])
+        cr = cb.CortexRecord.fromString(text)
+        assert cr.toString() == text and cr.getKmerAsString() == row["kmer"]
+        assert cr.getEdgeAsStrings() == row["edges"] and cr.getCoverages() == row["coverage"]
+        for c in range(2):                                        # getLeftAndRightEdges :154-182
+            es = row["edges"][c]
+            assert [chr(b) for b in cr.getInEdgesAsBytes(c, False)] == [x.upper() for x in es[:4] if x != "."]
+            assert [chr(b) for b in cr.getOutEdgesAsBytes(c, False)] == [x for x in es[4:] if x != "."]
+            assert cr.getInDegree(c) == sum(x != "." for x in es[:4]) and cr.getOutDegree(c) == sum(x != "." for x in es[4:])
+        assert cr.toString(1) == "%s %d %s" % (row["kmer"], row["coverage"][1], row["edges"][1])
+    a, b = cb.CortexRecord.fromString("AAAAC 1 ....A..."), cb.CortexRecord.fromString("AAAAG 1 ....A...")
+    assert a.compareTo(b) == -1 and a != b and a == cb.CortexRecord.fromString("AAAAC 1 ....A...")
+    assert cb.CortexRecord.fromString("AAAAC 1 a.g..C.T").getInEdgesAsStrings(0, True) == ["T", "C"]
+
+
+def test_synth_header_matches_abi_parser():
+    """tools/synth writes headers the library's parser accepts with the right geometry (data offset not 16-aligned)."""
+    ctx = synth.make_ctx_file(5, 100, 47, 4, adv_period=0, trailing=b"\x01\x02")
+    og = orc.Graph(ctx)
+    assert og.ok and og.h.num_records == 100 and og.h.record_size == 36 and og.h.data_offset % 16 != 0
+    rc, _ = open_status(ctx)
+    assert rc == (0 if HAS_GPU else N.CC_ERR_CUDA)              # parsed fine; only the device is missing

@@ -328,3 +328,40 @@ def test_full_size_config2_scan():
     got = g.findPacked(recs[:, :16].copy().view("<u8"))
     assert (got == idx.astype(np.int64)).all()
     rg.dispose(); g.dispose()
+
+
+# ------------------------------------------------------------------ multi-GPU helpers on one device
+
+@pytest.mark.parametrize("nshards", [1, 2, 5, 8])
+def test_bucket_by_owner_and_scatter(nshards):
+    """cc_bucket_by_owner_dev / cc_scatter_results_dev against numpy: counts per owner, stable grouping, original slots."""
+    k, n, nq = 47, 20000, 50000
+    table = synth.random_canonical_keys(3, n, k, "cpu")
+    ascii_q, canon, valid = synth.make_queries(5, table, k, nq, corrupt_permille=20)
+    words = torch.stack(canon, dim=1).contiguous().cuda()
+    flags = torch.where(valid, 0, 2).to(torch.uint8).cuda()
+    spl = torch.stack([torch.stack([w[n * r // nshards] for w in table]) for r in range(1, nshards)]).cuda() if nshards > 1 else None
+    from corticall_b200.host.sharded import CudaOps
+    ops = CudaOps(None, torch.device("cuda", 0))
+    counts, sorted_words, slots = ops.bucket(words, flags, spl, nshards)
+    torch.cuda.synchronize()
+    w = words.cpu().numpy().view(np.uint64)
+    keyf = lambda a: [tuple(int(x) for x in row) for row in a]
+    sp = keyf(spl.cpu().numpy().view(np.uint64)) if nshards > 1 else []
+    import bisect
+    owner = np.array([bisect.bisect_right(sp, t) for t in keyf(w)])
+    ok = valid.numpy()
+    assert counts.cpu().tolist() == np.bincount(owner[ok], minlength=nshards).tolist()
+    tot = int(ok.sum())
+    got_slots = slots.cpu().numpy()[:tot].astype(np.int64)
+    assert sorted(got_slots.tolist()) == np.nonzero(ok)[0].tolist()              # a permutation of the routed queries
+    assert (sorted_words.cpu().numpy().view(np.uint64)[:tot] == w[got_slots]).all()
+    assert (np.diff(owner[got_slots]) >= 0).all()                                 # grouped by owner, ascending
+    # the return leg
+    vals = torch.arange(tot, dtype=torch.int64, device="cuda") * 3 + 1
+    out = torch.full((nq,), -1, dtype=torch.int64, device="cuda")
+    ops.scatter(vals, slots[:tot], out)
+    torch.cuda.synchronize()
+    exp = np.full(nq, -1, dtype=np.int64)
+    exp[got_slots] = np.arange(tot) * 3 + 1
+    assert (out.cpu().numpy() == exp).all()
