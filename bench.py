@@ -396,6 +396,9 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         out["ms_per_step"] = ms
         out["exchange"] = "bucket by owner (cc_bucket_by_owner_dev) -> all_to_all_single (NCCL) -> local search -> all_to_all_single -> scatter"
         out["hit_fraction"] = float((res >= 0).sum().item()) / nq
+        sl.profile = True
+        sl.find_packed(qwords, qflags, res)
+        out["phase_ms_rank0"] = sl.last.get("phase_ms")
     g.dispose()
     return out
 

@@ -1,0 +1,144 @@
+// jni_shim.cpp -- JNI bindings of libcorticall_cuda for java/uk/ac/ox/well/cortexjdk/utils/io/graph/cortex/NativeCortex.java.
+// Argument marshalling ONLY: every function forwards to one cc_* entry point of include/corticall_cuda.h and throws
+// uk.ac.ox.well.cortexjdk.utils.exceptions.CortexJDKException (S/utils/exceptions/CortexJDKException.java:3-10) with
+// cc_last_error() on a non-zero status.
+//
+// Not built in the development image (no JDK, no jni.h): compiled only when <jni.h> is on the include path, e.g.
+//   g++ -std=c++17 -O2 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux jni_shim.cpp -L.. -lcorticall_cuda -o ../libcorticall_jni.so
+#if __has_include(<jni.h>)
+#include <jni.h>
+
+#include <vector>
+
+#include "../../include/corticall_cuda.h"
+
+#define JFN(ret, name) extern "C" JNIEXPORT ret JNICALL Java_uk_ac_ox_well_cortexjdk_utils_io_graph_cortex_NativeCortex_##name
+
+static bool check(JNIEnv *env, int status) {
+    if (status == CC_OK) return true;
+    jclass ex = env->FindClass("uk/ac/ox/well/cortexjdk/utils/exceptions/CortexJDKException");
+    if (ex) env->ThrowNew(ex, cc_last_error());
+    return false;
+}
+static cc_graph *G(jlong h) { return reinterpret_cast<cc_graph *>(h); }
+
+JFN(jlong, open)(JNIEnv *env, jclass, jstring path, jint device) {
+    const char *p = env->GetStringUTFChars(path, nullptr);
+    cc_graph *g = nullptr;
+    const int rc = cc_open(p, device, &g);
+    env->ReleaseStringUTFChars(path, p);
+    return check(env, rc) ? reinterpret_cast<jlong>(g) : 0;
+}
+JFN(void, dispose)(JNIEnv *, jclass, jlong h) { cc_dispose(G(h)); }
+
+JFN(jlongArray, header)(JNIEnv *env, jclass, jlong h) {
+    uint32_t v, k, s, c; uint64_t n, off, rs;
+    if (!check(env, cc_header(G(h), &v, &k, &s, &c, &n, &off, &rs))) return nullptr;
+    const jlong vals[7] = {(jlong)v, (jlong)k, (jlong)s, (jlong)c, (jlong)n, (jlong)off, (jlong)rs};
+    jlongArray out = env->NewLongArray(7);
+    env->SetLongArrayRegion(out, 0, 7, vals);
+    return out;
+}
+JFN(jstring, colorName)(JNIEnv *env, jclass, jlong h, jint color) {
+    std::vector<char> buf(1 << 16);
+    return check(env, cc_color_name(G(h), (uint32_t)color, buf.data(), buf.size())) ? env->NewStringUTF(buf.data()) : nullptr;
+}
+JFN(jstring, colorGraphName)(JNIEnv *env, jclass, jlong h, jint color) {
+    std::vector<char> buf(1 << 16);
+    return check(env, cc_color_graph_name(G(h), (uint32_t)color, buf.data(), buf.size())) ? env->NewStringUTF(buf.data()) : nullptr;
+}
+JFN(jlongArray, colorInfo)(JNIEnv *env, jclass, jlong h, jint color) {
+    cc_color_info ci;
+    if (!check(env, cc_color_info_get(G(h), (uint32_t)color, &ci))) return nullptr;
+    const jlong vals[8] = {(jlong)ci.mean_read_length, (jlong)ci.total_sequence, ci.tip_clipping, ci.low_covg_supernodes_removed,
+                           ci.low_covg_kmers_removed, ci.cleaned_against_graph, (jlong)ci.low_cov_supernodes_threshold,
+                           (jlong)ci.low_cov_kmer_threshold};
+    jlongArray out = env->NewLongArray(8);
+    env->SetLongArrayRegion(out, 0, 8, vals);
+    return out;
+}
+
+JFN(void, decodeRecords)(JNIEnv *env, jclass, jlong h, jlong first, jint count, jlongArray kmers, jintArray cov, jbyteArray edges) {
+    jlong *k = env->GetLongArrayElements(kmers, nullptr);
+    jint *c = env->GetIntArrayElements(cov, nullptr);
+    jbyte *e = env->GetByteArrayElements(edges, nullptr);
+    const int rc = cc_decode_records(G(h), (uint64_t)first, (uint64_t)count, reinterpret_cast<uint64_t *>(k),
+                                     reinterpret_cast<int32_t *>(c), reinterpret_cast<uint8_t *>(e));
+    if (rc == CC_OK) {     // Java long[] = Long.reverseBytes(native word) (CortexGraph.java:208-209)
+        const jsize nw = env->GetArrayLength(kmers);
+        for (jsize i = 0; i < nw; ++i) k[i] = (jlong)__builtin_bswap64((uint64_t)k[i]);
+    }
+    env->ReleaseLongArrayElements(kmers, k, 0);
+    env->ReleaseIntArrayElements(cov, c, 0);
+    env->ReleaseByteArrayElements(edges, e, 0);
+    check(env, rc);
+}
+
+JFN(jlong, findNovel)(JNIEnv *env, jclass, jlong h, jint child, jintArray parents, jbyteArray outRecords, jlongArray outIndex) {
+    uint32_t s = 0;
+    cc_header(G(h), nullptr, nullptr, &s, nullptr, nullptr, nullptr, nullptr);
+    const jsize np = env->GetArrayLength(parents);
+    jint *p = env->GetIntArrayElements(parents, nullptr);
+    jbyte *r = outRecords ? env->GetByteArrayElements(outRecords, nullptr) : nullptr;
+    jlong *ix = outIndex ? env->GetLongArrayElements(outIndex, nullptr) : nullptr;
+    uint64_t cap = r ? (uint64_t)env->GetArrayLength(outRecords) / (8ull * s + 5) : 0, total = 0;
+    if (ix) cap = cap < (uint64_t)env->GetArrayLength(outIndex) ? cap : (uint64_t)env->GetArrayLength(outIndex);
+    const int rc = cc_find_novel(G(h), child, reinterpret_cast<int32_t *>(p), np, r, reinterpret_cast<uint64_t *>(ix), cap, &total);
+    env->ReleaseIntArrayElements(parents, p, JNI_ABORT);
+    if (r) env->ReleaseByteArrayElements(outRecords, r, 0);
+    if (ix) env->ReleaseLongArrayElements(outIndex, ix, 0);
+    return check(env, rc) ? (jlong)total : -1;
+}
+JFN(jlong, writeRoiFile)(JNIEnv *env, jclass, jlong h, jint child, jintArray parents, jstring outPath) {
+    const jsize np = env->GetArrayLength(parents);
+    jint *p = env->GetIntArrayElements(parents, nullptr);
+    const char *path = env->GetStringUTFChars(outPath, nullptr);
+    uint64_t total = 0;
+    const int rc = cc_write_roi_file(G(h), child, reinterpret_cast<int32_t *>(p), np, path, &total);
+    env->ReleaseStringUTFChars(outPath, path);
+    env->ReleaseIntArrayElements(parents, p, JNI_ABORT);
+    return check(env, rc) ? (jlong)total : -1;
+}
+
+JFN(void, findAscii)(JNIEnv *env, jclass, jlong h, jbyteArray kmers, jint nq, jlongArray outIndex) {
+    jbyte *q = env->GetByteArrayElements(kmers, nullptr);
+    jlong *o = env->GetLongArrayElements(outIndex, nullptr);
+    const int rc = cc_find_ascii(G(h), reinterpret_cast<uint8_t *>(q), (uint64_t)nq, reinterpret_cast<int64_t *>(o), CC_ALGO_AUTO);
+    env->ReleaseByteArrayElements(kmers, q, JNI_ABORT);
+    env->ReleaseLongArrayElements(outIndex, o, 0);
+    check(env, rc);
+}
+JFN(void, findWindows)(JNIEnv *env, jclass, jlong h, jbyteArray seq, jlongArray outIndex) {
+    jbyte *q = env->GetByteArrayElements(seq, nullptr);
+    jlong *o = env->GetLongArrayElements(outIndex, nullptr);
+    const int rc = cc_find_windows(G(h), reinterpret_cast<uint8_t *>(q), (uint64_t)env->GetArrayLength(seq),
+                                   reinterpret_cast<int64_t *>(o), CC_ALGO_AUTO);
+    env->ReleaseByteArrayElements(seq, q, JNI_ABORT);
+    env->ReleaseLongArrayElements(outIndex, o, 0);
+    check(env, rc);
+}
+JFN(void, containsWindows)(JNIEnv *env, jclass, jlong h, jbyteArray seq, jbooleanArray outPresent) {
+    jbyte *q = env->GetByteArrayElements(seq, nullptr);
+    jboolean *o = env->GetBooleanArrayElements(outPresent, nullptr);
+    const int rc = cc_contains_windows(G(h), reinterpret_cast<uint8_t *>(q), (uint64_t)env->GetArrayLength(seq),
+                                       reinterpret_cast<uint8_t *>(o));
+    env->ReleaseByteArrayElements(seq, q, JNI_ABORT);
+    env->ReleaseBooleanArrayElements(outPresent, o, 0);
+    check(env, rc);
+}
+JFN(void, packCanonical)(JNIEnv *env, jclass, jint device, jbyteArray seq, jint k, jlongArray outKmers, jbyteArray outFlags) {
+    jbyte *q = env->GetByteArrayElements(seq, nullptr);
+    jlong *w = env->GetLongArrayElements(outKmers, nullptr);
+    jbyte *f = env->GetByteArrayElements(outFlags, nullptr);
+    const int rc = cc_pack_canonical(device, reinterpret_cast<uint8_t *>(q), (uint64_t)env->GetArrayLength(seq), (uint32_t)k,
+                                     reinterpret_cast<uint64_t *>(w), reinterpret_cast<uint8_t *>(f));
+    if (rc == CC_OK) {
+        const jsize nw = env->GetArrayLength(outKmers);
+        for (jsize i = 0; i < nw; ++i) w[i] = (jlong)__builtin_bswap64((uint64_t)w[i]);
+    }
+    env->ReleaseByteArrayElements(seq, q, JNI_ABORT);
+    env->ReleaseLongArrayElements(outKmers, w, 0);
+    env->ReleaseByteArrayElements(outFlags, f, 0);
+    check(env, rc);
+}
+#endif  // __has_include(<jni.h>)

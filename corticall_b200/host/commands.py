@@ -1,0 +1,100 @@
+"""The two callers of the hot path, with the reference's names and argument meaning, each reduced to ONE batched
+device call per graph / per contig:
+
+  FindROIs                S/commands/discover/roi/FindROIs.java:17-106      (the novelty scan + ROI writer)
+  CallHelpers.loadRois / loadChildWalk / getRegions / sectionRois
+                          S/commands/discover/call/Call.java:2348-2356, 2358-2381, 2425-2451, 191-197
+
+Only the k-mer work of `Call` is here; Tesserae alignment, bubble / breakpoint calling and VCF writing stay in the
+Java host (out of scope).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .cortex import CortexGraph, CortexRecord
+from .kmer import CanonicalKmer
+
+
+class FindROIs:
+    """`FindROIs -g trio.ctx -p mom -p dad -c kid -o rois.ctx`: fields named as the reference's @Argument fields."""
+
+    def __init__(self, GRAPH: CortexGraph, PARENTS: list[str], CHILD: str, out):
+        self.GRAPH, self.PARENTS, self.CHILD, self.out = GRAPH, list(PARENTS), CHILD, out
+        self.numNovelRecords = 0
+
+    def execute(self) -> int:
+        childColor = self.GRAPH.getColorForSampleName(self.CHILD)
+        parentColors = self.GRAPH.getColorsForSampleNames(self.PARENTS)
+        # a sample name that does not resolve gives colour -1, which the reference then uses as an array index
+        # (ArrayIndexOutOfBoundsException); the library reports the same condition as CC_ERR_ARG
+        self.numNovelRecords = self.GRAPH.writeRois(childColor, parentColors, os.fspath(self.out))
+        return self.numNovelRecords
+
+
+class CortexVertex:
+    """The three fields of utils/traversal/CortexVertex the child walk fills (bases, record, copy index)."""
+
+    __slots__ = ("bases", "record", "copyIndex", "recordIndex")
+
+    def __init__(self, bases: str, record, copyIndex: int, recordIndex: int):
+        self.bases, self.record, self.copyIndex, self.recordIndex = bases, record, copyIndex, recordIndex
+
+    def getKmerAsString(self): return self.bases
+    def getCortexRecord(self): return self.record
+    def getCopyIndex(self): return self.copyIndex
+    def getCanonicalKmer(self): return CanonicalKmer(self.bases)
+
+
+class CallHelpers:
+    @staticmethod
+    def loadRois(rg: CortexGraph) -> CortexGraph:
+        """Call.loadRois builds a HashSet<CanonicalKmer> by iterating the ROI graph.  Here the device-resident ROI
+        graph IS the set: membership of every window of a contig is one `containsWindows` call."""
+        rg.buildIndex()
+        return rg
+
+    @staticmethod
+    def loadChildWalk(contig: str, graph: CortexGraph, materialize: bool = True) -> list[CortexVertex]:
+        """Call.loadChildWalk :2358-2381: one findRecord per window of the contig -> one batched lookup."""
+        k = graph.getKmerSize()
+        idx = graph.findWindows(contig)
+        walk: list[CortexVertex] = []
+        seen: dict[str, int] = {}
+        recs = {}
+        if materialize:
+            hits = np.unique(idx[idx >= 0])
+            for i in hits.tolist():                      # decode each distinct hit once (device decode)
+                w, c, e = graph.decodeRecords(i - graph.firstIndex, 1)
+                recs[i] = graph._make_record(w[0], c[0], e[0])
+        for i in range(len(idx)):
+            sk = contig[i:i + k]
+            seen[sk] = seen[sk] + 1 if sk in seen else 0
+            walk.append(CortexVertex(sk, recs.get(int(idx[i])), seen[sk], int(idx[i])))
+        return walk
+
+    @staticmethod
+    def getRegions(rois: CortexGraph, contig: str) -> list[tuple[int, int]]:
+        """Call.getRegions :2425-2451: maximal runs of consecutive windows whose canonical k-mer is in the ROI set."""
+        present = rois.containsWindows(contig)
+        regions, start, stop = [], -1, 0
+        for i, p in enumerate(present.tolist()):
+            if p:
+                if start == -1:
+                    start = i
+                stop = i
+            elif start > -1:
+                regions.append((start, stop))
+                start, stop = -1, 0
+        if start > -1:
+            regions.append((start, stop))
+        return regions
+
+    @staticmethod
+    def sectionRois(rois: CortexGraph, trimmedQuery: str) -> list[CanonicalKmer]:
+        """Call.java:191-197: the sorted set of ROI k-mers a query section contains."""
+        k = rois.getKmerSize()
+        present = rois.containsWindows(trimmedQuery)
+        return sorted({CanonicalKmer(trimmedQuery[i:i + k]) for i in np.nonzero(present)[0].tolist()})

@@ -197,6 +197,7 @@ class CortexGraph:
             N.check(L.cc_open(self.cortexFile.encode(), device, C.byref(h)))
         self._h = h
         self._device = device
+        self.firstIndex = 0
         self._load_header()
         self.recordsSeen = 0
         self._block = None        # (first, words, cov, edges) of the decoded block the iterator is in
@@ -210,6 +211,7 @@ class CortexGraph:
         h = N._P()
         N.check(N.lib().cc_open_device(dev_ptr, kmerSize, getKmerBits(kmerSize), numColors, numRecords, firstIndex, device, C.byref(h)))
         self._h, self._device, self._keep, self.cortexFile = h, device, keepalive, None
+        self.firstIndex = firstIndex
         self._load_header()
         self.recordsSeen = 0
         self._block = None
@@ -376,7 +378,7 @@ class CortexGraph:
         if i < 0:
             return None
         saved = self._block
-        w, c, e = self.decodeRecords(i, 1)
+        w, c, e = self.decodeRecords(i - self.firstIndex, 1)
         self._block = saved
         return self._make_record(w[0], c[0], e[0])
 

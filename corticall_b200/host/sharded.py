@@ -66,24 +66,43 @@ class ShardedLookup:
         self.splitters = splitters.contiguous() if splitters is not None else None
         self.ops = ops if ops is not None else CudaOps(graph, device)
         self.last = {}
+        self.profile = False          # True: record per-phase device times (CUDA events) into self.last["phase_ms"]
 
     def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
         """words int64 [nq, s] canonical packed queries (this rank's part of the batch), flags uint8 [nq] or None
         (bit1/bit2 set = cannot match), out int64 [nq] receives the GLOBAL record index or -1."""
         world = self.world
+        marks = []
+
+        def mark(name):
+            if self.profile and words.is_cuda:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         out.fill_(-1)                                     # flagged queries are never routed
         counts, sorted_words, slots = self.ops.bucket(words, flags, self.splitters, world)
+        mark("bucket")
         recv_counts = torch.empty_like(counts)
         dist.all_to_all_single(recv_counts, counts, group=self.group)
         send = counts.tolist()                            # host needs the split sizes
         recv = recv_counts.tolist()
+        mark("counts")
         n_send, n_recv = sum(send), sum(recv)
         s = words.shape[1]
         inbox = torch.empty((n_recv, s), dtype=words.dtype, device=words.device)
         dist.all_to_all_single(inbox, sorted_words[:n_send], output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        mark("route")
         found = self.ops.search(inbox)
+        mark("search")
         back = torch.empty(n_send, dtype=torch.int64, device=words.device)
         dist.all_to_all_single(back, found, output_split_sizes=send, input_split_sizes=recv, group=self.group)
+        mark("return")
         self.ops.scatter(back, slots[:n_send], out)
+        mark("scatter")
         self.last = {"sent": send, "received": recv}
+        if marks:
+            torch.cuda.synchronize()
+            self.last["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
         return out

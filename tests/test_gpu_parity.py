@@ -365,3 +365,56 @@ def test_bucket_by_owner_and_scatter(nshards):
     exp = np.full(nq, -1, dtype=np.int64)
     exp[got_slots] = np.arange(tot) * 3 + 1
     assert (out.cpu().numpy() == exp).all()
+
+
+# ------------------------------------------------------------------ the callers: FindROIs.execute and the Call helpers
+
+def test_findrois_command_and_call_helpers(tmp_path):
+    """FindROIs -g trio.ctx -p mom -p dad -c child -o rois.ctx, then Call's loadRois / loadChildWalk / getRegions /
+    section ROI set on contigs, each against the oracle's per-window findRecord and a Python set of ROI k-mers."""
+    k, c, n = 31, 4, 40000
+    ctx = synth.make_ctx_file(99, n, k, c, novel_permille=40, adv_period=211)
+    path = tmp_path / "trio.ctx"
+    path.write_bytes(ctx)
+    graph = cb.CortexGraph(path)
+    out = tmp_path / "rois.ctx"
+    cmd = cb.FindROIs(graph, ["mom", "dad", "REF"], "Child", out)            # names are matched case-insensitively
+    nn = cmd.execute()
+    og = orc.Graph(ctx)
+    want, widx = og.find_rois(0, [1, 2, 3])
+    assert nn == len(widx) and out.read_bytes() == orc.roi_header(k, 1, "child") + want
+    with pytest.raises(cb.CortexJDKException):                               # unknown sample -> colour -1 -> Java AIOOBE
+        cb.FindROIs(graph, ["mom", "nobody"], "child", tmp_path / "x.ctx").execute()
+
+    rois = cb.CallHelpers.loadRois(cb.CortexGraph(out))
+    roi_set = {cr.getKmerAsString() for cr in rois}
+    assert len(roi_set) == nn
+    # a contig: stitched from graph k-mers (so many windows hit), with an N and a lower-case stretch
+    words, _, _ = graph.decodeRecords(0, n)
+    kmers = [graph._make_record(words[i], [0] * c, [0] * c).getKmerAsString() for i in list(widx[:40].astype(int)) + list(range(0, 400, 7))]
+    contig = "".join(kmers[:60])
+    contig = contig[:500] + "N" + contig[501:900] + contig[900:960].lower() + contig[960:]
+    walk = cb.CallHelpers.loadChildWalk(contig, graph)
+    want_idx = og.find_windows(contig.encode())
+    assert [v.recordIndex for v in walk] == want_idx.tolist()
+    seen = {}
+    for i, v in enumerate(walk):
+        sk = contig[i:i + k]
+        seen[sk] = seen[sk] + 1 if sk in seen else 0
+        assert v.bases == sk and v.copyIndex == seen[sk]
+        if want_idx[i] >= 0:
+            assert v.record.getKmerAsString() == cb.CanonicalKmer(sk).getKmerAsString()
+        else:
+            assert v.record is None
+    canon = [cb.SequenceUtils.alphanumericallyLowestOrientation(contig[i:i + k]) for i in range(len(contig) - k + 1)]
+    member = [x in roi_set for x in canon]
+    assert rois.containsWindows(contig).tolist() == member
+    regions, start = [], -1
+    for i, m in enumerate(member + [False]):
+        if m and start < 0:
+            start = i
+        if not m and start >= 0:
+            regions.append((start, i - 1)); start = -1
+    assert cb.CallHelpers.getRegions(rois, contig) == regions and len(regions) > 0
+    assert [x.getKmerAsString() for x in cb.CallHelpers.sectionRois(rois, contig)] == sorted({x for x, m in zip(canon, member) if m})
+    graph.dispose(); rois.dispose()
