@@ -194,6 +194,14 @@ int init_handle(cc_graph *g, int device) {
     CC_CUDA(cudaEventCreate(&g->ev0));
     CC_CUDA(cudaEventCreate(&g->ev1));
     CC_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device));
+    // Scratch for batched lookups comes from the stream-ordered pool; keep freed blocks cached instead of
+    // returning them to the driver at every synchronisation (re-mapping gigabytes per call costs milliseconds).
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     return CC_OK;
 }
 
@@ -332,6 +340,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "scan_ctas_per_sm")) o.scan_ctas_per_sm = (int)value;
     else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
     else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
+    else if (!strcmp(name, "lookup_queries_per_thread")) o.lookup_queries_per_thread = (int)value;
     else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;
     else if (!strcmp(name, "scan_debug")) o.scan_debug = (int)value;
     else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;

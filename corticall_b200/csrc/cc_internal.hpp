@@ -33,6 +33,7 @@ struct Options {
     int scan_ctas_per_sm = 2;
     int index_bits = 0;          // 0 = auto
     int lookup_block = 256;
+    int lookup_queries_per_thread = 2;   // 0 = the single-query kernel
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
     int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)

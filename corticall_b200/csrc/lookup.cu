@@ -277,6 +277,63 @@ __global__ void __launch_bounds__(kBlock) find_packed_kernel(const uint64_t *__r
     }
 }
 
+// The bucketed search with Q queries in flight per thread: all table reads are issued, then the first kProbe keys of
+// every bucket (independent loads), and only buckets longer than kProbe (rare at ~1 key per bucket) take the general
+// search on their remainder.  Lookups are latency-bound (two dependent random sectors each), so throughput follows the
+// number of independent loads in flight.
+constexpr uint32_t kProbe = 4;
+
+template <int S, int Q>
+__global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
+                                                                 uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
+    const uint64_t span = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t base = (uint64_t)blockIdx.x * kBlock + threadIdx.x; base < nq; base += span * Q) {
+        uint64_t q[Q][S];
+        uint32_t lo[Q], hi[Q];
+        bool live[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const uint64_t i = base + (uint64_t)j * span;
+            live[j] = i < nq;
+            if (live[j]) {
+                load_key<S>(words, i, q[j]);
+                if (flags && (flags[i] & 6u)) live[j] = false, out_index[i] = -1;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            lo[j] = hi[j] = 0;
+            if (live[j]) {
+                const uint32_t p = key_prefix<S>(q[j], ix.shift);
+                lo[j] = __ldg(ix.table + p);
+                hi[j] = __ldg(ix.table + p + 1);
+            }
+        }
+        uint64_t kk[Q][kProbe][S];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+#pragma unroll
+            for (uint32_t t = 0; t < kProbe; ++t) {
+                if (live[j] && lo[j] + t < hi[j]) load_key<S>(ix.keys, (uint64_t)lo[j] + t, kk[j][t]);
+                else {
+#pragma unroll
+                    for (int w = 0; w < S; ++w) kk[j][t][w] = ~0ull;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            if (!live[j]) continue;
+            int64_t r = -1;
+#pragma unroll
+            for (int t = (int)kProbe - 1; t >= 0; --t)
+                if (lo[j] + (uint32_t)t < hi[j] && words_equal<S>(kk[j][t], q[j])) r = (int64_t)lo[j] + t;
+            if (r < 0 && hi[j] - lo[j] > kProbe) r = search_range<S>(ix.keys, (uint64_t)lo[j] + kProbe, hi[j], q[j]);
+            out_index[base + (uint64_t)j * span] = r < 0 ? r : r + (int64_t)ix.first_index;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ index construction
 template <int S>
 __global__ void check_sorted_kernel(const uint64_t *__restrict__ keys, uint64_t n, unsigned long long *unsorted_at) {
@@ -486,6 +543,17 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
         cudaFreeAsync(words, st); cudaFreeAsync(flags, st);
         return rc;
     }
+    if (row_stride > 1 && nq >= (1u << 16)) {
+        // Independent rows cost k bytes of staging per query, which leaves the fused kernel at half occupancy for the
+        // latency-bound search; for large batches pack first (streaming), then search at full occupancy.
+        uint64_t *words = nullptr; uint8_t *flags = nullptr;
+        CC_CUDA(cudaMallocAsync(&words, nq * g->h.s * sizeof(uint64_t), st));
+        CC_CUDA(cudaMallocAsync(&flags, nq, st));
+        int rc = launch_pack_windows(dev_seq, 0, g->h.k, words, flags, row_stride, nq, st);
+        if (!rc) rc = launch_find_packed(g, words, flags, nq, dev_index, algo, st);
+        cudaFreeAsync(words, st); cudaFreeAsync(flags, st);
+        return rc;
+    }
     SeqJob job = make_job(dev_seq, nq, row_stride, g->h.k);
     const int grid = grid_for((nq + job.per_tile - 1) / job.per_tile, 1, g->sm_count, 6);
     IndexView ix = view_of(g);
@@ -537,7 +605,12 @@ int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *de
         CC_DISPATCH_S(s, find_packed_kernel<S_, false><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index));
         count_launch();
     } else {
-        CC_DISPATCH_S(s, find_packed_kernel<S_, true><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index));
+        const int qpt = options().lookup_queries_per_thread;
+        const int g2 = grid_for((nq + std::max(qpt, 1) - 1) / std::max(qpt, 1), kBlock, g->sm_count, 8);
+        if (qpt >= 4) { CC_DISPATCH_S(s, find_packed_mlp_kernel<S_, 4><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
+        else if (qpt >= 2) { CC_DISPATCH_S(s, find_packed_mlp_kernel<S_, 2><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
+        else if (qpt == 1) { CC_DISPATCH_S(s, find_packed_mlp_kernel<S_, 1><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
+        else { CC_DISPATCH_S(s, find_packed_kernel<S_, true><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
         count_launch();
     }
     CC_CUDA(cudaGetLastError());
@@ -557,10 +630,11 @@ int build_index(cc_graph *g, int bits_req) {
 
     int bits = bits_req > 0 ? bits_req : options().index_bits;
     if (bits <= 0) {
+        // about one key per bucket: a lookup is then one table sector plus one key sector (measured on B200 at
+        // n = 1e8: 2^24 buckets 1.2e10 lookups/s, 2^26 1.9e10; the table costs 4 bytes per bucket next to 8s per key)
         int lg = 0;
         while ((1ull << lg) < std::max<uint64_t>(n, 1)) ++lg;
-        bits = std::max(1, lg - 3);
-        bits = std::min(bits, 26);
+        bits = std::max(1, lg);
     }
     bits = std::min<int>(bits, (int)std::min<uint32_t>(2u * k, 30u));
     ix.bits = bits;
