@@ -390,15 +390,23 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         out["algorithmic_bytes_per_lookup"] = bpl
         out["algorithmic_gb_per_s"] = out["lookups_per_s"] * bpl / 1e9
     else:
-        sl = ShardedLookup(g, splitters, rank, world, dev)
-        ms = timeit(lambda: sl.find_packed(qwords, qflags, res))
+        from corticall_b200.host.sharded import RoutedLookup
+        rl = RoutedLookup(g, splitters, rank, world, dev, cap=nq, s=S_WORDS)
+        ms = timeit(lambda: rl.find_packed(qwords, qflags, res))
         out["lookups_per_s"] = nq * world / (ms / 1000.0)
         out["ms_per_step"] = ms
-        out["exchange"] = "bucket by owner (cc_bucket_by_owner_dev) -> all_to_all_single (NCCL) -> local search -> all_to_all_single -> scatter"
+        out["exchange"] = ("peer memory over NVLink, one kernel per leg: route (owner + P2P store into the owner's inbox) -> barrier -> "
+                           "search (P2P store of results into the origin) -> barrier -> gather")
         out["hit_fraction"] = float((res >= 0).sum().item()) / nq
+        # the NCCL all-to-all formulation of the same exchange, as the comparison and as a cross-check of the results
+        sl = ShardedLookup(g, splitters, rank, world, dev)
+        res2 = torch.empty_like(res)
+        ms2 = timeit(lambda: sl.find_packed(qwords, qflags, res2))
+        out["nccl_all_to_all_lookups_per_s"] = nq * world / (ms2 / 1000.0)
+        out["paths_agree"] = bool(torch.equal(res, res2))
         sl.profile = True
-        sl.find_packed(qwords, qflags, res)
-        out["phase_ms_rank0"] = sl.last.get("phase_ms")
+        sl.find_packed(qwords, qflags, res2)
+        out["nccl_phase_ms_rank0"] = sl.last.get("phase_ms")
     g.dispose()
     return out
 

@@ -77,6 +77,9 @@ SIGNATURES = {
     "cc_contains_windows": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "cc_bucket_by_owner_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint32, _P, C.c_int, _P, _P, _P, _P]),
     "cc_scatter_results_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, _P, _P]),
+    "cc_route_queries_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint32, _P, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, _P, _P]),
+    "cc_find_routed_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_uint64, _P, _P]),
+    "cc_gather_routed_dev": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint64, _P, _P]),
     "cc_last_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "cc_launch_count": (C.c_uint64, []),
     "cc_device_body": (C.c_int, [_P, C.POINTER(_P), _U64P]),

@@ -898,6 +898,34 @@ int cc_scatter_results_dev(int device, const int64_t *dev_values, const uint32_t
     return launch_scatter_results(dev_values, dev_slots, n, dev_out, static_cast<cudaStream_t>(stream));
 }
 
+// ---- routed lookups over peer memory (NVLink P2P): no collective library on the data path
+int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
+                         const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap, void *const *peer_inbox,
+                         void *const *peer_counts_in, uint32_t *dev_slots, uint64_t *dev_sent, int64_t *dev_out, void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (!peer_inbox || !peer_counts_in || !dev_sent || (nq && (!dev_words || !dev_slots || !dev_out)) || (nshards > 1 && !dev_splitters))
+        return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_route(dev_words, dev_flags, nq, s, dev_splitters, nshards, my_rank, cap, peer_inbox, peer_counts_in, dev_slots, dev_sent,
+                        dev_out, static_cast<cudaStream_t>(stream));
+}
+
+int cc_find_routed_dev(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+                       void *const *peer_ret, void *stream) {
+    if (!g || !dev_inbox || !dev_counts_in || !peer_ret) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    return launch_find_routed(g, dev_inbox, dev_counts_in, nshards, my_rank, cap, peer_ret, static_cast<cudaStream_t>(stream));
+}
+
+int cc_gather_routed_dev(int device, const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
+                         int64_t *dev_out, void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (!dev_ret || !dev_slots || !dev_sent || !dev_out) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_gather_routed(dev_ret, dev_slots, dev_sent, nshards, cap, dev_out, static_cast<cudaStream_t>(stream));
+}
+
 // ==================================================================== instrumentation
 int cc_last_stats(const cc_graph *g, cc_stats *out) {
     if (!g || !out) return fail(CC_ERR_ARG, "null argument");

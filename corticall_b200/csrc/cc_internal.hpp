@@ -146,5 +146,12 @@ int launch_bucket_by_owner(const uint64_t *dev_words, const uint8_t *dev_flags, 
                            const uint64_t *dev_splitters, int nshards, uint64_t *dev_counts, uint64_t *dev_sorted_words,
                            uint32_t *dev_slots, cudaStream_t st);
 int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n, int64_t *dev_out, cudaStream_t st);
+int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s, const uint64_t *dev_splitters, int nshards,
+                 int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, uint32_t *dev_slots, uint64_t *dev_sent,
+                 int64_t *dev_out, cudaStream_t st);
+int launch_find_routed(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+                       void *const *peer_ret, cudaStream_t st);
+int launch_gather_routed(const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
+                         int64_t *dev_out, cudaStream_t st);
 
 }  // namespace cc

@@ -183,6 +183,7 @@ __device__ __forceinline__ uint32_t key_prefix(const uint64_t (&q)[S], uint32_t 
     return (uint32_t)low;
 }
 
+constexpr int kMaxShards = 64;
 constexpr uint32_t kLinear = 8;     // bucket remainder scanned with independent loads
 
 // Index of the exact match of q in keys[lo, hi) (lowest on duplicates), or -1.
@@ -283,14 +284,51 @@ __global__ void __launch_bounds__(kBlock) find_packed_kernel(const uint64_t *__r
 // number of independent loads in flight.
 constexpr uint32_t kProbe = 4;
 
+// Q queries per thread: table reads for all, then the first kProbe keys of every bucket, then compare.
+template <int S, int Q>
+__device__ __forceinline__ void lookup_mlp(const IndexView &ix, const uint64_t (&q)[Q][S], const bool (&live)[Q], int64_t (&r)[Q]) {
+    uint32_t lo[Q], hi[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        lo[j] = hi[j] = 0;
+        if (live[j]) {
+            const uint32_t p = key_prefix<S>(q[j], ix.shift);
+            lo[j] = __ldg(ix.table + p);
+            hi[j] = __ldg(ix.table + p + 1);
+        }
+    }
+    uint64_t kk[Q][kProbe][S];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+#pragma unroll
+        for (uint32_t t = 0; t < kProbe; ++t) {
+            if (live[j] && lo[j] + t < hi[j]) load_key<S>(ix.keys, (uint64_t)lo[j] + t, kk[j][t]);
+            else {
+#pragma unroll
+                for (int w = 0; w < S; ++w) kk[j][t][w] = ~0ull;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        r[j] = -1;
+        if (!live[j]) continue;
+#pragma unroll
+        for (int t = (int)kProbe - 1; t >= 0; --t)
+            if (lo[j] + (uint32_t)t < hi[j] && words_equal<S>(kk[j][t], q[j])) r[j] = (int64_t)lo[j] + t;
+        if (r[j] < 0 && hi[j] - lo[j] > kProbe) r[j] = search_range<S>(ix.keys, (uint64_t)lo[j] + kProbe, hi[j], q[j]);
+        if (r[j] >= 0) r[j] += (int64_t)ix.first_index;
+    }
+}
+
 template <int S, int Q>
 __global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
                                                                  uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
     const uint64_t span = (uint64_t)gridDim.x * kBlock;
     for (uint64_t base = (uint64_t)blockIdx.x * kBlock + threadIdx.x; base < nq; base += span * Q) {
         uint64_t q[Q][S];
-        uint32_t lo[Q], hi[Q];
         bool live[Q];
+        int64_t r[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint64_t i = base + (uint64_t)j * span;
@@ -300,37 +338,147 @@ __global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t 
                 if (flags && (flags[i] & 6u)) live[j] = false, out_index[i] = -1;
             }
         }
+        lookup_mlp<S, Q>(ix, q, live, r);
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            lo[j] = hi[j] = 0;
-            if (live[j]) {
-                const uint32_t p = key_prefix<S>(q[j], ix.shift);
-                lo[j] = __ldg(ix.table + p);
-                hi[j] = __ldg(ix.table + p + 1);
-            }
-        }
-        uint64_t kk[Q][kProbe][S];
+        for (int j = 0; j < Q; ++j)
+            if (live[j]) out_index[base + (uint64_t)j * span] = r[j];
+    }
+}
+
+template <int S>
+__device__ __forceinline__ uint32_t owner_of(const uint64_t (&q)[S], const uint64_t *__restrict__ splitters, int nshards) {
+    // number of splitters <= q  (splitter j = first key of shard j+1)
+    uint32_t lo = 0, hi = (uint32_t)(nshards - 1);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        uint64_t sp[S];
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
+        for (int w = 0; w < S; ++w) sp[w] = splitters[mid * S + w];
+        if (words_less<S>(q, sp)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------ multi-GPU: routed lookups over peer memory
+// One kernel per leg, each fused with its transfer (no NCCL on the data path; buffers are peer-mapped over NVLink):
+//   route   owner of every query (splitter search) + block-aggregated reservation + P2P STORE of the key into the
+//           owner's inbox segment reserved for this rank; the original slot is kept locally
+//   search  the owner walks all inbox segments, searches its shard and P2P-STORES each result into the origin's
+//           return buffer at the same segment position
+//   gather  the origin scatters the returned indices to the original slots (local)
+constexpr int kRouteQ = 8;                   // queries per thread per tile of the route kernel
+
+struct PeerPtrs {
+    void *p[kMaxShards];
+};
+
+template <int S>
+__global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
+                                                       const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
+                                                       PeerPtrs inbox, uint32_t *__restrict__ slots, unsigned long long *cursors,
+                                                       int64_t *__restrict__ out) {
+    __shared__ uint32_t hist[kMaxShards];
+    __shared__ unsigned long long base[kMaxShards];
+    const uint64_t tile_q = (uint64_t)kBlock * kRouteQ;
+    const uint64_t ntiles = (nq + tile_q - 1) / tile_q;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i < nshards; i += kBlock) hist[i] = 0;
+        __syncthreads();
+        uint64_t q[kRouteQ][S];
+        uint32_t own[kRouteQ], rank_in[kRouteQ];
 #pragma unroll
-            for (uint32_t t = 0; t < kProbe; ++t) {
-                if (live[j] && lo[j] + t < hi[j]) load_key<S>(ix.keys, (uint64_t)lo[j] + t, kk[j][t]);
+        for (int j = 0; j < kRouteQ; ++j) {
+            const uint64_t i = tile * tile_q + (uint64_t)j * kBlock + threadIdx.x;
+            own[j] = 0xffffffffu;
+            if (i < nq) {
+                if (flags && (flags[i] & 6u)) out[i] = -1;           // never routed: cannot match
                 else {
-#pragma unroll
-                    for (int w = 0; w < S; ++w) kk[j][t][w] = ~0ull;
+                    load_key<S>(words, i, q[j]);
+                    own[j] = owner_of<S>(q[j], splitters, nshards);
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            if (!live[j]) continue;
-            int64_t r = -1;
+        for (int j = 0; j < kRouteQ; ++j)
+            if (own[j] != 0xffffffffu) rank_in[j] = atomicAdd(&hist[own[j]], 1u);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nshards; i += kBlock) base[i] = hist[i] ? atomicAdd(&cursors[i], (unsigned long long)hist[i]) : 0ull;
+        __syncthreads();
 #pragma unroll
-            for (int t = (int)kProbe - 1; t >= 0; --t)
-                if (lo[j] + (uint32_t)t < hi[j] && words_equal<S>(kk[j][t], q[j])) r = (int64_t)lo[j] + t;
-            if (r < 0 && hi[j] - lo[j] > kProbe) r = search_range<S>(ix.keys, (uint64_t)lo[j] + kProbe, hi[j], q[j]);
-            out_index[base + (uint64_t)j * span] = r < 0 ? r : r + (int64_t)ix.first_index;
+        for (int j = 0; j < kRouteQ; ++j) {
+            if (own[j] == 0xffffffffu) continue;
+            const uint64_t pos = base[own[j]] + rank_in[j];
+            if (pos < cap) {
+                uint64_t *dst = static_cast<uint64_t *>(inbox.p[own[j]]) + ((uint64_t)my_rank * cap + pos) * S;
+                if (S == 2) *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(q[j][0], q[j][1 % S]);
+                else {
+#pragma unroll
+                    for (int w = 0; w < S; ++w) dst[w] = q[j][w];
+                }
+                slots[(uint64_t)own[j] * cap + pos] = (uint32_t)(tile * tile_q + (uint64_t)j * kBlock + threadIdx.x);
+            }
         }
+        __syncthreads();
+    }
+    __threadfence_system();
+}
+
+// counts_in[my_rank] on every owner := number of keys this rank routed to it (P2P stores of 8 bytes)
+__global__ void publish_counts_kernel(const unsigned long long *cursors, int nshards, int my_rank, uint64_t cap, PeerPtrs counts_in) {
+    const int o = threadIdx.x;
+    if (o < nshards) {
+        const unsigned long long c = cursors[o] < cap ? cursors[o] : cap;
+        static_cast<unsigned long long *>(counts_in.p[o])[my_rank] = c;
+    }
+    __threadfence_system();
+}
+
+template <int S, int Q>
+__global__ void __launch_bounds__(kBlock) find_routed_kernel(const uint64_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
+                                                             int nshards, int my_rank, uint64_t cap, IndexView ix, PeerPtrs ret) {
+    __shared__ unsigned long long pre[kMaxShards + 1];
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < nshards; ++i) { pre[i] = acc; acc += counts_in[i]; }
+        pre[nshards] = acc;
+    }
+    __syncthreads();
+    const uint64_t total = pre[nshards];
+    const uint64_t span = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t basei = (uint64_t)blockIdx.x * kBlock + threadIdx.x; basei < total; basei += span * Q) {
+        uint64_t q[Q][S];
+        bool live[Q];
+        int64_t r[Q];
+        uint32_t src[Q];
+        uint64_t pos[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const uint64_t f = basei + (uint64_t)j * span;
+            live[j] = f < total;
+            src[j] = 0; pos[j] = 0;
+            if (live[j]) {
+                uint32_t sgm = 0;
+                while (sgm + 1 < (uint32_t)nshards && f >= pre[sgm + 1]) ++sgm;
+                src[j] = sgm;
+                pos[j] = f - pre[sgm];
+                load_key<S>(inbox, (uint64_t)sgm * cap + pos[j], q[j]);
+            }
+        }
+        lookup_mlp<S, Q>(ix, q, live, r);
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (live[j]) static_cast<int64_t *>(ret.p[src[j]])[(uint64_t)my_rank * cap + pos[j]] = r[j];
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(kBlock) gather_routed_kernel(const int64_t *__restrict__ ret, const uint32_t *__restrict__ slots,
+                                                               const unsigned long long *__restrict__ sent, int nshards, uint64_t cap,
+                                                               int64_t *__restrict__ out) {
+    for (int o = 0; o < nshards; ++o) {
+        const uint64_t n = sent[o] < cap ? sent[o] : cap;
+        for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock)
+            out[slots[(uint64_t)o * cap + i]] = ret[(uint64_t)o * cap + i];
     }
 }
 
@@ -385,22 +533,6 @@ __global__ void __launch_bounds__(kBlock) find_sorted_kernel(const uint64_t *__r
 }
 
 // ------------------------------------------------------------------ multi-GPU helpers
-template <int S>
-__device__ __forceinline__ uint32_t owner_of(const uint64_t (&q)[S], const uint64_t *__restrict__ splitters, int nshards) {
-    // number of splitters <= q  (splitter j = first key of shard j+1)
-    uint32_t lo = 0, hi = (uint32_t)(nshards - 1);
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        uint64_t sp[S];
-#pragma unroll
-        for (int w = 0; w < S; ++w) sp[w] = splitters[mid * S + w];
-        if (words_less<S>(q, sp)) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-constexpr int kMaxShards = 64;
-
 template <int S>
 __global__ void __launch_bounds__(kBlock) owner_count_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
                                                              const uint64_t *__restrict__ splitters, int nshards,
@@ -689,6 +821,54 @@ int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots,
     if (n == 0) return CC_OK;
     const int grid = grid_for(n, 256, sm_count_now(), 8);
     scatter_results_kernel<<<grid, 256, 0, st>>>(dev_values, dev_slots, n, dev_out);
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+// ------------------------------------------------------------------ routed lookups (peer memory) launchers
+int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s, const uint64_t *dev_splitters, int nshards,
+                 int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, uint32_t *dev_slots, uint64_t *dev_sent,
+                 int64_t *dev_out, cudaStream_t st) {
+    if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
+    if (my_rank < 0 || my_rank >= nshards) return fail(CC_ERR_ARG, "rank %d out of range", my_rank);
+    if (nq >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "routed batches are limited to 2^32-1 queries per rank");
+    PeerPtrs inbox{}, counts{};
+    for (int i = 0; i < nshards; ++i) { inbox.p[i] = peer_inbox[i]; counts.p[i] = peer_counts[i]; }
+    unsigned long long *cursors = reinterpret_cast<unsigned long long *>(dev_sent);
+    CC_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * nshards, st));
+    if (nq) {
+        const int grid = grid_for((nq + (uint64_t)kBlock * kRouteQ - 1) / ((uint64_t)kBlock * kRouteQ), 1, sm_count_now(), 4);
+        CC_DISPATCH_S(s, route_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox,
+                                                                    dev_slots, cursors, dev_out));
+        count_launch();
+    }
+    publish_counts_kernel<<<1, kMaxShards, 0, st>>>(cursors, nshards, my_rank, cap, counts);
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_find_routed(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+                       void *const *peer_ret, cudaStream_t st) {
+    if (int rc = check_k(g->h.k)) return rc;
+    if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
+    PeerPtrs ret{};
+    for (int i = 0; i < nshards; ++i) ret.p[i] = peer_ret[i];
+    IndexView ix = view_of(g);
+    const int grid = g->sm_count * 8;
+    CC_DISPATCH_S(g->h.s, find_routed_kernel<S_, 2><<<grid, kBlock, 0, st>>>(dev_inbox, reinterpret_cast<const unsigned long long *>(dev_counts_in),
+                                                                             nshards, my_rank, cap, ix, ret));
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_gather_routed(const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
+                         int64_t *dev_out, cudaStream_t st) {
+    if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
+    gather_routed_kernel<<<sm_count_now() * 8, kBlock, 0, st>>>(dev_ret, dev_slots, reinterpret_cast<const unsigned long long *>(dev_sent),
+                                                                nshards, cap, dev_out);
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;

@@ -106,3 +106,85 @@ class ShardedLookup:
             torch.cuda.synchronize()
             self.last["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
         return out
+
+
+class RoutedLookup:
+    """The same sharded lookup with NO collective library on the data path: every leg is one kernel fused with its
+    transfer over peer-mapped memory (NVLink P2P stores):
+
+        cc_route_queries_dev  owner search + block-aggregated reservation + store of each key straight into the owner's
+                              inbox segment for this rank (slots stay local)
+        barrier               (symmetric-memory signal pads; orders the peer stores)
+        cc_find_routed_dev    the owner searches every inbox segment and stores each result straight into the origin's
+                              return buffer, same segment position
+        barrier
+        cc_gather_routed_dev  the origin scatters the returned indices to the original slots
+
+    The host never reads a count, so the whole batch is asynchronous on the current stream.  Buffers are one symmetric
+    allocation per rank (torch.distributed._symmetric_memory: plumbing only).  `cap` is the capacity of one
+    (source, owner) segment; a rank can route at most `cap` queries to one owner per batch (worst case = its batch size).
+    """
+
+    def __init__(self, graph, splitters, rank: int, world: int, device, cap: int, s: int, group=None, emulate=None):
+        import ctypes as C
+        self.g, self.rank, self.world, self.cap, self.s = graph, rank, world, int(cap), int(s)
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.splitters = splitters.contiguous() if splitters is not None else None
+        # layout of the symmetric block, in int64 elements
+        self.off_inbox = 0
+        self.off_ret = world * self.cap * self.s
+        self.off_counts = self.off_ret + world * self.cap
+        total = self.off_counts + max(world, 8)
+        if emulate is None:
+            import torch.distributed._symmetric_memory as symm
+            self.block = symm.empty(total, dtype=torch.int64, device=device)
+            self.hdl = symm.rendezvous(self.block, (group or dist.group.WORLD).group_name)
+            bases = [int(p) for p in self.hdl.buffer_ptrs]
+        else:                                   # single-process emulation of all ranks on one device (tests)
+            self.block = emulate[rank]
+            self.hdl = None
+            bases = [int(t.data_ptr()) for t in emulate]
+        self.block.zero_()
+        arr = C.c_void_p * world
+        self.p_inbox = arr(*[b + 8 * self.off_inbox for b in bases])
+        self.p_ret = arr(*[b + 8 * self.off_ret for b in bases])
+        self.p_counts = arr(*[b + 8 * self.off_counts for b in bases])
+        self.slots = torch.empty(world * self.cap, dtype=torch.int32, device=device)
+        self.sent = torch.zeros(max(world, 8), dtype=torch.int64, device=device)
+
+    @staticmethod
+    def block_elems(world: int, cap: int, s: int) -> int:
+        return world * cap * s + world * cap + max(world, 8)
+
+    def _barrier(self):
+        if self.hdl is not None:
+            self.hdl.barrier()
+
+    def route(self, words, flags, out):
+        if words.shape[0] > self.cap:
+            raise ValueError("batch of %d queries exceeds the segment capacity %d" % (words.shape[0], self.cap))
+        st = torch.cuda.current_stream().cuda_stream
+        N.check(N.lib().cc_route_queries_dev(self.index, words.data_ptr(), flags.data_ptr() if flags is not None else None,
+                                             words.shape[0], self.s, self.splitters.data_ptr() if self.splitters is not None else None,
+                                             self.world, self.rank, self.cap, self.p_inbox, self.p_counts,
+                                             self.slots.data_ptr(), self.sent.data_ptr(), out.data_ptr(), st))
+
+    def search(self):
+        st = torch.cuda.current_stream().cuda_stream
+        base = self.block.data_ptr()
+        N.check(N.lib().cc_find_routed_dev(self.g._h, base + 8 * self.off_inbox, base + 8 * self.off_counts, self.world, self.rank,
+                                           self.cap, self.p_ret, st))
+
+    def gather(self, out):
+        st = torch.cuda.current_stream().cuda_stream
+        N.check(N.lib().cc_gather_routed_dev(self.index, self.block.data_ptr() + 8 * self.off_ret, self.slots.data_ptr(),
+                                             self.sent.data_ptr(), self.world, self.cap, out.data_ptr(), st))
+
+    def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
+        self.route(words, flags, out)
+        self._barrier()
+        self.search()
+        self._barrier()
+        self.gather(out)
+        return out

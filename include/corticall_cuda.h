@@ -186,6 +186,24 @@ CC_API int cc_bucket_by_owner_dev(int device, const uint64_t *dev_words, const u
 CC_API int cc_scatter_results_dev(int device, const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n,
                                   int64_t *dev_out, void *stream);
 
+/* Routed lookups over PEER MEMORY (NVLink P2P; buffers are symmetric allocations mapped into every rank, e.g. with
+ * torch.distributed._symmetric_memory or cudaIpc): each leg is one kernel fused with its transfer, no collective
+ * library on the data path.  Layout, identical on every rank (cap = capacity of one (source, owner) segment):
+ *   inbox     uint64 [nshards][cap][s]  on the OWNER : keys routed to it, segment = source rank
+ *   counts_in uint64 [nshards]          on the OWNER : keys in each segment
+ *   ret       int64  [nshards][cap]     on the ORIGIN: results, segment = owner rank, same positions as sent
+ *   slots     uint32 [nshards][cap], sent uint64 [nshards]   local to the origin
+ * Order of use per batch on one stream: cc_route_queries_dev -> cross-rank barrier -> cc_find_routed_dev -> barrier ->
+ * cc_gather_routed_dev.  peer_* are HOST arrays of nshards DEVICE pointers (entry r = rank r's buffer; own rank = local). */
+CC_API int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
+                                const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap,
+                                void *const *peer_inbox, void *const *peer_counts_in,
+                                uint32_t *dev_slots, uint64_t *dev_sent, int64_t *dev_out /* flagged queries get -1 here */, void *stream);
+CC_API int cc_find_routed_dev(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank,
+                              uint64_t cap, void *const *peer_ret, void *stream);
+CC_API int cc_gather_routed_dev(int device, const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards,
+                                uint64_t cap, int64_t *dev_out, void *stream);
+
 /* ---------------------------------------------------------------- instrumentation */
 CC_API int cc_last_stats(const cc_graph *g, cc_stats *out);
 /* Total kernels this library has launched in this process (bench.py's gpu_launches). */

@@ -418,3 +418,56 @@ def test_findrois_command_and_call_helpers(tmp_path):
     assert cb.CallHelpers.getRegions(rois, contig) == regions and len(regions) > 0
     assert [x.getKmerAsString() for x in cb.CallHelpers.sectionRois(rois, contig)] == sorted({x for x, m in zip(canon, member) if m})
     graph.dispose(); rois.dispose()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_routed_lookup_emulated_ranks(world):
+    """The peer-memory lookup path (route -> search -> gather) with all ranks emulated on one device: plain device
+    tensors stand in for the symmetric allocations (every 'peer pointer' is a local pointer) and the legs of all ranks
+    run one after another on one stream, which is exactly the ordering the cross-rank barriers enforce."""
+    from corticall_b200.host.sharded import RoutedLookup
+    k, c, n = 47, 4, 60000
+    ctx = synth.make_ctx_file(31, n, k, c, adv_period=0)
+    og = orc.Graph(ctx)
+    whole = cb.CortexGraph(ctx)
+    words_all, _, _ = whole.decodeRecords(0, n)
+    body = torch.from_numpy(whole.getRawRecords(0, n)).cuda()
+    table = [torch.from_numpy(words_all[:, w].copy().view(np.int64)) for w in range(2)]
+    dev = torch.device("cuda", 0)
+    spl = torch.stack([torch.stack([t[n * r // world] for t in table]) for r in range(1, world)]).cuda() if world > 1 else None
+    nq_per = [5000 + 700 * r for r in range(world)]
+    cap = max(nq_per)
+    blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, 2), dtype=torch.int64, device=dev) for _ in range(world)]
+    shards, rls, qs = [], [], []
+    for r in range(world):
+        lo, hi = n * r // world, n * (r + 1) // world
+        g = cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body)
+        shards.append(g)
+        rls.append(RoutedLookup(g, spl, r, world, dev, cap, 2, emulate=blocks))
+        a, canon, valid = synth.make_queries(200 + r, table, k, nq_per[r], corrupt_permille=25)
+        qs.append((a, torch.stack(canon, dim=1).contiguous().cuda(), torch.where(valid, 0, 2).to(torch.uint8).cuda(),
+                   torch.full((nq_per[r],), -7, dtype=torch.int64, device=dev)))
+    for r in range(world):
+        rls[r].route(qs[r][1], qs[r][2], qs[r][3])
+    for r in range(world):
+        rls[r].search()
+    for r in range(world):
+        rls[r].gather(qs[r][3])
+    torch.cuda.synchronize()
+    for r in range(world):
+        want = og.find_batch(qs[r][0].numpy())
+        assert (qs[r][3].cpu().numpy() == want).all(), r
+        assert int(rls[r].sent[:world].sum()) == int((qs[r][2] == 0).sum())
+    # a second batch through the same buffers (stale segment contents must not leak)
+    for r in range(world):
+        rls[r].route(qs[r][1][:100], qs[r][2][:100], qs[r][3][:100])
+    for r in range(world):
+        rls[r].search()
+    for r in range(world):
+        rls[r].gather(qs[r][3][:100])
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert (qs[r][3][:100].cpu().numpy() == og.find_batch(qs[r][0][:100].numpy())).all()
+    for g in shards:
+        g.dispose()
+    whole.dispose()
