@@ -734,6 +734,9 @@ uint64_t scan_tiles_for(uint64_t n, uint32_t s, uint32_t c) {
 }
 
 int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
+    // cudaMemset runs on the legacy default stream, which the handle's non-blocking stream does not wait for:
+    // settle it before anything on another stream may touch the fresh allocation.
+    bool fresh = false;
     if (!tile_counter) {
         CC_CUDA(cudaMalloc(&tile_counter, 256));
         CC_CUDA(cudaMemset(tile_counter, 0, 256));
@@ -741,6 +744,7 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
         CC_CUDA(cudaMemset(totals, 0, 256));
         CC_CUDA(cudaMalloc(&dev_error, 256));
         CC_CUDA(cudaMemset(dev_error, 0, 256));
+        fresh = true;
     }
     if (ntiles > tile_state_cap) {
         if (tile_state) CC_CUDA(cudaFree(tile_state));
@@ -749,6 +753,7 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
         CC_CUDA(cudaMemset(tile_state, 0, cap * sizeof(uint64_t)));
         tile_state_cap = cap;
         epoch = 0;
+        fresh = true;
     }
     if (nparents > parents_cap) {
         if (parents) CC_CUDA(cudaFree(parents));
@@ -756,6 +761,7 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
         CC_CUDA(cudaMalloc(&parents, cap * sizeof(int32_t)));
         parents_cap = cap;
     }
+    if (fresh) CC_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     return CC_OK;
 }
 
