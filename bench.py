@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--records", type=int, default=25_000_000, help="records per rank (configs[1] = 2.5e7)")
     ap.add_argument("--table", type=int, default=100_000_000, help="lookup table records (configs[2] = 1e8)")
-    ap.add_argument("--queries", type=int, default=1 << 28, help="lookup queries per step (configs[2] names 1e9)")
+    ap.add_argument("--queries", type=int, default=1_000_000_000, help="lookup queries per step, all ranks together (configs[2] = 1e9)")
     ap.add_argument("--no-lookup", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--spinup", type=float, default=1.0, help="seconds of untimed back-to-back scans before warm-up")
@@ -237,7 +237,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     kernel_ms = total_ms / args.steps            # a step is exactly one launch of scan_novel_kernel on this stream
     achieved = alg_bytes / (kernel_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "scan_novel_kernel",
+                "traffic": None, "peak_source": peak_src, "kernel": "scan_novel_fast_kernel (+ no-op redo_chunks_kernel launch)",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_avg": kernel_ms, "kernel_ms_min": per_launch[0],
                 "kernel_ms_median": per_launch[len(per_launch) // 2],
                 "frac_of_nominal_8TBs": achieved / 8000.0}
@@ -398,6 +398,9 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         out["exchange"] = ("peer memory over NVLink, one kernel per leg: route (owner + P2P store into the owner's inbox) -> barrier -> "
                            "search (P2P store of results into the origin) -> barrier -> gather")
         out["hit_fraction"] = float((res >= 0).sum().item()) / nq
+        barrier()
+        rl.find_packed(qwords, qflags, res, profile=True)
+        out["phase_ms_rank0"] = rl.phase_ms
         # the NCCL all-to-all formulation of the same exchange, as the comparison and as a cross-check of the results
         sl = ShardedLookup(g, splitters, rank, world, dev)
         res2 = torch.empty_like(res)

@@ -344,6 +344,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;
     else if (!strcmp(name, "scan_debug")) o.scan_debug = (int)value;
     else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;
+    else if (!strcmp(name, "scan_stage_buf_bytes")) o.scan_stage_buf_bytes = (int)value;
     else if (!strcmp(name, "scan_chunk_tiles")) o.scan_chunk_tiles = (int)value;
     else return fail(CC_ERR_ARG, "unknown option '%s'", name);
     return CC_OK;

@@ -37,6 +37,7 @@ struct Options {
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
     int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)
+    int scan_stage_buf_bytes = 2048;   // fast kernel: staging bytes per consumer warp per chunk parity
     int scan_debug = 0;          // diagnosis only: bit0 = skip the look-back (WRONG output positions)
 };
 Options &options();
@@ -60,6 +61,7 @@ std::vector<uint8_t> make_roi_header(uint32_t k, uint32_t s, const std::string &
 // ------------------------------------------------------------------ device workspace for the scan
 struct ScanWorkspace {
     uint64_t *tile_state = nullptr;   // look-back descriptors
+    uint64_t *dirty_list = nullptr;   // {chunk, prefix} pairs queued by the fast scan for the rewrite kernel
     uint64_t tile_state_cap = 0;
     uint32_t *tile_counter = nullptr; // dynamic tile ticket
     uint64_t *totals = nullptr;       // [0] in, [1] out (ping-pong for chunked scans)

@@ -372,14 +372,21 @@ struct PeerPtrs {
     void *p[kMaxShards];
 };
 
+// Tile of kBlock*kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory so that each
+// owner's run leaves as fully coalesced stores (whole 128-byte lines over NVLink instead of 16-byte fragments).
 template <int S>
 __global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
                                                        const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
                                                        PeerPtrs inbox, uint32_t *__restrict__ slots, unsigned long long *cursors,
                                                        int64_t *__restrict__ out) {
-    __shared__ uint32_t hist[kMaxShards];
+    extern __shared__ __align__(16) uint8_t route_smem[];
+    constexpr uint32_t tile_q = kBlock * kRouteQ;
+    uint64_t *stage_keys = reinterpret_cast<uint64_t *>(route_smem);                       // [tile_q][S], grouped by owner
+    uint32_t *stage_slot = reinterpret_cast<uint32_t *>(route_smem + (size_t)tile_q * S * 8);   // [tile_q]
+    __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1];
     __shared__ unsigned long long base[kMaxShards];
-    const uint64_t tile_q = (uint64_t)kBlock * kRouteQ;
+    __shared__ uint64_t spl[(kMaxShards - 1) * S];
+    for (int i = threadIdx.x; i < (nshards - 1) * S; i += kBlock) spl[i] = splitters[i];
     const uint64_t ntiles = (nq + tile_q - 1) / tile_q;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int i = threadIdx.x; i < nshards; i += kBlock) hist[i] = 0;
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restric
                 if (flags && (flags[i] & 6u)) out[i] = -1;           // never routed: cannot match
                 else {
                     load_key<S>(words, i, q[j]);
-                    own[j] = owner_of<S>(q[j], splitters, nshards);
+                    own[j] = owner_of<S>(q[j], spl, nshards);
                 }
             }
         }
@@ -402,21 +409,33 @@ __global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restric
         for (int j = 0; j < kRouteQ; ++j)
             if (own[j] != 0xffffffffu) rank_in[j] = atomicAdd(&hist[own[j]], 1u);
         __syncthreads();
-        for (int i = threadIdx.x; i < nshards; i += kBlock) base[i] = hist[i] ? atomicAdd(&cursors[i], (unsigned long long)hist[i]) : 0ull;
+        if (threadIdx.x < (uint32_t)nshards)
+            base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)hist[threadIdx.x]) : 0ull;
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int i = 0; i < nshards; ++i) { loc[i] = acc; acc += hist[i]; }
+            loc[nshards] = acc;
+        }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
             if (own[j] == 0xffffffffu) continue;
-            const uint64_t pos = base[own[j]] + rank_in[j];
-            if (pos < cap) {
-                uint64_t *dst = static_cast<uint64_t *>(inbox.p[own[j]]) + ((uint64_t)my_rank * cap + pos) * S;
-                if (S == 2) *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(q[j][0], q[j][1 % S]);
-                else {
+            const uint32_t at = loc[own[j]] + rank_in[j];
 #pragma unroll
-                    for (int w = 0; w < S; ++w) dst[w] = q[j][w];
-                }
-                slots[(uint64_t)own[j] * cap + pos] = (uint32_t)(tile * tile_q + (uint64_t)j * kBlock + threadIdx.x);
-            }
+            for (int w = 0; w < S; ++w) stage_keys[(size_t)at * S + w] = q[j][w];
+            stage_slot[at] = (uint32_t)(tile * tile_q + (uint64_t)j * kBlock + threadIdx.x);
+        }
+        __syncthreads();
+        for (int o = 0; o < nshards; ++o) {
+            const uint32_t cnt = hist[o];
+            if (cnt == 0) continue;
+            const uint64_t b0 = base[o];
+            const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)cnt, (unsigned long long)(cap - b0));
+            uint64_t *dst = static_cast<uint64_t *>(inbox.p[o]) + ((uint64_t)my_rank * cap + b0) * S;
+            const uint64_t *src = stage_keys + (size_t)loc[o] * S;
+            for (uint32_t t = threadIdx.x; t < keep * S; t += kBlock) dst[t] = src[t];
+            uint32_t *sdst = slots + (uint64_t)o * cap + b0;
+            for (uint32_t t = threadIdx.x; t < keep; t += kBlock) sdst[t] = stage_slot[loc[o] + t];
         }
         __syncthreads();
     }
@@ -838,9 +857,14 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     unsigned long long *cursors = reinterpret_cast<unsigned long long *>(dev_sent);
     CC_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * nshards, st));
     if (nq) {
-        const int grid = grid_for((nq + (uint64_t)kBlock * kRouteQ - 1) / ((uint64_t)kBlock * kRouteQ), 1, sm_count_now(), 4);
-        CC_DISPATCH_S(s, route_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox,
-                                                                    dev_slots, cursors, dev_out));
+        const size_t smem = (size_t)kBlock * kRouteQ * (8 * s + 4);
+        const int per_sm = std::max(1, std::min(4, (int)((200u << 10) / (smem + 4096))));
+        const int grid = grid_for((nq + (uint64_t)kBlock * kRouteQ - 1) / ((uint64_t)kBlock * kRouteQ), 1, sm_count_now(), per_sm);
+        CC_DISPATCH_S(s, {
+            CC_CUDA(cudaFuncSetAttribute(route_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            route_kernel<S_><<<grid, kBlock, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox, dev_slots,
+                                                         cursors, dev_out);
+        });
         count_launch();
     }
     publish_counts_kernel<<<1, kMaxShards, 0, st>>>(cursors, nshards, my_rank, cap, counts);

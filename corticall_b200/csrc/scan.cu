@@ -76,6 +76,10 @@ struct ScanKParams {
     // fast kernel only
     uint32_t chunk_log2, num_chunks, stg_stride, stg_cap, Ow;
     uint32_t *overflow;
+    // chunks whose staging list overflowed in the fast kernel: {chunk index, exclusive output prefix} pairs, rewritten
+    // by redo_chunks_kernel.  dirty_ctl[0] = entries, [1] = ticket, [2] = CTAs done (reset by the last CTA to leave).
+    uint64_t *dirty_list;
+    uint32_t *dirty_ctl;
     TileGeom g;
 };
 
@@ -417,7 +421,7 @@ __device__ __forceinline__ void producer_loop_chunks(FastCtrl *ctrl, uint8_t *st
 }
 
 template <bool ALIGNED4, int NP>
-__global__ void __launch_bounds__(kThreads, 2) scan_novel_fast_kernel(const __grid_constant__ ScanKParams p) {
+__global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __grid_constant__ ScanKParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     FastCtrl *ctrl = reinterpret_cast<FastCtrl *>(smem);
     uint32_t *parents_s = reinterpret_cast<uint32_t *>(smem + kCtrlBytes);
@@ -473,7 +477,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_novel_fast_kernel(const __gr
             const uint64_t total = sum;
             const uint64_t excl = lookback(p.tile_state, (uint32_t)chunk, total, p.epoch, p.total_in, p.err);
             if (ovf) {
-                if (lane == 0) atomicExch(p.overflow, p.epoch);
+                if (lane == 0) {          // counts are exact, only the staged bytes were dropped: queue the chunk for a rewrite
+                    const uint32_t at = atomicAdd(&p.dirty_ctl[0], 1u);
+                    p.dirty_list[2ull * at] = (uint64_t)(uint32_t)chunk;
+                    p.dirty_list[2ull * at + 1] = excl;
+                }
             } else if (sum != 0) {
                 // ---- copy the staged runs out in (tile, warp) order = input order.  Entry e = t*8 + w is held by
                 // lane e%32 in cv[e/32]; every lane copies its own (at most four, usually empty) runs, so the
@@ -617,6 +625,184 @@ __global__ void __launch_bounds__(kThreads, 2) scan_novel_fast_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------ dense chunks: rewrite with a known base
+// Runs right behind the fast kernel over the chunks it queued (none on a sparse graph: every CTA draws one ticket
+// and leaves).  The exclusive prefix of a queued chunk is already known, so a CTA streams the chunk's tiles again and
+// writes in order with a block-local scan only: per tile the novel records are laid out in shared memory as the
+// byte image of their output run (same 16-byte phase as the destination) and copied out with aligned 16-byte stores.
+struct RedoCtrl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    int32_t tile_id[kMaxStages];
+    uint64_t tile_base[kMaxStages];        // exclusive output prefix of the chunk the tile belongs to
+    uint32_t wcnt[kConsumerWarps];
+};
+static_assert(sizeof(RedoCtrl) <= kCtrlBytes, "control block too large");
+
+template <bool ALIGNED4, int NP>
+__global__ void __launch_bounds__(kThreads, 2) redo_chunks_kernel(const __grid_constant__ ScanKParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    RedoCtrl *ctrl = reinterpret_cast<RedoCtrl *>(smem);
+    uint32_t *parents_s = reinterpret_cast<uint32_t *>(smem + kCtrlBytes);
+    const uint32_t parents_bytes = NP >= 0 ? 0u : (((uint32_t)p.nparents * 4u + 127u) & ~127u);
+    const TileGeom &g = p.g;
+    uint8_t *image = smem + kCtrlBytes + parents_bytes;                              // tile_records*O + 32 bytes
+    const uint32_t image_bytes = (g.tile_records * p.O + 32u + 127u) & ~127u;
+    uint8_t *stage0 = image + image_bytes;
+    const uint32_t ndirty = *reinterpret_cast<const volatile uint32_t *>(&p.dirty_ctl[0]);
+
+    if (ndirty != 0) {
+        if (NP < 0)
+            for (int i = threadIdx.x; i < p.nparents; i += kThreads) parents_s[i] = p.cov_off + 4u * (uint32_t)p.parents[i];
+        if (threadIdx.x == 0) {
+            for (uint32_t i = 0; i < g.stages; ++i) {
+                mbar_init(&ctrl->full[i], 1);
+                mbar_init(&ctrl->empty[i], kConsumerWarps);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.body) & 15u);
+        if (warp == kProducerWarp) {
+            if (lane == 0) {
+                const uint64_t policy = make_evict_first_policy();
+                const uint8_t *abase = p.body - mis;
+                uint32_t it = 0;
+                while (true) {
+                    const uint32_t e = atomicAdd(&p.dirty_ctl[1], 1u);
+                    if (e >= ndirty) {
+                        const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
+                        mbar_wait(&ctrl->empty[st], ph ^ 1u, p.err, DEV_TIMEOUT_EMPTY);
+                        ctrl->tile_id[st] = -1;
+                        mbar_arrive(&ctrl->full[st]);
+                        break;
+                    }
+                    const uint32_t chunk = (uint32_t)p.dirty_list[2ull * e];
+                    const uint64_t base = p.dirty_list[2ull * e + 1];
+                    const uint32_t t0 = chunk << p.chunk_log2;
+                    const uint32_t t1 = min(t0 + (1u << p.chunk_log2), g.num_tiles);
+                    for (uint32_t t = t0; t < t1; ++t, ++it) {
+                        const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
+                        mbar_wait(&ctrl->empty[st], ph ^ 1u, p.err, DEV_TIMEOUT_EMPTY);
+                        ctrl->tile_id[st] = (int32_t)t;
+                        ctrl->tile_base[st] = base;
+                        const uint64_t rec0 = (uint64_t)t * g.tile_records;
+                        const uint64_t left = p.n - rec0;
+                        const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
+                        const uint32_t bytes = (nrec * g.S + mis + 15u) & ~15u;
+                        mbar_arrive_expect_tx(&ctrl->full[st], bytes);
+                        bulk_g2s(stage0 + (size_t)st * g.stage_bytes, abase + rec0 * g.S, bytes, &ctrl->full[st], policy);
+                    }
+                }
+            }
+        } else if (warp < kConsumerWarps) {
+            const uint32_t S = g.S;
+            const uint32_t rpw = g.tile_records / kConsumerWarps;
+            const uint32_t T = 1u << p.chunk_log2;
+            uint32_t poff[kFastParents > 0 ? kFastParents : 1];
+#pragma unroll
+            for (int i = 0; i < kFastParents; ++i) poff[i] = p.parent_off[i];
+            const uint32_t lane_lt = (1u << lane) - 1u;
+            uint64_t running = 0;                       // novel records of the chunk's earlier tiles
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
+                mbar_wait(&ctrl->full[st], ph, p.err, DEV_TIMEOUT_FULL);
+                const int32_t tile = ctrl->tile_id[st];
+                if (tile < 0) break;
+                if (((uint32_t)tile & (T - 1u)) == 0) running = 0;
+                const uint64_t out_pos0 = ctrl->tile_base[st] + running;       // output position of the tile's first novel record
+                const uint64_t rec0 = (uint64_t)tile * g.tile_records;
+                const uint64_t left = p.n - rec0;
+                const uint32_t nrec = left < g.tile_records ? (uint32_t)left : g.tile_records;
+                const uint8_t *tile_s = stage0 + (size_t)st * g.stage_bytes + mis;
+                uint32_t masks[kMaxIters];
+                uint32_t wtotal = 0;
+#pragma unroll
+                for (int j = 0; j < kMaxIters; ++j) {
+                    masks[j] = 0;
+                    if (j * 32 < (int)rpw) {
+                        const uint32_t r = warp * rpw + (uint32_t)j * 32u + lane;
+                        const uint8_t *rec = tile_s + r * S;
+                        bool novel = false;
+                        if (r < nrec) {
+                            uint32_t any_parent = 0;
+                            if (NP >= 0) {
+#pragma unroll
+                                for (int i = 0; i < (NP > 0 ? NP : 0); ++i) any_parent |= lds_u32<ALIGNED4>(rec + poff[i]);
+                            } else {
+                                for (int i = 0; i < p.nparents; ++i) any_parent |= lds_u32<ALIGNED4>(rec + parents_s[i]);
+                            }
+                            const int32_t child_cov = (int32_t)lds_u32<ALIGNED4>(rec + p.child_off);
+                            novel = (child_cov > 0) && (any_parent == 0);
+                        }
+                        masks[j] = __ballot_sync(0xffffffffu, novel);
+                        wtotal += __popc(masks[j]);
+                    }
+                }
+                if (lane == 0) ctrl->wcnt[warp] = wtotal;
+                named_bar_sync(1, kConsumerThreads);                            // counts visible; image free (see the barrier below)
+                uint32_t before = 0, tile_total = 0;
+#pragma unroll
+                for (int w = 0; w < kConsumerWarps; ++w) {
+                    const uint32_t cw = ctrl->wcnt[w];
+                    if (w < (int)warp) before += cw;
+                    tile_total += cw;
+                }
+                // byte image of the tile's output run, phase-aligned with its destination
+                uint8_t *dst0 = p.out + out_pos0 * p.O;
+                const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst0) & 15u);
+                uint32_t at = before;
+#pragma unroll
+                for (int j = 0; j < kMaxIters; ++j) {
+                    const uint32_t m = masks[j];
+                    if (j * 32 < (int)rpw && m != 0) {
+                        if ((m >> lane) & 1u) {
+                            const uint32_t r = warp * rpw + (uint32_t)j * 32u + lane;
+                            const uint8_t *rec = tile_s + r * S;
+                            const uint32_t q = at + __popc(m & lane_lt);
+                            uint8_t *d = image + shift + q * p.O;
+                            for (uint32_t b = 0; b < p.cov_off; ++b) d[b] = rec[b];
+#pragma unroll
+                            for (uint32_t b = 0; b < 4; ++b) d[p.cov_off + b] = rec[p.child_off + b];
+                            d[p.cov_off + 4u] = rec[p.edge_off + p.child];
+                            if (p.out_index && out_pos0 + q < p.cap) p.out_index[out_pos0 + q] = p.index_base + rec0 + r;
+                        }
+                        at += __popc(m);
+                    }
+                }
+                named_bar_sync(1, kConsumerThreads);                            // image complete
+                // records beyond cap are dropped
+                uint64_t keep = 0;
+                if (out_pos0 < p.cap) keep = (p.cap - out_pos0 < tile_total) ? (p.cap - out_pos0) : tile_total;
+                const uint32_t nbytes = (uint32_t)keep * p.O;
+                const uint32_t head = min(nbytes, (16u - shift) & 15u);
+                const uint32_t ctid = threadIdx.x;                               // 0..255
+                if (ctid < head) dst0[ctid] = image[shift + ctid];
+                const uint32_t body16 = (nbytes - head) >> 4;
+                const uint4 *src4 = reinterpret_cast<const uint4 *>(image + shift + head);
+                uint4 *dst4 = reinterpret_cast<uint4 *>(dst0 + head);
+                for (uint32_t i = ctid; i < body16; i += kConsumerThreads) dst4[i] = src4[i];
+                const uint32_t done = head + (body16 << 4);
+                if (ctid < nbytes - done) dst0[done + ctid] = image[shift + done + ctid];
+                running += tile_total;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctrl->empty[st]);                   // (the next tile's first barrier also guards the image)
+            }
+        }
+    }
+    // ---- the last CTA to leave resets the queue for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(&p.dirty_ctl[2], 1u);
+        if (done == gridDim.x - 1) {
+            p.dirty_ctl[0] = 0; p.dirty_ctl[1] = 0; p.dirty_ctl[2] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // ------------------------------------------------------------------ K1: decode into columns (keys / coverage / edges)
 template <bool ALIGNED4>
 __global__ void __launch_bounds__(kThreads, 2) decode_columns_kernel(const __grid_constant__ DecodeKParams p) {
@@ -751,6 +937,8 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
         uint64_t cap = std::max<uint64_t>(ntiles, 1024);
         CC_CUDA(cudaMalloc(&tile_state, cap * sizeof(uint64_t)));
         CC_CUDA(cudaMemset(tile_state, 0, cap * sizeof(uint64_t)));
+        if (dirty_list) CC_CUDA(cudaFree(dirty_list));
+        CC_CUDA(cudaMalloc(&dirty_list, cap * 2 * sizeof(uint64_t)));
         tile_state_cap = cap;
         epoch = 0;
         fresh = true;
@@ -767,6 +955,7 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
 
 void ScanWorkspace::release() {
     if (tile_state) cudaFree(tile_state);
+    if (dirty_list) cudaFree(dirty_list);
     if (tile_counter) cudaFree(tile_counter);
     if (totals) cudaFree(totals);
     if (parents) cudaFree(parents);
@@ -793,7 +982,7 @@ FastGeom pick_fast_geometry(uint64_t n, uint32_t S, uint32_t O, uint32_t extra_s
     const uint32_t stage_bytes = (R * S + 32u + 127u) & ~127u;
     f.Ow = (O + 3u) & ~3u;
     f.stg_stride = f.Ow + 4u;
-    f.stg_cap = kStageBufBytes / f.stg_stride;
+    f.stg_cap = (uint32_t)std::max(256, o.scan_stage_buf_bytes) / f.stg_stride;
     if (f.stg_cap < 4) return f;
     f.stg_bytes = (2u * kConsumerWarps * f.stg_cap * f.stg_stride + 127u) & ~127u;
     int stages = std::min(std::max(o.scan_stages, 2), kMaxStages);
@@ -853,13 +1042,13 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
     p.tile_state = ws.tile_state; p.tile_counter = ws.tile_counter;
     p.err = ws.dev_error; p.debug = (uint32_t)o.scan_debug;
     p.overflow = reinterpret_cast<uint32_t *>(ws.totals + 16);
+    p.dirty_list = ws.dirty_list;
+    p.dirty_ctl = reinterpret_cast<uint32_t *>(ws.totals + 20);
     const bool aligned4 = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.body) & 3u) == 0);
     const int np_slot = fastp ? a.nparents : kFastParents + 1;
     using Kern = void (*)(const ScanKParams);
 
     // ---- fast kernel (chunked, deferred look-back)
-    bool guarded = false;
-    uint32_t fast_epoch = 0;
     const FastGeom f = pick_fast_geometry(a.n, S, p.O, parents_bytes, lim.smem_optin, ctas);
     if (f.ok && f.num_chunks <= ws.tile_state_cap) {
         if (int rc = next_epoch(ws, st)) return rc;
@@ -880,8 +1069,26 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
         kern<<<grid, kThreads, smem, st>>>(q);
         count_launch();
         CC_CUDA(cudaGetLastError());
-        guarded = true;
-        fast_epoch = ws.epoch;
+        // ---- rewrite of the chunks whose staging overflowed (dense novelty); a no-op launch on sparse graphs
+        ScanKParams r = q;
+        const uint32_t image_bytes = (f.g.tile_records * p.O + 32u + 127u) & ~127u;
+        int rstages = (int)f.g.stages;
+        const int64_t rbudget = (int64_t)lim.smem_optin / ctas - 1024 - kCtrlBytes - parents_bytes - image_bytes;
+        while (rstages > 2 && (int64_t)rstages * f.g.stage_bytes > rbudget) --rstages;
+        if ((int64_t)rstages * f.g.stage_bytes > rbudget) return fail(CC_ERR_UNSUPPORTED, "record size %u bytes does not fit the rewrite kernel", S);
+        r.g.stages = (uint32_t)rstages;
+        const size_t rsmem = kCtrlBytes + parents_bytes + image_bytes + (size_t)rstages * f.g.stage_bytes;
+        static const Kern rtable[2][kFastParents + 2] = {
+            {redo_chunks_kernel<false, 0>, redo_chunks_kernel<false, 1>, redo_chunks_kernel<false, 2>, redo_chunks_kernel<false, 3>,
+             redo_chunks_kernel<false, 4>, redo_chunks_kernel<false, -1>},
+            {redo_chunks_kernel<true, 0>, redo_chunks_kernel<true, 1>, redo_chunks_kernel<true, 2>, redo_chunks_kernel<true, 3>,
+             redo_chunks_kernel<true, 4>, redo_chunks_kernel<true, -1>}};
+        Kern rkern = rtable[aligned4 ? 1 : 0][np_slot];
+        CC_CUDA(cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        rkern<<<grid, kThreads, rsmem, st>>>(r);
+        count_launch();
+        CC_CUDA(cudaGetLastError());
+        return CC_OK;
     }
 
     // ---- general kernel (per-tile look-back, any density): alone, or behind the fast kernel and run only on overflow
@@ -892,8 +1099,8 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, p.g.num_tiles);
     p.ticket_base = ws.ticket_base;
     ws.ticket_base += p.g.num_tiles + grid;         // drawn by the CTAs, or added by block 0 when the launch is skipped
-    p.run_if = guarded ? p.overflow : nullptr;
-    p.run_expect = fast_epoch;
+    p.run_if = nullptr;
+    p.run_expect = 0;
     p.skip_tickets = p.g.num_tiles + grid;
     const size_t smem = kCtrlBytes + parents_bytes + (size_t)p.g.stages * p.g.stage_bytes;
     static const Kern table[2][kFastParents + 2] = {

@@ -181,10 +181,27 @@ class RoutedLookup:
         N.check(N.lib().cc_gather_routed_dev(self.index, self.block.data_ptr() + 8 * self.off_ret, self.slots.data_ptr(),
                                              self.sent.data_ptr(), self.world, self.cap, out.data_ptr(), st))
 
-    def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
+    def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor, profile: bool = False) -> torch.Tensor:
+        marks = []
+
+        def mark(name):
+            if profile:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         self.route(words, flags, out)
+        mark("route")
         self._barrier()
+        mark("barrier1")
         self.search()
+        mark("search")
         self._barrier()
+        mark("barrier2")
         self.gather(out)
+        mark("gather")
+        if marks:
+            torch.cuda.synchronize()
+            self.phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
         return out
