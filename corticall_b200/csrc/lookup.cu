@@ -265,6 +265,80 @@ __global__ void __launch_bounds__(kBlock) seq_kernel(SeqJob job, uint64_t *__res
     }
 }
 
+// ------------------------------------------------------------------ K3 for independent k-byte rows (query lists)
+// A warp takes 32 consecutive rows (32*k contiguous bytes): 16-byte coalesced loads of the aligned superset into a
+// per-warp shared buffer, then lane i packs row i base by base.  Same flags and canonical rule as window_canonical.
+template <int S>
+__global__ void __launch_bounds__(kBlock) pack_rows_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
+                                                           uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags) {
+    extern __shared__ __align__(16) uint8_t rows_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t wbytes = (32u * k + 32u + 15u) & ~15u;
+    uint8_t *buf = rows_smem + (size_t)warp * wbytes;
+    const uint64_t ngroups = (nq + 31) / 32;
+    const uint64_t gstride = (uint64_t)gridDim.x * (kBlock / 32);
+    for (uint64_t grp = (uint64_t)blockIdx.x * (kBlock / 32) + warp; grp < ngroups; grp += gstride) {
+        const uint64_t row0 = grp * 32;
+        const uint32_t rows = (uint32_t)min((uint64_t)32, nq - row0);
+        const uint8_t *src = kmers + row0 * k;
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(src - shift);
+        const uint32_t n16 = (shift + rows * k + 15u) >> 4;
+        __syncwarp();
+        for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(buf)[i] = __ldg(src4 + i);
+        __syncwarp();
+        if (lane < rows) {
+            const uint8_t *a = buf + shift + lane * k;
+            uint64_t fw[S];
+#pragma unroll
+            for (int w = 0; w < S; ++w) fw[w] = 0;
+            uint32_t bad = 0, low = 0;
+            for (uint32_t i = 0; i < k; ++i) {
+                const uint32_t ch = a[i];
+                const uint32_t f = ch | 0x20u;
+                const bool ok = (f == 'a') | (f == 'c') | (f == 'g') | (f == 't');
+                bad |= ok ? 0u : 1u;
+                low |= (ok && (ch & 0x20u)) ? 1u : 0u;
+                const uint64_t code = ok ? base_code(ch) : 0u;
+#pragma unroll
+                for (int w = 0; w < S - 1; ++w) fw[w] = (fw[w] << 2) | (fw[w + 1] >> 62);
+                fw[S - 1] = (fw[S - 1] << 2) | code;
+            }
+            uint32_t flags = 0;
+            uint64_t outw[S];
+            if (bad) {
+#pragma unroll
+                for (int w = 0; w < S; ++w) outw[w] = 0;
+                flags = 2u;
+            } else {
+                uint64_t rc[S];
+                revcomp_words<S>(fw, rc, k);
+                bool flip = words_less<S>(rc, fw);
+                if (low) {          // mixed / lower case: the reference compares ASCII bytes (SequenceUtils.java:211-219)
+                    flags |= 4u;
+                    flip = false;
+                    for (uint32_t i = 0; i < k; ++i) {
+                        const int8_t f = (int8_t)a[i];
+                        const int8_t r = (int8_t)complement_ascii(a[k - 1 - i]);
+                        if (f < r) break;
+                        if (f > r) { flip = true; break; }
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < S; ++w) outw[w] = flip ? rc[w] : fw[w];
+                flags |= flip ? 1u : 0u;
+            }
+            const uint64_t row = row0 + lane;
+            if (S == 2) reinterpret_cast<ulonglong2 *>(out_words)[row] = make_ulonglong2(outw[0], outw[1 % S]);
+            else {
+#pragma unroll
+                for (int w = 0; w < S; ++w) out_words[row * S + w] = outw[w];
+            }
+            out_flags[row] = (uint8_t)flags;
+        }
+    }
+}
+
 template <int S, bool BUCKETED>
 __global__ void __launch_bounds__(kBlock) find_packed_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
                                                              uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
@@ -671,6 +745,18 @@ int launch_pack_windows(const uint8_t *dev_seq, uint64_t /*len*/, uint32_t k, ui
     if (int rc = check_k(k)) return rc;
     if (nq == 0) return CC_OK;
     const uint32_t s = (k + 31) / 32;
+    if (row_stride == k && row_stride > 1) {       // independent rows
+        const size_t smem = (size_t)(kBlock / 32) * ((32u * k + 32u + 15u) & ~15u);
+        const int per_sm = std::max(1, std::min(8, (int)((200u << 10) / (smem + 1024))));
+        const int grid = grid_for((nq + 31) / 32, kBlock / 32, sm_count_now(), per_sm);
+        CC_DISPATCH_S(s, {
+            CC_CUDA(cudaFuncSetAttribute(pack_rows_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pack_rows_kernel<S_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags);
+        });
+        count_launch();
+        CC_CUDA(cudaGetLastError());
+        return CC_OK;
+    }
     SeqJob job = make_job(dev_seq, nq, row_stride, k);
     const int grid = grid_for((nq + job.per_tile - 1) / job.per_tile, 1, sm_count_now(), 6);
     IndexView none{};

@@ -471,3 +471,42 @@ def test_routed_lookup_emulated_ranks(world):
     for g in shards:
         g.dispose()
     whole.dispose()
+
+
+@pytest.mark.parametrize("k", [5, 31, 32, 33, 47, 63, 64, 95, 128])
+def test_pack_rows_vs_oracle(k):
+    """cc_pack_kmers_dev (independent k-byte rows, the query-list form of K3) against the oracle's per-row canonicalise+pack,
+    including N / lower-case / odd bytes, a ragged last warp and a misaligned base pointer."""
+    nq = 70_003
+    s = (k + 31) // 32
+    seq = synth.random_genome(17 + k, nq * k + 5, n_permille=1).numpy().copy()
+    seq[1000:1400] += 32
+    seq[5000] = ord("."); seq[9000] = 200
+    for off in (0, 5):
+        rows = seq[off:off + nq * k].reshape(nq, k)
+        buf = torch.from_numpy(seq).cuda()
+        words = torch.zeros((nq, s), dtype=torch.int64, device="cuda"); flags = torch.zeros(nq, dtype=torch.uint8, device="cuda")
+        N.check(N.lib().cc_pack_kmers_dev(0, buf.data_ptr() + off, nq, k, words.data_ptr(), flags.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        got_w, got_f = words.cpu().numpy().view(np.uint64), flags.cpu().numpy()
+        # oracle: every row is a length-k sequence with exactly one window
+        step = max(1, nq // 3000)
+        for i in list(range(0, nq, step)) + [nq - 1, 1000 // k, 1400 // k, 5000 // k, 9000 // k]:
+            ow, of = orc.pack_windows(rows[i], k)
+            assert (got_w[i] == ow[0]).all() and got_f[i] == of[0], (k, off, i)
+
+
+def test_large_ascii_batch_uses_two_pass_path():
+    """A query list big enough for the pack-then-search path (>= 65536 rows) returns what the oracle's findRecord does."""
+    k, c, n = 47, 4, 30000
+    ctx = synth.make_ctx_file(8, n, k, c, adv_period=0)
+    g = cb.CortexGraph(ctx)
+    og = orc.Graph(ctx)
+    words, _, _ = g.decodeRecords(0, n)
+    tw = [torch.from_numpy(words[:, w].copy().view(np.int64)) for w in range(2)]
+    q_ascii, _, _ = synth.make_queries(3, tw, k, 90_000, corrupt_permille=20)
+    got = g.findRecordIndices(q_ascii.numpy())
+    sub = np.arange(0, 90_000, 7)
+    assert (got[sub] == og.find_batch(q_ascii.numpy()[sub])).all()
+    assert (got >= 0).sum() > 30000
+    g.dispose()

@@ -85,6 +85,10 @@ for bits in (0, 24, 26, 27, 28, 29):
         print("lookup packed %-9s bits=%2d qpt=%d n=%.1e q=%.1e  %.3f ms  %.3g lookups/s" % (name, bits, qpt, nt, nq, ms, nq / ms * 1e3), flush=True)
 N.set_option("lookup_queries_per_thread", 2)
 g.buildIndex(0)
+pw = torch.empty(nq * 2, dtype=torch.int64, device="cuda"); pf = torch.empty(nq, dtype=torch.uint8, device="cuda")
+ms = timeit(lambda: N.check(L.cc_pack_kmers_dev(0, a.data_ptr(), nq, k, pw.data_ptr(), pf.data_ptr(), st)), reps=5)
+print("pack   rows k=47 (query list)              q=%.1e  %.3f ms  %.3g rows/s  %6.0f GB/s (k+8s+1 B/row)" % (nq, ms, nq / ms * 1e3, nq * (k + 17) / ms / 1e6), flush=True)
+del pw, pf
 ms = timeit(lambda: N.check(L.cc_find_ascii_dev(g._h, a.data_ptr(), nq, res.data_ptr(), 0, st)), reps=5)
 print("lookup ascii rows (pack+find fused)       q=%.1e  %.3f ms  %.3g lookups/s" % (nq, ms, nq / ms * 1e3), flush=True)
 nm = nq // 4
