@@ -401,6 +401,7 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         barrier()
         rl.find_packed(qwords, qflags, res, profile=True)
         out["phase_ms_rank0"] = rl.phase_ms
+        del rl
         # the NCCL all-to-all formulation of the same exchange, as the comparison and as a cross-check of the results
         sl = ShardedLookup(g, splitters, rank, world, dev)
         res2 = torch.empty_like(res)

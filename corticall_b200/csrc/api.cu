@@ -341,6 +341,9 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
     else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
     else if (!strcmp(name, "lookup_queries_per_thread")) o.lookup_queries_per_thread = (int)value;
+    else if (!strcmp(name, "route_blocks_per_sm")) o.route_blocks_per_sm = (int)value;
+    else if (!strcmp(name, "routed_search_blocks_per_sm")) o.routed_search_blocks_per_sm = (int)value;
+    else if (!strcmp(name, "gather_blocks_per_sm")) o.gather_blocks_per_sm = (int)value;
     else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;
     else if (!strcmp(name, "scan_debug")) o.scan_debug = (int)value;
     else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;
@@ -925,6 +928,111 @@ int cc_gather_routed_dev(int device, const int64_t *dev_ret, const uint32_t *dev
     if (!dev_ret || !dev_slots || !dev_sent || !dev_out) return fail(CC_ERR_ARG, "null argument");
     DeviceGuard guard(device);
     return launch_gather_routed(dev_ret, dev_slots, dev_sent, nshards, cap, dev_out, static_cast<cudaStream_t>(stream));
+}
+
+// ==================================================================== next rows: merged view (CortexCollection / Join)
+int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out) {
+    if (!graphs || !out || ngraphs < 1) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    const int device = graphs[0]->device;
+    for (int i = 0; i < ngraphs; ++i) {
+        if (!graphs[i]) return fail(CC_ERR_ARG, "null graph");
+        if (graphs[i]->device != device) return fail(CC_ERR_ARG, "graphs to join must live on one device");
+        if (graphs[i]->h.k != graphs[0]->h.k)      // CortexCollection.java:43-45
+            return fail(CC_ERR_ARG, "Graph kmer sizes are not equal.  Expected k=%u, but found k=%u in graph %s", graphs[0]->h.k,
+                        graphs[i]->h.k, graphs[i]->path.c_str());
+    }
+    DeviceGuard guard(device);
+    for (int i = 0; i < ngraphs; ++i)
+        if (int rc = ensure_index(graphs[i])) return rc;          // key columns; rejects unsorted inputs
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(new cc_graph(), destroy);
+    g->path = "<join>";
+    g->h = graphs[0]->h;
+    g->h.data_offset = 0;
+    if (int rc = init_handle(g.get(), device)) return rc;
+    const uint32_t s = graphs[0]->h.s;
+    // fold left: ((g0 U g1) U g2) ...
+    void *cur_body = nullptr;          // owned intermediate (null while the running result is graphs[0] itself)
+    const uint8_t *body = graphs[0]->dev_body;
+    const uint64_t *keys = graphs[0]->index.keys;
+    uint64_t n = graphs[0]->h.num_records;
+    uint32_t c = graphs[0]->h.c;
+    uint64_t *cur_keys = nullptr;
+    struct Tmp { void *&b; uint64_t *&k; ~Tmp() { if (b) cudaFree(b); if (k) cudaFree(k); } } tmp{cur_body, cur_keys};
+    for (int i = 1; i < ngraphs; ++i) {
+        void *nb = nullptr;
+        uint64_t nn = 0;
+        if (int rc = join_pair(body, keys, n, c, graphs[i]->dev_body, graphs[i]->index.keys, graphs[i]->h.num_records, graphs[i]->h.c, s,
+                               g->stream, &nb, &nn)) return rc;
+        if (cur_body) cudaFree(cur_body);
+        if (cur_keys) { cudaFree(cur_keys); cur_keys = nullptr; }
+        cur_body = nb;
+        body = static_cast<const uint8_t *>(nb);
+        n = nn;
+        c += graphs[i]->h.c;
+        for (const ColorMeta &cm : graphs[i]->h.colors) g->h.colors.push_back(cm);
+        if (i + 1 < ngraphs) {         // key column of the intermediate for the next union
+            CC_CUDA(cudaMalloc(&cur_keys, std::max<uint64_t>(n * s, 2) * 8 + 64));
+            if (int rc = g->scan_ws.ensure(0, 0)) return rc;
+            if (int rc = launch_decode_columns(body, n, s, c, cur_keys, nullptr, nullptr, g->scan_ws, g->sm_count, g->stream)) return rc;
+            CC_CUDA(cudaStreamSynchronize(g->stream));
+            keys = cur_keys;
+        }
+    }
+    if (!cur_body) {                   // a single graph: copy it
+        CC_CUDA(cudaMalloc(&cur_body, n * graphs[0]->h.record_size + 256));
+        CC_CUDA(cudaMemcpy(cur_body, body, n * graphs[0]->h.record_size, cudaMemcpyDeviceToDevice));
+    }
+    g->h.c = c;
+    g->h.record_size = 8ull * s + 5ull * c;
+    g->h.num_records = n;
+    g->dev_alloc = cur_body;
+    g->dev_body = static_cast<const uint8_t *>(cur_body);
+    cur_body = nullptr;
+    *out = g.release();
+    return CC_OK;
+}
+
+// CortexGraphWriter.initialize :31-104 + one write of the whole body.  total_sequence is emitted the way the reference
+// does after ITS round trip: it reads the field big-endian (BinaryFile.readUnsignedLong :34-38) and writes it
+// little-endian (:60-63), i.e. byte-reversed with respect to the input file.
+int cc_write_graph(const cc_graph *g, const char *path) {
+    if (!g || !path) return fail(CC_ERR_ARG, "null argument");
+    std::vector<uint8_t> hdr;
+    auto u32 = [&](uint32_t v) { for (int i = 0; i < 4; ++i) hdr.push_back((uint8_t)(v >> (8 * i))); };
+    auto raw = [&](const void *p, size_t n) { hdr.insert(hdr.end(), (const uint8_t *)p, (const uint8_t *)p + n); };
+    static const uint8_t err[16] = {0, 0xd8, 0xa3, 0x70, 0x3d, 0x0a, 0xd7, 0xa3, 0xf8, 0x3f, 0, 0, 0, 0, 0, 0};
+    raw("CORTEX", 6);
+    u32(6); u32(g->h.k); u32(g->h.s); u32(g->h.c);
+    for (const ColorMeta &c : g->h.colors) u32(c.info.mean_read_length);
+    for (const ColorMeta &c : g->h.colors) { const uint64_t v = c.info.total_sequence; for (int i = 7; i >= 0; --i) hdr.push_back((uint8_t)(v >> (8 * i))); }
+    for (const ColorMeta &c : g->h.colors) { u32((uint32_t)c.sample_name.size()); raw(c.sample_name.data(), c.sample_name.size()); }
+    for (size_t i = 0; i < g->h.colors.size(); ++i) raw(err, 16);
+    for (const ColorMeta &c : g->h.colors) {
+        hdr.push_back(c.info.tip_clipping ? 1 : 0);
+        hdr.push_back(c.info.low_covg_supernodes_removed ? 1 : 0);
+        hdr.push_back(c.info.low_covg_kmers_removed ? 1 : 0);
+        hdr.push_back(c.info.cleaned_against_graph ? 1 : 0);
+        u32(c.info.low_cov_supernodes_threshold);
+        u32(c.info.low_cov_kmer_threshold);
+        u32((uint32_t)c.graph_name.size());
+        raw(c.graph_name.data(), c.graph_name.size());
+    }
+    raw("CORTEX", 6);
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(CC_ERR_IO, "Unable to open file '%s'", path);
+    bool ok = fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size();
+    const uint64_t bytes = g->h.num_records * g->h.record_size;
+    std::vector<uint8_t> buf(std::min<uint64_t>(bytes, 256ull << 20));
+    DeviceGuard guard(g->device);
+    for (uint64_t off = 0; ok && off < bytes; off += buf.size()) {
+        const uint64_t nb = std::min<uint64_t>(buf.size(), bytes - off);
+        if (cudaMemcpy(buf.data(), g->dev_body + off, nb, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); return cuda_fail(cudaGetLastError(), "cudaMemcpy", __FILE__, __LINE__); }
+        ok = fwrite(buf.data(), 1, nb, f) == nb;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(CC_ERR_IO, "Unable to write record to file '%s'", path);
+    return CC_OK;
 }
 
 // ==================================================================== instrumentation

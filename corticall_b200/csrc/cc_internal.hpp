@@ -33,7 +33,10 @@ struct Options {
     int scan_ctas_per_sm = 2;
     int index_bits = 0;          // 0 = auto
     int lookup_block = 256;
-    int lookup_queries_per_thread = 2;   // 0 = the single-query kernel
+    int lookup_queries_per_thread = 2;
+    int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1
+    int routed_search_blocks_per_sm = 8;  // grid of find_routed_kernel (resident blocks are limited by registers anyway)
+    int gather_blocks_per_sm = 8;   // 0 = the single-query kernel
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
     int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)
@@ -148,6 +151,8 @@ int launch_bucket_by_owner(const uint64_t *dev_words, const uint8_t *dev_flags, 
                            const uint64_t *dev_splitters, int nshards, uint64_t *dev_counts, uint64_t *dev_sorted_words,
                            uint32_t *dev_slots, cudaStream_t st);
 int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n, int64_t *dev_out, cudaStream_t st);
+int join_pair(const uint8_t *body_a, const uint64_t *keys_a, uint64_t na, uint32_t ca, const uint8_t *body_b, const uint64_t *keys_b,
+              uint64_t nb, uint32_t cb, uint32_t s, cudaStream_t st, void **out_body, uint64_t *out_n);
 int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s, const uint64_t *dev_splitters, int nshards,
                  int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, uint32_t *dev_slots, uint64_t *dev_sent,
                  int64_t *dev_out, cudaStream_t st);

@@ -446,30 +446,30 @@ struct PeerPtrs {
     void *p[kMaxShards];
 };
 
-// Tile of kBlock*kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory so that each
+// Tile of BLOCK*kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory so that each
 // owner's run leaves as fully coalesced stores (whole 128-byte lines over NVLink instead of 16-byte fragments).
-template <int S>
-__global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
+template <int S, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
                                                        const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
                                                        PeerPtrs inbox, uint32_t *__restrict__ slots, unsigned long long *cursors,
                                                        int64_t *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t route_smem[];
-    constexpr uint32_t tile_q = kBlock * kRouteQ;
+    constexpr uint32_t tile_q = BLOCK * kRouteQ;
     uint64_t *stage_keys = reinterpret_cast<uint64_t *>(route_smem);                       // [tile_q][S], grouped by owner
     uint32_t *stage_slot = reinterpret_cast<uint32_t *>(route_smem + (size_t)tile_q * S * 8);   // [tile_q]
     __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1];
     __shared__ unsigned long long base[kMaxShards];
     __shared__ uint64_t spl[(kMaxShards - 1) * S];
-    for (int i = threadIdx.x; i < (nshards - 1) * S; i += kBlock) spl[i] = splitters[i];
+    for (int i = threadIdx.x; i < (nshards - 1) * S; i += BLOCK) spl[i] = splitters[i];
     const uint64_t ntiles = (nq + tile_q - 1) / tile_q;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int i = threadIdx.x; i < nshards; i += kBlock) hist[i] = 0;
+        for (int i = threadIdx.x; i < nshards; i += BLOCK) hist[i] = 0;
         __syncthreads();
         uint64_t q[kRouteQ][S];
         uint32_t own[kRouteQ], rank_in[kRouteQ];
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            const uint64_t i = tile * tile_q + (uint64_t)j * kBlock + threadIdx.x;
+            const uint64_t i = tile * tile_q + (uint64_t)j * BLOCK + threadIdx.x;
             own[j] = 0xffffffffu;
             if (i < nq) {
                 if (flags && (flags[i] & 6u)) out[i] = -1;           // never routed: cannot match
@@ -479,9 +479,18 @@ __global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restric
                 }
             }
         }
+        // warp-aggregated ranking: one shared-memory atomic per (warp, owner) instead of one per query -- with few
+        // owners the per-query atomics all hit the same two or eight addresses and serialise
+        const uint32_t lane = threadIdx.x & 31u, lane_lt = (1u << lane) - 1u;
 #pragma unroll
-        for (int j = 0; j < kRouteQ; ++j)
-            if (own[j] != 0xffffffffu) rank_in[j] = atomicAdd(&hist[own[j]], 1u);
+        for (int j = 0; j < kRouteQ; ++j) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, own[j]);
+            const uint32_t leader = __ffs(peers) - 1u;
+            uint32_t b = 0;
+            if (lane == leader && own[j] != 0xffffffffu) b = atomicAdd(&hist[own[j]], (uint32_t)__popc(peers));
+            b = __shfl_sync(0xffffffffu, b, leader);
+            rank_in[j] = b + __popc(peers & lane_lt);
+        }
         __syncthreads();
         if (threadIdx.x < (uint32_t)nshards)
             base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)hist[threadIdx.x]) : 0ull;
@@ -497,7 +506,7 @@ __global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restric
             const uint32_t at = loc[own[j]] + rank_in[j];
 #pragma unroll
             for (int w = 0; w < S; ++w) stage_keys[(size_t)at * S + w] = q[j][w];
-            stage_slot[at] = (uint32_t)(tile * tile_q + (uint64_t)j * kBlock + threadIdx.x);
+            stage_slot[at] = (uint32_t)(tile * tile_q + (uint64_t)j * BLOCK + threadIdx.x);
         }
         __syncthreads();
         for (int o = 0; o < nshards; ++o) {
@@ -507,9 +516,9 @@ __global__ void __launch_bounds__(kBlock) route_kernel(const uint64_t *__restric
             const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)cnt, (unsigned long long)(cap - b0));
             uint64_t *dst = static_cast<uint64_t *>(inbox.p[o]) + ((uint64_t)my_rank * cap + b0) * S;
             const uint64_t *src = stage_keys + (size_t)loc[o] * S;
-            for (uint32_t t = threadIdx.x; t < keep * S; t += kBlock) dst[t] = src[t];
+            for (uint32_t t = threadIdx.x; t < keep * S; t += BLOCK) dst[t] = src[t];
             uint32_t *sdst = slots + (uint64_t)o * cap + b0;
-            for (uint32_t t = threadIdx.x; t < keep; t += kBlock) sdst[t] = stage_slot[loc[o] + t];
+            for (uint32_t t = threadIdx.x; t < keep; t += BLOCK) sdst[t] = stage_slot[loc[o] + t];
         }
         __syncthreads();
     }
@@ -565,12 +574,12 @@ __global__ void __launch_bounds__(kBlock) find_routed_kernel(const uint64_t *__r
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(kBlock) gather_routed_kernel(const int64_t *__restrict__ ret, const uint32_t *__restrict__ slots,
-                                                               const unsigned long long *__restrict__ sent, int nshards, uint64_t cap,
-                                                               int64_t *__restrict__ out) {
+__global__ void gather_routed_kernel(const int64_t *__restrict__ ret, const uint32_t *__restrict__ slots,
+                                     const unsigned long long *__restrict__ sent, int nshards, uint64_t cap,
+                                     int64_t *__restrict__ out) {
     for (int o = 0; o < nshards; ++o) {
         const uint64_t n = sent[o] < cap ? sent[o] : cap;
-        for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock)
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
             out[slots[(uint64_t)o * cap + i]] = ret[(uint64_t)o * cap + i];
     }
 }
@@ -943,14 +952,27 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     unsigned long long *cursors = reinterpret_cast<unsigned long long *>(dev_sent);
     CC_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * nshards, st));
     if (nq) {
-        const size_t smem = (size_t)kBlock * kRouteQ * (8 * s + 4);
-        const int per_sm = std::max(1, std::min(4, (int)((200u << 10) / (smem + 4096))));
-        const int grid = grid_for((nq + (uint64_t)kBlock * kRouteQ - 1) / ((uint64_t)kBlock * kRouteQ), 1, sm_count_now(), per_sm);
-        CC_DISPATCH_S(s, {
-            CC_CUDA(cudaFuncSetAttribute(route_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            route_kernel<S_><<<grid, kBlock, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox, dev_slots,
-                                                         cursors, dev_out);
-        });
+        // small blocks (128 threads) when the leg is to be overlapped with the search on another stream: one of them
+        // fits next to three resident search blocks
+        const bool small = options().route_blocks_per_sm > 0;
+        const int block = small ? 128 : kBlock;
+        const size_t smem = (size_t)block * kRouteQ * (8 * s + 4);
+        int per_sm = std::max(1, std::min(4, (int)((200u << 10) / (smem + 4096))));
+        if (small) per_sm = std::min(per_sm, options().route_blocks_per_sm);
+        const int grid = grid_for((nq + (uint64_t)block * kRouteQ - 1) / ((uint64_t)block * kRouteQ), 1, sm_count_now(), per_sm);
+        if (small) {
+            CC_DISPATCH_S(s, {
+                CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                route_kernel<S_, 128><<<grid, 128, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox,
+                                                                dev_slots, cursors, dev_out);
+            });
+        } else {
+            CC_DISPATCH_S(s, {
+                CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                route_kernel<S_, kBlock><<<grid, kBlock, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox,
+                                                                      dev_slots, cursors, dev_out);
+            });
+        }
         count_launch();
     }
     publish_counts_kernel<<<1, kMaxShards, 0, st>>>(cursors, nshards, my_rank, cap, counts);
@@ -966,7 +988,7 @@ int launch_find_routed(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *d
     PeerPtrs ret{};
     for (int i = 0; i < nshards; ++i) ret.p[i] = peer_ret[i];
     IndexView ix = view_of(g);
-    const int grid = g->sm_count * 8;
+    const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
     CC_DISPATCH_S(g->h.s, find_routed_kernel<S_, 2><<<grid, kBlock, 0, st>>>(dev_inbox, reinterpret_cast<const unsigned long long *>(dev_counts_in),
                                                                              nshards, my_rank, cap, ix, ret));
     count_launch();
@@ -977,7 +999,8 @@ int launch_find_routed(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *d
 int launch_gather_routed(const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
                          int64_t *dev_out, cudaStream_t st) {
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
-    gather_routed_kernel<<<sm_count_now() * 8, kBlock, 0, st>>>(dev_ret, dev_slots, reinterpret_cast<const unsigned long long *>(dev_sent),
+    const bool small = options().gather_blocks_per_sm > 0 && options().gather_blocks_per_sm < 8;
+    gather_routed_kernel<<<sm_count_now() * std::max(1, options().gather_blocks_per_sm), small ? 128 : kBlock, 0, st>>>(dev_ret, dev_slots, reinterpret_cast<const unsigned long long *>(dev_sent),
                                                                 nshards, cap, dev_out);
     count_launch();
     CC_CUDA(cudaGetLastError());

@@ -34,6 +34,45 @@ class FindROIs:
         return self.numNovelRecords
 
 
+class CortexCollection:
+    """S/utils/io/graph/cortex/CortexCollection.java: several graphs presented as one (colours concatenated, records
+    merged by k-mer).  The merge is done once on the device (cc_join); iteration, getRecord and findRecord are then
+    those of the merged CortexGraph."""
+
+    def __init__(self, *graphs):
+        if len(graphs) == 1 and isinstance(graphs[0], (list, tuple)):
+            graphs = tuple(graphs[0])
+        self.graphList = list(graphs)
+        self.merged = CortexGraph.join(self.graphList)
+
+    def __getattr__(self, name):            # DeBruijnGraph surface: delegate to the merged graph
+        return getattr(self.merged, name)
+
+    def __iter__(self):
+        return iter(self.merged)
+
+    def getGraph(self, color: int) -> CortexGraph:                      # :65-75
+        for g in self.graphList:
+            if color < g.getNumColors():
+                return g
+            color -= g.getNumColors()
+        raise IndexError(color)
+
+
+class Join:
+    """`Join -g a.ctx -g b.ctx ... -o joined.ctx` (S/commands/utils/Join.java:16-58)."""
+
+    def __init__(self, GRAPHS, out):
+        self.GRAPHS, self.out = list(GRAPHS), out
+
+    def execute(self) -> int:
+        cc = CortexCollection(self.GRAPHS)
+        cc.merged.writeGraph(self.out)
+        n = cc.merged.getNumRecords()
+        cc.merged.dispose()
+        return n
+
+
 class CortexVertex:
     """The three fields of utils/traversal/CortexVertex the child walk fills (bases, record, copy index)."""
 

@@ -445,6 +445,27 @@ class CortexGraph:
         N.check(N.lib().cc_write_roi_file(self._h, child, _ptr(par), par.size, os.fspath(out_path).encode(), C.byref(cnt)))
         return cnt.value
 
+    @classmethod
+    def join(cls, graphs) -> "CortexGraph":
+        """The merged view CortexCollection iterates and Join writes (CortexCollection.java:245-293): sorted union of
+        the graphs' k-mers, colours concatenated in argument order -- as a new device-resident graph."""
+        graphs = list(graphs)
+        arr = (N._P * len(graphs))(*[g._h for g in graphs])
+        h = N._P()
+        N.check(N.lib().cc_join(arr, len(graphs), C.byref(h)))
+        self = cls.__new__(cls)
+        self._h, self._device, self._keep, self.cortexFile = h, graphs[0]._device, None, None
+        self.firstIndex = 0
+        self._load_header()
+        self.recordsSeen = 0
+        self._block = None
+        self._nextRecord = self._record_at(0)
+        return self
+
+    def writeGraph(self, out_path) -> None:
+        """CortexGraphWriter over the whole graph (header from the colours, then every record)."""
+        N.check(N.lib().cc_write_graph(self._h, os.fspath(out_path).encode()))
+
     def lastStats(self) -> N.Stats:
         st = N.Stats()
         N.check(N.lib().cc_last_stats(self._h, C.byref(st)))

@@ -205,3 +205,77 @@ class RoutedLookup:
             torch.cuda.synchronize()
             self.phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
         return out
+
+
+class PipelinedRoutedLookup:
+    """RoutedLookup over sub-batches with the NVLink legs overlapped with the search.
+
+    Two RoutedLookup buffer sets (parity = sub-batch & 1) and two streams: X carries route_i and gather_i, Y carries
+    search_i.  Order on X: R0 R1 G0 R2 G1 R3 G2 ... ; on Y: S0 S1 S2 ...  Cross-rank barriers follow R_i (on X) and S_i
+    (on Y), so every rank issues the same sequence per stream and a buffer set is never overwritten while a peer still
+    reads it.  The route / gather kernels are launched as one 128-thread block per SM on a high-priority
+    stream, so they fit beside the three resident blocks of the (latency-bound, full-occupancy) search kernel.
+    """
+
+    def __init__(self, graph, splitters, rank: int, world: int, device, sub_batch: int, s: int, group=None):
+        self.sub = int(sub_batch)
+        self.sets = [RoutedLookup(graph, splitters, rank, world, device, self.sub, s, group=group) for _ in range(2)]
+        self.sx = torch.cuda.Stream(device=device, priority=-1)     # NVLink legs first: they are short and hide behind the search
+        self.sy = torch.cuda.Stream(device=device)
+        self.world = world
+
+    def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
+        nq = words.shape[0]
+        nsub = max(1, (nq + self.sub - 1) // self.sub)
+        if self.world > 1:
+            # every rank must run the same number of sub-batches (the barriers are collective)
+            t = torch.tensor([nsub], dtype=torch.int64, device=words.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nsub = int(t.item())
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(cur)
+        self.sx.wait_stream(cur)
+        self.sy.wait_stream(cur)
+        routed = [torch.cuda.Event() for _ in range(nsub)]
+        searched = [torch.cuda.Event() for _ in range(nsub)]
+        N.set_option("route_blocks_per_sm", 1)          # 128-thread blocks: one fits beside three resident search blocks
+        N.set_option("gather_blocks_per_sm", 1)
+
+        def part(i):
+            lo, hi = min(i * self.sub, nq), min((i + 1) * self.sub, nq)
+            return words[lo:hi], (flags[lo:hi] if flags is not None else None), out[lo:hi]
+
+        def route(i):
+            w, f, o = part(i)
+            with torch.cuda.stream(self.sx):
+                self.sets[i & 1].route(w, f, o)
+                self.sets[i & 1]._barrier()
+                routed[i].record(self.sx)
+
+        def search(i):
+            with torch.cuda.stream(self.sy):
+                self.sy.wait_event(routed[i])
+                self.sets[i & 1].search()
+                self.sets[i & 1]._barrier()
+                searched[i].record(self.sy)
+
+        def gather(i):
+            _, _, o = part(i)
+            with torch.cuda.stream(self.sx):
+                self.sx.wait_event(searched[i])
+                self.sets[i & 1].gather(o)
+
+        try:
+            for i in range(nsub):
+                route(i)
+                search(i)
+                if i >= 1:
+                    gather(i - 1)
+            gather(nsub - 1)
+        finally:
+            N.set_option("route_blocks_per_sm", 0)
+            N.set_option("gather_blocks_per_sm", 8)
+        cur.wait_stream(self.sx)
+        cur.wait_stream(self.sy)
+        return out

@@ -204,6 +204,15 @@ CC_API int cc_find_routed_dev(cc_graph *g, const uint64_t *dev_inbox, const uint
 CC_API int cc_gather_routed_dev(int device, const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards,
                                 uint64_t cap, int64_t *dev_out, void *stream);
 
+/* ---------------------------------------------------------------- next rows: merged view of several graphs */
+/* CortexCollection / Join (S/utils/io/graph/cortex/CortexCollection.java:34-62,245-293, S/commands/utils/Join.java:23-57):
+ * the sorted union of the graphs' k-mers; colours concatenated in argument order; a k-mer absent from a graph has
+ * coverage 0 and no edges in that graph's colours.  All graphs on one device, same k.  Returns a new device-resident
+ * graph (dispose with cc_dispose). */
+CC_API int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out);
+/* CortexGraphWriter (S/utils/io/graph/cortex/CortexGraphWriter.java:31-138): header from the colours, then every record. */
+CC_API int cc_write_graph(const cc_graph *g, const char *path);
+
 /* ---------------------------------------------------------------- instrumentation */
 CC_API int cc_last_stats(const cc_graph *g, cc_stats *out);
 /* Total kernels this library has launched in this process (bench.py's gpu_launches). */

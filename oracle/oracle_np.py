@@ -370,3 +370,38 @@ def temp_graph_assembler(haplotypes: list[tuple[str, list[str]]], k: int) -> byt
                 if b in outs[c]: e |= 1 << i
             body["edges"][r, c] = e
     return write_header(k, s, colors) + body.tobytes()
+
+
+# ----------------------------------------------------------------------------- Join / CortexCollection
+
+def join(bufs: list[bytes]) -> bytes:
+    """S/commands/utils/Join.java:23-57 over S/utils/io/graph/cortex/CortexCollection.java:34-62,245-293:
+    the ascending union of the graphs' k-mers, colours concatenated in argument order, coverage 0 / no edges in the
+    colours of a graph that lacks the k-mer; header written by CortexGraphWriter from the input colours -- with
+    total_sequence byte-reversed, because the reference reads that field big-endian (BinaryFile.java:34-38) and
+    writes it little-endian (CortexGraphWriter.java:60-63)."""
+    hdrs = [parse_header(b) for b in bufs]
+    k, s = hdrs[0]["kmer_size"], hdrs[0]["kmer_bits"]
+    for h in hdrs:
+        if h["kmer_size"] != k:
+            raise CortexFormatError("Graph kmer sizes are not equal")          # CortexCollection.java:43-45
+    recs = [records_view(b, h) for b, h in zip(bufs, hdrs)]
+    be = [np.ascontiguousarray(r["kmer"]).astype(">u8").view(np.dtype((np.void, 8 * s))).reshape(-1) for r in recs]
+    allk = np.unique(np.concatenate(be)) if sum(len(x) for x in be) else np.zeros(0, dtype=be[0].dtype)
+    ctot = sum(h["num_colors"] for h in hdrs)
+    out = np.zeros(len(allk), dtype=record_dtype(s, ctot))
+    out["kmer"] = allk.view(">u8").reshape(-1, s).astype("<u8")
+    c0 = 0
+    for r, keys, h in zip(recs, be, hdrs):
+        c = h["num_colors"]
+        pos = np.searchsorted(allk, keys)
+        out["cov"][pos, c0:c0 + c] = r["cov"]
+        out["edges"][pos, c0:c0 + c] = r["edges"]
+        c0 += c
+    colors = []
+    for h in hdrs:
+        for col in h["colors"]:
+            col = dict(col)
+            col["total_sequence"] = int.from_bytes(int(col["total_sequence"]).to_bytes(8, "little"), "big")
+            colors.append(col)
+    return write_header(k, s, colors) + out.tobytes()

@@ -510,3 +510,54 @@ def test_large_ascii_batch_uses_two_pass_path():
     assert (got[sub] == og.find_batch(q_ascii.numpy()[sub])).all()
     assert (got >= 0).sum() > 30000
     g.dispose()
+
+
+# ------------------------------------------------------------------ next row: CortexCollection / Join
+
+@pytest.mark.parametrize("k,colors,sizes", [(31, (1, 1), (5000, 7000)), (47, (1, 1, 1, 1), (20000, 30000, 25000, 9000)),
+                                            (63, (2, 3), (4000, 4001)), (47, (4, 1), (50000, 3)), (31, (1, 2), (0, 500)),
+                                            (95, (1, 1, 1), (3000, 1, 2999))])
+def test_join_vs_oracle(tmp_path, k, colors, sizes):
+    """cc_join / Join.execute against the oracle's union (CortexCollection.next semantics): overlapping key sets
+    (every graph draws from one pool so many k-mers are shared), colour remap, absent k-mers zero-filled, header."""
+    from oracle import oracle_np as onp
+    pool = synth.random_canonical_keys(123 + k, int(max(sizes) * 1.5) + 10, k, "cpu")
+    ctxs, graphs = [], []
+    for gi, (c, n) in enumerate(zip(colors, sizes)):
+        g = torch.Generator().manual_seed(1000 + gi)
+        pick = torch.sort(torch.randperm(len(pool[0]), generator=g)[:n]).values
+        words = [w[pick] for w in pool]
+        cov, edges = synth.coverage_and_edges(50 + gi, n, c, "cpu", adv_period=0)
+        body = synth.assemble_records(words, cov, edges) if n else torch.zeros((0, 8 * len(pool) + 5 * c), dtype=torch.uint8)
+        names = ["g%d_c%d" % (gi, j) for j in range(c)]
+        ctx = synth.header_bytes(k, c, names) + body.numpy().tobytes()
+        ctxs.append(ctx)
+        p = tmp_path / ("g%d.ctx" % gi)
+        p.write_bytes(ctx)
+        graphs.append(cb.CortexGraph(p))
+    want = onp.join(ctxs)
+    out = tmp_path / "joined.ctx"
+    n = cb.Join(graphs, out).execute()
+    got = out.read_bytes()
+    hw = onp.parse_header(want)
+    assert n == hw["num_records"]
+    assert got == want
+    # the merged view behaves like a graph: iteration order, colour names, lookups
+    coll = cb.CortexCollection(graphs)
+    assert coll.getNumColors() == sum(colors) and coll.getSampleName(sum(colors) - 1) == "g%d_c%d" % (len(colors) - 1, colors[-1] - 1)
+    if n:
+        rec = coll.getRecord(n // 2)
+        assert coll.findRecord(rec.getKmerAsString()) == rec
+        assert coll.getGraph(sum(colors) - 1) is graphs[-1]
+    coll.merged.dispose()
+    for g in graphs:
+        g.dispose()
+
+
+def test_join_rejects_mismatched_k(tmp_path):
+    a = cb.CortexGraph(synth.make_ctx_file(1, 100, 31, 1, adv_period=0))
+    b = cb.CortexGraph(synth.make_ctx_file(2, 100, 33, 1, adv_period=0))
+    with pytest.raises(cb.CortexJDKException) as ei:
+        cb.CortexGraph.join([a, b])
+    assert "kmer sizes are not equal" in str(ei.value)
+    a.dispose(); b.dispose()

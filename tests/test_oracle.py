@@ -313,3 +313,24 @@ def test_writer_round_trip():                                            # Corte
     again = onp.write_header(h["kmer_size"], h["kmer_bits"], h["colors"]) + rec.tobytes()
     assert again == ctx
     assert [c["sample_name"] for c in h["colors"]] == ["mom", "dad", "kid"]
+
+
+# ---------------------------------------------------------------- Join / CortexCollection (CortexCollectionTest :34-111)
+
+def test_join_oracle_matches_assembler():
+    """Joining per-sample graphs gives the multi-colour graph TempGraphAssembler builds from the same haplotypes
+    (coverage = occurrence count per sample), which is how CortexCollectionTest checks merged iteration."""
+    rng = random.Random(5)
+    haps = [(nm, ["".join(rng.choice("ACGT") for _ in range(300))]) for nm in ("mom", "dad", "kid")]
+    whole = onp.temp_graph_assembler(haps, 7)
+    parts = [onp.temp_graph_assembler([h], 7) for h in haps]
+    joined = onp.join(parts)
+    hw, hj = onp.parse_header(whole), onp.parse_header(joined)
+    assert hj["num_colors"] == 3 and [c["sample_name"] for c in hj["colors"]] == ["mom", "dad", "kid"]
+    rw, rj = onp.records_view(whole, hw), onp.records_view(joined, hj)
+    assert hw["num_records"] == hj["num_records"]
+    assert (rw["kmer"] == rj["kmer"]).all() and (rw["cov"] == rj["cov"]).all()
+    # edges of a k-mer inside one sample's graph are the union over that sample only: identical to the assembler's per-colour edges
+    assert (rw["edges"] == rj["edges"]).all()
+    one = onp.join([parts[0]])
+    assert onp.records_view(one, onp.parse_header(one)).tobytes() == onp.records_view(parts[0], onp.parse_header(parts[0])).tobytes()
