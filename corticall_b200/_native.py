@@ -81,6 +81,7 @@ SIGNATURES = {
     "cc_find_routed_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "cc_gather_routed_dev": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint64, _P, _P]),
     "cc_join": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "cc_sort": (C.c_int, [_P, C.POINTER(_P)]),
     "cc_write_graph": (C.c_int, [_P, C.c_char_p]),
     "cc_last_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "cc_launch_count": (C.c_uint64, []),

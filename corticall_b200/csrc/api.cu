@@ -993,6 +993,42 @@ int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out) {
     return CC_OK;
 }
 
+// Sort (S/commands/utils/Sort.java:19-50): records in ascending k-mer order (stable, like Arrays.sort on objects), same
+// header.  Accepts the hash-ordered graphs McCortex writes; the result satisfies findRecord's sortedness requirement.
+int cc_sort(cc_graph *g_in, cc_graph **out) {
+    if (!g_in || !out) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(g_in->device);
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(new cc_graph(), destroy);
+    g->path = "<sort>";
+    g->h = g_in->h;
+    g->h.data_offset = 0;
+    if (int rc = init_handle(g.get(), g_in->device)) return rc;
+    const uint64_t n = g_in->h.num_records;
+    const uint32_t s = g_in->h.s, S = (uint32_t)g_in->h.record_size;
+    if (s > 4) return fail(CC_ERR_UNSUPPORTED, "k-mers wider than 4 words (k > 128) are not supported by sort");
+    void *body = nullptr;
+    CC_CUDA(cudaMalloc(&body, n * S + 256));
+    g->dev_alloc = body;
+    g->dev_body = static_cast<const uint8_t *>(body);
+    if (n) {
+        uint64_t *keys = nullptr;
+        CC_CUDA(cudaMalloc(&keys, std::max<uint64_t>(n * s, 2) * 8 + 64));
+        struct K { uint64_t *p; ~K() { cudaFree(p); } } kf{keys};
+        if (int rc = g->scan_ws.ensure(0, 0)) return rc;
+        if (int rc = launch_decode_columns(g_in->dev_body, n, s, g_in->h.c, keys, nullptr, nullptr, g->scan_ws, g->sm_count, g->stream)) return rc;
+        uint32_t *perm = nullptr;
+        if (int rc = sort_permutation(keys, n, s, g_in->h.k, g->stream, &perm)) return rc;
+        int rc = launch_gather_records(g_in->dev_body, perm, n, S, static_cast<uint8_t *>(body), g->stream);
+        cudaFreeAsync(perm, g->stream);
+        if (rc) return rc;
+    }
+    CC_CUDA(cudaMemsetAsync(static_cast<uint8_t *>(body) + n * S, 0, 256, g->stream));
+    CC_CUDA(cudaStreamSynchronize(g->stream));
+    *out = g.release();
+    return CC_OK;
+}
+
 // CortexGraphWriter.initialize :31-104 + one write of the whole body.  total_sequence is emitted the way the reference
 // does after ITS round trip: it reads the field big-endian (BinaryFile.readUnsignedLong :34-38) and writes it
 // little-endian (:60-63), i.e. byte-reversed with respect to the input file.

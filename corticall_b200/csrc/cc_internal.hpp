@@ -153,6 +153,8 @@ int launch_bucket_by_owner(const uint64_t *dev_words, const uint8_t *dev_flags, 
 int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n, int64_t *dev_out, cudaStream_t st);
 int join_pair(const uint8_t *body_a, const uint64_t *keys_a, uint64_t na, uint32_t ca, const uint8_t *body_b, const uint64_t *keys_b,
               uint64_t nb, uint32_t cb, uint32_t s, cudaStream_t st, void **out_body, uint64_t *out_n);
+int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t k, cudaStream_t st, uint32_t **perm_out);
+int launch_gather_records(const uint8_t *body, const uint32_t *perm, uint64_t n, uint32_t S, uint8_t *out, cudaStream_t st);
 int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s, const uint64_t *dev_splitters, int nshards,
                  int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, uint32_t *dev_slots, uint64_t *dev_sent,
                  int64_t *dev_out, cudaStream_t st);

@@ -8,7 +8,7 @@
 //   S/commands/utils/Join.java:23-57                        Join = write that stream with CortexGraphWriter
 //
 // B200 design.  A k-way merge is folded into two-way unions.  One union of A and B (sorted, duplicate-free key columns):
-// merge-path partition of the merged order (ties: A first) into tiles, a counting pass (a B key equal to the A key right
+// every thread finds its slice of the merged order (ties: A first) by a merge-path search, a counting pass (a B key equal to the A key right
 // before it is a duplicate and yields no output of its own), an exclusive scan of the tile counts, an emit pass that
 // writes, for every output record, the source index in A and in B (or -1), and a compose pass that gathers both source
 // records into the wider output record through shared memory so the output leaves as aligned 16-byte stores.
@@ -56,13 +56,6 @@ __device__ __forceinline__ uint64_t merge_path(const uint64_t *__restrict__ A, u
         if (key_le<S>(a, b)) lo = mid + 1; else hi = mid;
     }
     return lo;
-}
-
-template <int S>
-__global__ void partition_kernel(const uint64_t *__restrict__ A, uint64_t na, const uint64_t *__restrict__ B, uint64_t nb,
-                                 uint64_t ntiles, uint64_t *__restrict__ tile_a) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t <= ntiles) tile_a[t] = merge_path<S>(A, na, B, nb, min(t * (uint64_t)kTile, na + nb));
 }
 
 // Walks this thread's kVT merged elements.  EMIT=false: returns how many output records they start.
@@ -190,6 +183,35 @@ __global__ void __launch_bounds__(kComposeRecords) compose_kernel(const ComposeP
     }
 
 }  // namespace
+
+// out[i] = body[perm[i]] for whole records, staged through shared memory so the output leaves as aligned 16-byte stores
+__global__ void __launch_bounds__(kComposeRecords) gather_records_kernel(const uint8_t *__restrict__ body, const uint32_t *__restrict__ perm,
+                                                                         uint64_t n, uint32_t S, uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t gat_smem[];
+    const uint64_t r = (uint64_t)blockIdx.x * kComposeRecords + threadIdx.x;
+    if (r < n) {
+        const uint8_t *src = body + (uint64_t)perm[r] * S;
+        uint8_t *d = gat_smem + (size_t)threadIdx.x * S;
+        for (uint32_t i = 0; i < S; ++i) d[i] = src[i];
+    }
+    __syncthreads();
+    const uint64_t r0 = (uint64_t)blockIdx.x * kComposeRecords;
+    const uint64_t nbytes = min((uint64_t)kComposeRecords, n - r0) * S;
+    uint8_t *dst = out + r0 * S;
+    const uint64_t n16 = nbytes >> 4;
+    for (uint64_t i = threadIdx.x; i < n16; i += kComposeRecords) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(gat_smem)[i];
+    for (uint64_t i = (n16 << 4) + threadIdx.x; i < nbytes; i += kComposeRecords) dst[i] = gat_smem[i];
+}
+
+int launch_gather_records(const uint8_t *body, const uint32_t *perm, uint64_t n, uint32_t S, uint8_t *out, cudaStream_t st) {
+    if (n == 0) return CC_OK;
+    const size_t smem = (size_t)kComposeRecords * S;
+    CC_CUDA(cudaFuncSetAttribute(gather_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gather_records_kernel<<<(unsigned)((n + kComposeRecords - 1) / kComposeRecords), kComposeRecords, smem, st>>>(body, perm, n, S, out);
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
 
 // Two-way union on the device.  keys_* are the sorted key columns; body_* the record arrays.  Allocates *out_body
 // (caller frees with cudaFree) and returns the number of output records.

@@ -813,6 +813,35 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
     return CC_OK;
 }
 
+// Stable ascending order of n multi-word keys: LSD radix sort by (word s-1 ... word 0), carrying the permutation.
+// *perm_out is stream-ordered memory (cudaFreeAsync).
+int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t k, cudaStream_t st, uint32_t **perm_out) {
+    if (n >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "sorting is limited to 2^32-1 keys");
+    uint32_t *perm_a = nullptr, *perm_b = nullptr; uint64_t *key_a = nullptr, *key_b = nullptr; void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    CC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_a, key_b, perm_a, perm_b, (int64_t)n, 0, 64, st));
+    CC_CUDA(cudaMallocAsync(&perm_a, std::max<uint64_t>(n, 1) * 4, st)); CC_CUDA(cudaMallocAsync(&perm_b, std::max<uint64_t>(n, 1) * 4, st));
+    CC_CUDA(cudaMallocAsync(&key_a, std::max<uint64_t>(n, 1) * 8, st)); CC_CUDA(cudaMallocAsync(&key_b, std::max<uint64_t>(n, 1) * 8, st));
+    CC_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
+    const int grid = grid_for(std::max<uint64_t>(n, 1), kBlock, sm_count_now(), 8);
+    iota_kernel<<<grid, kBlock, 0, st>>>(perm_a, n); count_launch();
+    const uint32_t top_bits = 2u * k - 64u * (s - 1);
+    int rc = CC_OK;
+    for (int w = (int)s - 1; w >= 0 && rc == CC_OK && n > 0; --w) {
+        CC_DISPATCH_S(s, extract_word_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, perm_a, n, w, key_a));
+        count_launch();
+        const int end_bit = (w == 0) ? (int)top_bits : 64;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_a, key_b, perm_a, perm_b, (int64_t)n, 0, end_bit, st);
+        count_launch(2 * ((end_bit + 7) / 8));
+        if (e != cudaSuccess) rc = cuda_fail(e, "cub::DeviceRadixSort::SortPairs", __FILE__, __LINE__);
+        std::swap(perm_a, perm_b);
+    }
+    cudaFreeAsync(perm_b, st); cudaFreeAsync(key_a, st); cudaFreeAsync(key_b, st); cudaFreeAsync(tmp, st);
+    if (rc) { cudaFreeAsync(perm_a, st); return rc; }
+    *perm_out = perm_a;
+    return CC_OK;
+}
+
 int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, int64_t *dev_index,
                        int algo, cudaStream_t st) {
     if (int rc = check_k(g->h.k)) return rc;
@@ -821,32 +850,11 @@ int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *de
     const uint32_t s = g->h.s;
     const int grid = grid_for(nq, kBlock, g->sm_count, 8);
     if (algo == CC_ALGO_MERGE) {
-        if (nq >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "sorted-merge batches are limited to 2^32-1 queries");
-        // LSD radix sort of the batch by (word s-1 ... word 0), carrying the permutation.
-        uint32_t *perm_a = nullptr, *perm_b = nullptr; uint64_t *key_a = nullptr, *key_b = nullptr; void *tmp = nullptr;
-        size_t tmp_bytes = 0;
-        CC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_a, key_b, perm_a, perm_b, (int64_t)nq, 0, 64, st));
-        CC_CUDA(cudaMallocAsync(&perm_a, nq * 4, st)); CC_CUDA(cudaMallocAsync(&perm_b, nq * 4, st));
-        CC_CUDA(cudaMallocAsync(&key_a, nq * 8, st)); CC_CUDA(cudaMallocAsync(&key_b, nq * 8, st));
-        CC_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
-        iota_kernel<<<grid, kBlock, 0, st>>>(perm_a, nq); count_launch();
-        const uint32_t top_bits = 2u * g->h.k - 64u * (s - 1);
-        int rc = CC_OK;
-        for (int w = (int)s - 1; w >= 0 && rc == CC_OK; --w) {
-            CC_DISPATCH_S(s, extract_word_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, perm_a, nq, w, key_a));
-            count_launch();
-            const int end_bit = (w == 0) ? (int)top_bits : 64;
-            cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_a, key_b, perm_a, perm_b, (int64_t)nq, 0, end_bit, st);
-            count_launch(2 * ((end_bit + 7) / 8));
-            if (e != cudaSuccess) rc = cuda_fail(e, "cub::DeviceRadixSort::SortPairs", __FILE__, __LINE__);
-            std::swap(perm_a, perm_b);
-        }
-        if (rc == CC_OK) {
-            CC_DISPATCH_S(s, find_sorted_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, perm_a, nq, ix, dev_index));
-            count_launch();
-        }
-        cudaFreeAsync(perm_a, st); cudaFreeAsync(perm_b, st); cudaFreeAsync(key_a, st); cudaFreeAsync(key_b, st); cudaFreeAsync(tmp, st);
-        if (rc) return rc;
+        uint32_t *perm = nullptr;
+        if (int rc = sort_permutation(dev_words, nq, s, g->h.k, st, &perm)) return rc;
+        CC_DISPATCH_S(s, find_sorted_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, perm, nq, ix, dev_index));
+        count_launch();
+        cudaFreeAsync(perm, st);
     } else if (algo == CC_ALGO_BSEARCH) {
         CC_DISPATCH_S(s, find_packed_kernel<S_, false><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index));
         count_launch();

@@ -73,6 +73,20 @@ class Join:
         return n
 
 
+class Sort:
+    """`Sort -cg raw.ctx -o sorted.ctx` (S/commands/utils/Sort.java:12-51)."""
+
+    def __init__(self, CORTEX_GRAPH: CortexGraph, out):
+        self.CORTEX_GRAPH, self.out = CORTEX_GRAPH, out
+
+    def execute(self) -> int:
+        sg = self.CORTEX_GRAPH.sorted()
+        sg.writeGraph(self.out)
+        n = sg.getNumRecords()
+        sg.dispose()
+        return n
+
+
 class CortexVertex:
     """The three fields of utils/traversal/CortexVertex the child walk fills (bases, record, copy index)."""
 

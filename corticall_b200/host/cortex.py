@@ -462,6 +462,19 @@ class CortexGraph:
         self._nextRecord = self._record_at(0)
         return self
 
+    def sorted(self) -> "CortexGraph":
+        """Sort (S/commands/utils/Sort.java:19-50): the same records in ascending k-mer order, as a new graph."""
+        h = N._P()
+        N.check(N.lib().cc_sort(self._h, C.byref(h)))
+        other = CortexGraph.__new__(CortexGraph)
+        other._h, other._device, other._keep, other.cortexFile = h, self._device, None, None
+        other.firstIndex = 0
+        other._load_header()
+        other.recordsSeen = 0
+        other._block = None
+        other._nextRecord = other._record_at(0)
+        return other
+
     def writeGraph(self, out_path) -> None:
         """CortexGraphWriter over the whole graph (header from the colours, then every record)."""
         N.check(N.lib().cc_write_graph(self._h, os.fspath(out_path).encode()))

@@ -210,6 +210,8 @@ CC_API int cc_gather_routed_dev(int device, const int64_t *dev_ret, const uint32
  * coverage 0 and no edges in that graph's colours.  All graphs on one device, same k.  Returns a new device-resident
  * graph (dispose with cc_dispose). */
 CC_API int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out);
+/* Sort (S/commands/utils/Sort.java:19-50): a new graph with the records in ascending k-mer order (stable), same header. */
+CC_API int cc_sort(cc_graph *g, cc_graph **out);
 /* CortexGraphWriter (S/utils/io/graph/cortex/CortexGraphWriter.java:31-138): header from the colours, then every record. */
 CC_API int cc_write_graph(const cc_graph *g, const char *path);
 

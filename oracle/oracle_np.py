@@ -405,3 +405,18 @@ def join(bufs: list[bytes]) -> bytes:
             col["total_sequence"] = int.from_bytes(int(col["total_sequence"]).to_bytes(8, "little"), "big")
             colors.append(col)
     return write_header(k, s, colors) + out.tobytes()
+
+
+def sort_graph(buf: bytes) -> bytes:
+    """S/commands/utils/Sort.java:19-50: Arrays.sort of the records by k-mer string (stable), same header re-emitted by
+    CortexGraphWriter (total_sequence byte-reversed, see join())."""
+    h = parse_header(buf)
+    rec = records_view(buf, h)
+    be = np.ascontiguousarray(rec["kmer"]).astype(">u8").view(np.dtype((np.void, 8 * h["kmer_bits"]))).reshape(-1)
+    order = np.argsort(be, kind="stable")
+    colors = []
+    for col in h["colors"]:
+        col = dict(col)
+        col["total_sequence"] = int.from_bytes(int(col["total_sequence"]).to_bytes(8, "little"), "big")
+        colors.append(col)
+    return write_header(h["kmer_size"], h["kmer_bits"], colors) + rec[order].tobytes()

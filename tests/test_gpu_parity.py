@@ -130,6 +130,7 @@ SHAPES = [  # k, c, n
     (127, 5, 2000),      # 4 words
     (33, 7, 4097),
     (47, 4, 31), (47, 4, 32), (47, 4, 33), (47, 4, 3), (31, 2, 1),
+    (31, 45, 2500),      # 233-byte records: 256-record tiles do not fit -> the general (per-tile look-back) scan kernel
 ]
 
 
@@ -561,3 +562,29 @@ def test_join_rejects_mismatched_k(tmp_path):
         cb.CortexGraph.join([a, b])
     assert "kmer sizes are not equal" in str(ei.value)
     a.dispose(); b.dispose()
+
+
+@pytest.mark.parametrize("k,c,n", [(31, 2, 20000), (47, 4, 60000), (63, 21, 3000), (95, 1, 5000), (47, 4, 1), (31, 3, 0)])
+def test_sort_vs_oracle(tmp_path, k, c, n):
+    """cc_sort / Sort.execute on a shuffled (hash-ordered, as McCortex writes) graph: bit-exact file against the oracle's
+    stable sort; the sorted graph then serves lookups, which the shuffled one refuses."""
+    from oracle import oracle_np as onp
+    ctx = synth.make_ctx_file(11 + k, n, k, c, adv_period=0) if n else synth.header_bytes(k, c)
+    h = onp.parse_header(ctx)
+    rec = onp.records_view(ctx, h)
+    rng = np.random.default_rng(3)
+    shuffled = ctx[:h["data_offset"]] + rec[rng.permutation(n)].tobytes()
+    p = tmp_path / "raw.ctx"
+    p.write_bytes(shuffled)
+    raw = cb.CortexGraph(p)
+    out = tmp_path / "sorted.ctx"
+    assert cb.Sort(raw, out).execute() == n
+    assert out.read_bytes() == onp.sort_graph(shuffled)
+    if n > 100:
+        with pytest.raises(cb.CortexJDKException):
+            raw.findRecord("A" * k)
+        sg = cb.CortexGraph(out)
+        cr = sg.getRecord(n // 3)
+        assert sg.findRecord(cr.getKmerAsString()) == cr
+        sg.dispose()
+    raw.dispose()

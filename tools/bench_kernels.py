@@ -100,3 +100,31 @@ nwin = seq.numel() - k + 1
 res2 = torch.empty(nwin, dtype=torch.int64, device="cuda")
 ms = timeit(lambda: N.check(L.cc_find_windows_dev(g._h, seq.data_ptr(), seq.numel(), res2.data_ptr(), 0, st)), reps=5)
 print("lookup windows of a genome (all miss)      q=%.1e  %.3f ms  %.3g lookups/s" % (nwin, ms, nwin / ms * 1e3), flush=True)
+
+# ---- join (CortexCollection / Join): 4 single-colour graphs drawn from one pool -> 4-colour trio graph
+del g, body, table, qw, qf, res, a, seq, res2
+torch.cuda.empty_cache()
+nj = 25_000_000 if not quick else 5_000_000
+pool = synth.random_canonical_keys(77, int(nj * 1.3), 47, "cuda")
+gs, keep = [], []
+for gi in range(4):
+    gen = torch.Generator(device="cuda").manual_seed(gi)
+    pick = torch.sort(torch.randperm(len(pool[0]), generator=gen, device="cuda")[:nj]).values
+    cov, edges = synth.coverage_and_edges(gi, nj, 1, "cuda", adv_period=0)
+    b = synth.assemble_records([w[pick] for w in pool], cov, edges)
+    keep.append(b)
+    gg = cb.CortexGraph.fromDevice(b.data_ptr(), 47, 1, nj, keepalive=b)
+    gg.buildIndex()
+    gs.append(gg)
+torch.cuda.synchronize()
+import time
+for _ in range(2):
+    t0 = time.perf_counter()
+    j = cb.CortexGraph.join(gs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    nout = j.getNumRecords()
+    j.dispose()
+inb = 4 * nj * 21
+print("join   4 x %.1e single-colour k=47 graphs -> %.3e records x 36 B   %.2f ms   %.3g input records/s  %.0f GB/s (in+out bytes)" % (
+    nj, nout, dt * 1e3, 4 * nj / dt, (inb + nout * 36) / dt / 1e9), flush=True)
