@@ -40,7 +40,7 @@ struct Options {
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
     int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)
-    int scan_stage_buf_bytes = 2048;   // fast kernel: staging bytes per consumer warp per chunk parity
+    int scan_stage_buf_bytes = 4096;   // fast kernel: staging bytes (global scratch) per consumer warp per chunk parity
     int scan_debug = 0;          // diagnosis only: bit0 = skip the look-back (WRONG output positions)
 };
 Options &options();
@@ -64,6 +64,8 @@ std::vector<uint8_t> make_roi_header(uint32_t k, uint32_t s, const std::string &
 // ------------------------------------------------------------------ device workspace for the scan
 struct ScanWorkspace {
     uint64_t *tile_state = nullptr;   // look-back descriptors
+    uint8_t *scratch = nullptr;       // global staging lists of the fast scan kernel
+    size_t scratch_bytes = 0;
     uint64_t *dirty_list = nullptr;   // {chunk, prefix} pairs queued by the fast scan for the rewrite kernel
     uint64_t tile_state_cap = 0;
     uint32_t *tile_counter = nullptr; // dynamic tile ticket
@@ -74,6 +76,7 @@ struct ScanWorkspace {
     uint32_t epoch = 0;
     uint32_t ticket_base = 0;         // tickets drawn so far from tile_counter (host mirror)
     int ensure(uint64_t ntiles, uint32_t nparents);
+    int ensure_scratch(size_t bytes);
     void release();
 };
 

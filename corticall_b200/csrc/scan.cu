@@ -75,6 +75,7 @@ struct ScanKParams {
     uint32_t run_expect, skip_tickets;
     // fast kernel only
     uint32_t chunk_log2, num_chunks, stg_stride, stg_cap, Ow;
+    uint8_t *stg_scratch;               // global (L2-resident) staging lists: [grid][2][kConsumerWarps][stg_cap] entries
     uint32_t *overflow;
     // chunks whose staging list overflowed in the fast kernel: {chunk index, exclusive output prefix} pairs, rewritten
     // by redo_chunks_kernel.  dirty_ctl[0] = entries, [1] = ticket, [2] = CTAs done (reset by the last CTA to leave).
@@ -194,6 +195,52 @@ __device__ __forceinline__ uint64_t lookback(uint64_t *state, uint32_t tile, uin
     }
     if (lane == 0) st_relaxed_gpu(&state[tile], pack_desc(kFlagPrefix, epoch, excl + agg));
     return excl;
+}
+
+// Two-phase form of the look-back for a warp that serves several chunks at once.
+//   lookback_publish  announces the aggregate (chunk 0 announces its inclusive prefix straight away)
+//   lookback_try      one polling pass over the predecessors; false if any descriptor in reach is not there yet
+__device__ __forceinline__ void lookback_publish(uint64_t *state, uint32_t unit, uint64_t agg, uint32_t epoch, const uint64_t *total_in) {
+    if ((threadIdx.x & 31u) != 0) return;
+    if (unit == 0) st_relaxed_gpu(&state[0], pack_desc(kFlagPrefix, epoch, (total_in ? *total_in : 0ull) + agg));
+    else st_relaxed_gpu(&state[unit], pack_desc(kFlagAgg, epoch, agg));
+}
+__device__ __forceinline__ bool lookback_try(uint64_t *state, uint32_t unit, uint64_t agg, uint32_t epoch, const uint64_t *total_in,
+                                             uint64_t &excl_out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (unit == 0) { excl_out = total_in ? *total_in : 0ull; return true; }
+    const uint64_t want_epoch = (uint64_t)(epoch & kEpochMask);
+    uint64_t excl = 0;
+    int64_t idx = (int64_t)unit - 1;
+    while (true) {
+        const int64_t my = idx - (int64_t)lane;
+        uint64_t d = kFlagAgg;
+        bool ready = true;
+        if (my >= 0) {
+            d = ld_relaxed_gpu(&state[my]);
+            ready = (d & kFlagMask) != 0 && ((d >> 40) & kEpochMask) == want_epoch;
+        }
+        const uint32_t is_prefix = __ballot_sync(0xffffffffu, ready && (d & kFlagMask) == kFlagPrefix);
+        const uint32_t not_ready = __ballot_sync(0xffffffffu, !ready);
+        uint64_t v = (my >= 0 && ready) ? (d & kValueMask) : 0ull;
+        if (is_prefix) {
+            const uint32_t first = __ffs(is_prefix) - 1;       // nearest predecessor holding a prefix
+            if (not_ready & ((2u << first) - 1u)) return false;   // someone nearer than that prefix has not published yet
+            if (lane > first) v = 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            excl += v;
+            break;
+        }
+        if (not_ready) return false;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        idx -= 32;
+    }
+    if (lane == 0) st_relaxed_gpu(&state[unit], pack_desc(kFlagPrefix, epoch, excl + agg));
+    excl_out = excl;
+    return true;
 }
 
 // ------------------------------------------------------------------ K1+K2: novelty scan
@@ -373,19 +420,24 @@ __global__ void __launch_bounds__(kThreads, 2) scan_novel_kernel(const __grid_co
 // already filling the other staging buffer with the next chunk.  A chunk whose staging list overflows (dense
 // novelty) raises *overflow = epoch; the general kernel is launched right behind this one and runs only then.
 constexpr int kMaxChunkTiles = 16;
-constexpr uint32_t kStageBufBytes = 2048;          // staging bytes per consumer warp per segment parity
 
+// Consumers may run up to kSegRing chunks ahead of the scan warp: the look-back of a chunk has to wait for the slowest of
+// the concurrently running predecessor chunks, and with only two slots that wait stalled the streaming (measured: 10 %).
+constexpr int kSegRing = 8;
+constexpr uint32_t kFastCtrlBytes = 13312;
+constexpr uint32_t kMaxListed = 2048;          // staged records per chunk the scan warp can list (8 warps x stg_cap)
 struct FastCtrl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t seg_done[2];           // consumer warps -> scan warp: segment (chunk) fully evaluated and staged
-    uint64_t seg_free[2];           // scan warp -> consumer warps: staging buffer / counts of that parity are free
+    uint64_t seg_done[kSegRing];    // consumer warps -> scan warp: segment (chunk) fully evaluated and staged
+    uint64_t seg_free[kSegRing];    // scan warp -> consumer warps: staging lists / counts of that slot are free
     int32_t tile_id[kMaxStages];
-    int32_t seg_chunk[2];           // chunk index of the segment, -1 = no more work
-    uint32_t ovfw[2][kConsumerWarps];
-    uint32_t cnt[2][kMaxChunkTiles * kConsumerWarps];
+    int32_t seg_chunk[kSegRing];    // chunk index of the segment, -1 = no more work
+    uint32_t ovfw[kSegRing][kConsumerWarps];
+    uint32_t cnt[kSegRing][kMaxChunkTiles * kConsumerWarps];
+    uint32_t list[kMaxListed];      // scan warp: the chunk's staged records in output order, (warp << 24) | index
 };
-static_assert(sizeof(FastCtrl) <= kCtrlBytes, "control block too large");
+static_assert(sizeof(FastCtrl) <= kFastCtrlBytes, "control block too large");
 
 __device__ __forceinline__ void producer_loop_chunks(FastCtrl *ctrl, uint8_t *stage0, const ScanKParams &p) {
     const TileGeom &g = p.g;
@@ -424,12 +476,13 @@ template <bool ALIGNED4, int NP>
 __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __grid_constant__ ScanKParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     FastCtrl *ctrl = reinterpret_cast<FastCtrl *>(smem);
-    uint32_t *parents_s = reinterpret_cast<uint32_t *>(smem + kCtrlBytes);
+    uint32_t *parents_s = reinterpret_cast<uint32_t *>(smem + kFastCtrlBytes);
     const uint32_t parents_bytes = NP >= 0 ? 0u : (((uint32_t)p.nparents * 4u + 127u) & ~127u);
-    uint8_t *stg0 = smem + kCtrlBytes + parents_bytes;                          // [2][kConsumerWarps][stg_cap] entries
+    // Staging lists live in global memory (they are written at the novelty rate, well under 1 % of the traffic, and stay
+    // in L2), which leaves all of shared memory to the tile ring: more bytes in flight per SM, and room for long lists.
     const uint32_t stg_warp_bytes = p.stg_cap * p.stg_stride;
-    const uint32_t stg_bytes = (2u * kConsumerWarps * stg_warp_bytes + 127u) & ~127u;
-    uint8_t *stage0 = stg0 + stg_bytes;
+    uint8_t *stg0 = p.stg_scratch + (size_t)blockIdx.x * kSegRing * kConsumerWarps * stg_warp_bytes;   // [kSegRing][kConsumerWarps][stg_cap]
+    uint8_t *stage0 = smem + kFastCtrlBytes + parents_bytes;
 
     const TileGeom &g = p.g;
     if (NP < 0)
@@ -439,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
             mbar_init(&ctrl->full[i], 1);
             mbar_init(&ctrl->empty[i], kConsumerWarps);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSegRing; ++i) {
             mbar_init(&ctrl->seg_done[i], kConsumerWarps);
             mbar_init(&ctrl->seg_free[i], 1);
         }
@@ -455,14 +508,67 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
     const uint32_t T = 1u << p.chunk_log2;
 
     if (warp == kScanWarp) {
-        for (uint32_t seg = 0;; ++seg) {
-            const uint32_t par = seg & 1u, k = seg >> 1;
-            mbar_wait(&ctrl->seg_done[par], k & 1u, p.err, DEV_TIMEOUT_FULL);
+        // Two cursors over the ring of chunk slots: `pub` announces the aggregate of every chunk the consumers have
+        // finished AS SOON AS it is finished; `seg` resolves prefixes and copies out, in order.  Announcing must never
+        // queue behind a look-back that is itself waiting for other CTAs' announcements -- that feedback serialised
+        // the whole grid when both were done by one blocking loop.
+        uint32_t pub = 0, seg = 0;
+        bool end_seen = false;
+        auto announce = [&]() {
+            while (!end_seen && pub < seg + kSegRing) {
+                const uint32_t ppar = pub % kSegRing, pk = pub / kSegRing;
+                if (pub == seg) mbar_wait(&ctrl->seg_done[ppar], pk & 1u, p.err, DEV_TIMEOUT_FULL);
+                else if (!mbar_try_wait(&ctrl->seg_done[ppar], pk & 1u)) break;
+                const int32_t pchunk = ctrl->seg_chunk[ppar];
+                if (pchunk < 0) { end_seen = true; ++pub; break; }
+                const uint32_t pt0 = (uint32_t)pchunk << p.chunk_log2;
+                const uint32_t pnent = min(T, g.num_tiles - pt0) * kConsumerWarps;
+                uint32_t psum = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t e = (uint32_t)i * 32u + lane;
+                    psum += e < pnent ? ctrl->cnt[ppar][e] : 0u;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+                if (!(p.debug & 1u)) lookback_publish(p.tile_state, (uint32_t)pchunk, psum, p.epoch, p.total_in);
+                ++pub;
+            }
+        };
+        // one staged entry -> registers (independent word loads: one L2 round trip for the whole warp)
+        auto fetch = [&](uint32_t par, uint32_t r, uint32_t nrec, uint32_t (&wv)[12]) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) wv[i] = 0u;
+            if (r < nrec) {
+                const uint32_t dsc = ctrl->list[r];
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(stg0 + (size_t)(par * kConsumerWarps + (dsc >> 24)) * stg_warp_bytes +
+                                                                         (size_t)(dsc & 0xffffffu) * p.stg_stride);
+                const uint32_t nw = p.stg_stride >> 2;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) if ((uint32_t)i < nw) wv[i] = src[i];
+            }
+        };
+        auto emit = [&](uint64_t pos, uint64_t chunk_rec0, const uint32_t (&wv)[12]) {
+            if (pos >= p.cap) return;
+            uint8_t *dst = p.out + pos * p.O;
+#pragma unroll
+            for (int b = 0; b < 37; ++b)
+                if ((uint32_t)b < p.O) dst[b] = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
+            if (p.out_index) {
+                uint32_t rel = 0;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) if ((uint32_t)i == (p.Ow >> 2)) rel = wv[i];
+                p.out_index[pos] = p.index_base + chunk_rec0 + rel;
+            }
+        };
+        while (true) {
+            announce();
+            const uint32_t par = seg % kSegRing;
             const int32_t chunk = ctrl->seg_chunk[par];
-            if (chunk < 0) break;
+            if (chunk < 0) break;                      // (pub > seg here, so slot `par` has been waited for)
             const uint32_t t0 = (uint32_t)chunk << p.chunk_log2;
-            const uint32_t ntile = min(T, g.num_tiles - t0);
-            const uint32_t nent = ntile * kConsumerWarps;
+            const uint32_t nent = min(T, g.num_tiles - t0) * kConsumerWarps;
+            const uint64_t chunk_rec0 = (uint64_t)t0 * g.tile_records;
             uint32_t cv[4];
             uint32_t sum = 0;
 #pragma unroll
@@ -474,25 +580,17 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             const bool ovf = __any_sync(0xffffffffu, lane < kConsumerWarps && ctrl->ovfw[par][lane & 7u] != 0u);
-            const uint64_t total = sum;
-            const uint64_t excl = lookback(p.tile_state, (uint32_t)chunk, total, p.epoch, p.total_in, p.err);
-            if (ovf) {
-                if (lane == 0) {          // counts are exact, only the staged bytes were dropped: queue the chunk for a rewrite
-                    const uint32_t at = atomicAdd(&p.dirty_ctl[0], 1u);
-                    p.dirty_list[2ull * at] = (uint64_t)(uint32_t)chunk;
-                    p.dirty_list[2ull * at + 1] = excl;
-                }
-            } else if (sum != 0) {
-                // ---- copy the staged runs out in (tile, warp) order = input order.  Entry e = t*8 + w is held by
-                // lane e%32 in cv[e/32]; every lane copies its own (at most four, usually empty) runs, so the
-                // copy is a few dozen independent byte moves per lane instead of a serial walk over the runs.
-                const uint64_t chunk_rec0 = (uint64_t)t0 * g.tile_records;
+            const bool narrow = p.stg_stride <= 48u;                 // entry fits the register path (k <= 128)
+            const bool copy = sum != 0 && !ovf && !(p.debug & 4u);
+            uint32_t wa[12], wb[12];
+            if (copy) {
+                // ---- the chunk's staged records in (tile, warp) = input order: entry e = t*8 + w is held by lane e%32 in
+                // cv[e/32]; list[] gets (consumer warp, index in its staging list) for every record, in output order
                 uint32_t row_carry = 0;             // records in entries of earlier i (row-major prefix)
                 uint32_t col_carry = 0;             // records of warp (lane&7) in tiles of earlier i
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t v = cv[i];
-                    // exclusive prefix over entries in order (lanes ascending)
                     uint32_t inc = v;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -500,36 +598,60 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
                         if ((int)lane >= o) inc += t;
                     }
                     const uint32_t row_total = __shfl_sync(0xffffffffu, inc, 31);
-                    // records of the same consumer warp (same lane&7) in the earlier tiles of this group of four
                     const uint32_t u8 = __shfl_up_sync(0xffffffffu, v, 8);
                     const uint32_t u16 = __shfl_up_sync(0xffffffffu, v, 16);
                     const uint32_t u24 = __shfl_up_sync(0xffffffffu, v, 24);
                     const uint32_t col_pre = (lane >= 8 ? u8 : 0u) + (lane >= 16 ? u16 : 0u) + (lane >= 24 ? u24 : 0u);
                     uint32_t col_total = v + __shfl_xor_sync(0xffffffffu, v, 8);
                     col_total += __shfl_xor_sync(0xffffffffu, col_total, 16);
-                    if (v != 0) {
-                        const uint64_t pos0 = excl + row_carry + (inc - v);
-                        const uint32_t w = lane & (kConsumerWarps - 1u);
-                        const uint8_t *sp = stg0 + (size_t)(par * kConsumerWarps + w) * stg_warp_bytes +
-                                            (size_t)(col_carry + col_pre) * p.stg_stride;
-                        for (uint32_t q = 0; q < v; ++q) {
-                            const uint64_t pos = pos0 + q;
-                            if (pos < p.cap) {
-                                uint8_t *dst = p.out + pos * p.O;
-                                const uint8_t *src = sp + q * p.stg_stride;
-                                for (uint32_t b = 0; b < p.O; ++b) dst[b] = src[b];
-                                if (p.out_index)
-                                    p.out_index[pos] = p.index_base + chunk_rec0 + *reinterpret_cast<const uint32_t *>(src + p.Ow);
-                            }
-                        }
-                    }
+                    const uint32_t first = row_carry + (inc - v), start = col_carry + col_pre;
+                    for (uint32_t q = 0; q < v; ++q) ctrl->list[first + q] = ((lane & (kConsumerWarps - 1u)) << 24) | (start + q);
                     row_carry += row_total;
                     col_carry += col_total;
                 }
+                __syncwarp();
+                // the entries do not depend on the prefix: fetch the first 64 now, so their L2 round trip overlaps the look-back
+                if (narrow) { fetch(par, lane, sum, wa); fetch(par, lane + 32, sum, wb); }
             }
-            if ((uint32_t)chunk == p.num_chunks - 1 && lane == 0) *p.total_out = excl + total;
+            uint64_t excl = 0;
+            if (!(p.debug & 1u)) {
+                uint64_t t_start = 0;
+                while (!lookback_try(p.tile_state, (uint32_t)chunk, sum, p.epoch, p.total_in, excl)) {
+                    announce();                        // keep announcing while predecessors are still running
+                    if (t_start == 0) t_start = globaltimer_ns();
+                    else if (globaltimer_ns() - t_start > kWatchdogNs) watchdog_fail(p.err, DEV_TIMEOUT_LOOKBACK);
+                }
+            }
+            if (ovf) {
+                if (lane == 0) {          // counts are exact, only the staged bytes were dropped: queue the chunk for a rewrite
+                    const uint32_t at = atomicAdd(&p.dirty_ctl[0], 1u);
+                    p.dirty_list[2ull * at] = (uint64_t)(uint32_t)chunk;
+                    p.dirty_list[2ull * at + 1] = excl;
+                }
+            } else if (copy) {
+                if (narrow) {
+                    if (lane < sum) emit(excl + lane, chunk_rec0, wa);
+                    if (lane + 32 < sum) emit(excl + lane + 32, chunk_rec0, wb);
+                    for (uint32_t r = 64 + lane; r < sum; r += 32) {
+                        fetch(par, r, sum, wa);
+                        emit(excl + r, chunk_rec0, wa);
+                    }
+                } else {                            // very wide k-mers (k > 128): byte by byte
+                    for (uint32_t r = lane; r < sum; r += 32) {
+                        const uint64_t pos = excl + r;
+                        if (pos >= p.cap) continue;
+                        const uint32_t dsc = ctrl->list[r];
+                        const uint8_t *src = stg0 + (size_t)(par * kConsumerWarps + (dsc >> 24)) * stg_warp_bytes + (size_t)(dsc & 0xffffffu) * p.stg_stride;
+                        uint8_t *dst = p.out + pos * p.O;
+                        for (uint32_t b = 0; b < p.O; ++b) dst[b] = src[b];
+                        if (p.out_index) p.out_index[pos] = p.index_base + chunk_rec0 + *reinterpret_cast<const uint32_t *>(src + p.Ow);
+                    }
+                }
+            }
+            if ((uint32_t)chunk == p.num_chunks - 1 && lane == 0) *p.total_out = excl + sum;
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctrl->seg_free[par]);
+            ++seg;
         }
         return;
     }
@@ -549,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
         const uint32_t st = it % g.stages, ph = (it / g.stages) & 1u;
         mbar_wait(&ctrl->full[st], ph, p.err, DEV_TIMEOUT_FULL);
         const int32_t tile = ctrl->tile_id[st];
-        const uint32_t par = seg & 1u, k = seg >> 1;
+        const uint32_t par = seg % kSegRing, k = seg / kSegRing;
         if (tile < 0) {
             if (k >= 1) mbar_wait(&ctrl->seg_free[par], (k - 1u) & 1u, p.err, DEV_TIMEOUT_LOOKBACK);
             if (warp == 0 && lane == 0) ctrl->seg_chunk[par] = -1;
@@ -594,7 +716,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
                 if (m != 0) {
                     const uint32_t c = __popc(m);
                     if (fill + c <= p.stg_cap) {
-                        if (novel) {
+                        if (novel && !(p.debug & 8u)) {
                             // staged entry = the output record (s words verbatim, child coverage LE, child edge byte:
                             // CortexGraphWriter.addRecord :106-138), padded to Ow, then the chunk-relative record number
                             uint8_t *dst = stg + (size_t)(fill + __popc(m & lane_lt)) * p.stg_stride;
@@ -614,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_novel_fast_kernel(const __gr
         }
         if (lane == 0) ctrl->cnt[par][tin * kConsumerWarps + warp] = tile_cnt;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->empty[st]);
+        if (lane == 0) mbar_arrive_relaxed(&ctrl->empty[st]);      // the stage was only read; staging stores may still be in flight
         if (tin == T - 1u || (uint32_t)tile == g.num_tiles - 1u) {
             if (lane == 0) {
                 ctrl->ovfw[par][warp] = ovf;
@@ -953,7 +1075,19 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
     return CC_OK;
 }
 
+int ScanWorkspace::ensure_scratch(size_t bytes) {
+    if (bytes > scratch_bytes) {
+        if (scratch) CC_CUDA(cudaFree(scratch));
+        scratch = nullptr;
+        scratch_bytes = 0;
+        CC_CUDA(cudaMalloc(&scratch, bytes + 256));
+        scratch_bytes = bytes;
+    }
+    return CC_OK;
+}
+
 void ScanWorkspace::release() {
+    if (scratch) cudaFree(scratch);
     if (tile_state) cudaFree(tile_state);
     if (dirty_list) cudaFree(dirty_list);
     if (tile_counter) cudaFree(tile_counter);
@@ -982,11 +1116,11 @@ FastGeom pick_fast_geometry(uint64_t n, uint32_t S, uint32_t O, uint32_t extra_s
     const uint32_t stage_bytes = (R * S + 32u + 127u) & ~127u;
     f.Ow = (O + 3u) & ~3u;
     f.stg_stride = f.Ow + 4u;
-    f.stg_cap = (uint32_t)std::max(256, o.scan_stage_buf_bytes) / f.stg_stride;
+    f.stg_cap = std::min<uint32_t>((uint32_t)std::max(256, o.scan_stage_buf_bytes) / f.stg_stride, kMaxListed / kConsumerWarps);
     if (f.stg_cap < 4) return f;
-    f.stg_bytes = (2u * kConsumerWarps * f.stg_cap * f.stg_stride + 127u) & ~127u;
+    f.stg_bytes = (uint32_t)kSegRing * kConsumerWarps * f.stg_cap * f.stg_stride;          // per CTA, in the global scratch
     int stages = std::min(std::max(o.scan_stages, 2), kMaxStages);
-    const int64_t budget = (int64_t)max_smem_optin / std::max(ctas_per_sm, 1) - 1024 - kCtrlBytes - extra_smem - f.stg_bytes;
+    const int64_t budget = (int64_t)max_smem_optin / std::max(ctas_per_sm, 1) - 1024 - kFastCtrlBytes - extra_smem;
     while (stages > 2 && (int64_t)stages * stage_bytes > budget) --stages;
     if ((int64_t)stages * stage_bytes > budget) return f;
     if (((uint64_t)R * S + 31u) >= (1u << 20)) return f;
@@ -1058,7 +1192,9 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, f.num_chunks);
         q.ticket_base = ws.ticket_base;
         ws.ticket_base += f.num_chunks + grid;      // every CTA draws its chunks plus one terminal ticket
-        const size_t smem = kCtrlBytes + parents_bytes + f.stg_bytes + (size_t)f.g.stages * f.g.stage_bytes;
+        const size_t smem = kFastCtrlBytes + parents_bytes + (size_t)f.g.stages * f.g.stage_bytes;
+        if (int rc = ws.ensure_scratch((size_t)grid * f.stg_bytes)) return rc;
+        q.stg_scratch = ws.scratch;
         static const Kern ftable[2][kFastParents + 2] = {
             {scan_novel_fast_kernel<false, 0>, scan_novel_fast_kernel<false, 1>, scan_novel_fast_kernel<false, 2>,
              scan_novel_fast_kernel<false, 3>, scan_novel_fast_kernel<false, 4>, scan_novel_fast_kernel<false, -1>},

@@ -14,7 +14,7 @@ cap = n // 8
 out = torch.empty(cap * 21 + 64, dtype=torch.uint8, device="cuda"); cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 res = []
-for ctas, stg, tile, stages in itertools.product((2, 3, 4), (512, 1024, 2048), (16384, 20480, 24576, 28672, 32768, 40960), (2, 3, 4)):
+for ctas, stg, tile, stages in itertools.product((2, 3, 4), (2048, 8192), (16384, 20480, 28672, 40960, 49152), (2, 3, 4, 6)):
     for kname, v in (("scan_ctas_per_sm", ctas), ("scan_stage_buf_bytes", stg), ("scan_tile_bytes", tile), ("scan_stages", stages)):
         N.set_option(kname, v)
     step = lambda: N.check(L.cc_find_novel_dev(g._h, 0, parents.ctypes.data, 3, out.data_ptr(), None, cap, cnt.data_ptr(), st))
