@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <mutex>
 
 #include "cc_internal.hpp"
 
@@ -296,6 +297,19 @@ int ensure_index(cc_graph *g) {
                     (unsigned long long)g->index.unsorted_at);
     return CC_OK;
 }
+
+// Scratch from the device's stream-ordered pool (cached across calls: init_handle raises the release threshold).
+struct PoolBuf {
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t n, cudaStream_t stream) {
+        st = stream;
+        CC_CUDA(cudaMallocAsync(&p, std::max<size_t>(n, 16), stream));
+        return CC_OK;
+    }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
 
 struct DevBuf {
     void *p = nullptr;
@@ -588,11 +602,20 @@ int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s
     if (int rc = check_device(device)) return rc;
     if (k == 0 || s != (k + 31) / 32) return fail(CC_ERR_ARG, "kmer_bits %u does not match kmer_size %u", s, k);
     DeviceGuard guard(device);
-    // A transient handle over nothing: only its workspace, stream and header fields are used.
-    cc_graph *gp = nullptr;
-    if (int rc = cc_open_device(nullptr, k, s, c, 0, 0, device, &gp)) return rc;
-    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(gp, destroy);
+    // A handle over nothing, kept per device for the life of the process: only its workspace (look-back state, staging
+    // scratch -- tens of MB, too costly to allocate per call), stream and header fields are used.
+    static std::mutex mu;
+    static cc_graph *cache[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device >= 64) return fail(CC_ERR_ARG, "device %d out of range", device);
+    if (!cache[device]) {
+        if (int rc = cc_open_device(nullptr, k, s, c, 0, 0, device, &cache[device])) return rc;
+    }
+    struct Borrow { cc_graph *p; cc_graph *get() const { return p; } cc_graph *operator->() const { return p; } } g{cache[device]};
+    g->h.k = k; g->h.s = s; g->h.c = c;
+    g->h.record_size = 8ull * s + 5ull * c;
     g->h.num_records = n;
+    g->parents_cached.clear();
     if (int rc = check_colors(g.get(), child, parents, nparents)) return rc;
 
     const uint64_t S = g->h.record_size, O = 8ull * s + 5;
@@ -601,7 +624,7 @@ int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s
     if (chunk_rec < 32) chunk_rec = 32;
     const uint64_t nchunks = n ? (n + chunk_rec - 1) / chunk_rec : 0;
     constexpr int NB = 3;
-    DevBuf buf[NB], dout, didx;
+    PoolBuf buf[NB];
     cudaStream_t copy_st = nullptr;
     cudaEvent_t copied[NB] = {}, consumed[NB] = {}, t0 = nullptr, t1 = nullptr;
     struct Cleanup {
@@ -619,7 +642,7 @@ int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s
     for (int i = 0; i < NB; ++i) {
         CC_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
         CC_CUDA(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
-        if (i < (int)std::min<uint64_t>(nchunks, NB)) if (int rc = buf[i].alloc(chunk_rec * S + 256)) return rc;
+        if (i < (int)std::min<uint64_t>(nchunks, NB)) if (int rc = buf[i].alloc(chunk_rec * S + 256, g->stream)) return rc;
     }
     const uint64_t want = out_records ? std::min(cap, n) : 0;
     // device staging for the output: expected-small; the scan is re-run with a larger one if it overflows
@@ -629,9 +652,9 @@ int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s
     uint64_t h2d = 0;
     float total_ms = 0.f;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        DevBuf o, ix;
-        if (int rc = o.alloc(dcap * O + 64)) return rc;
-        if (out_index) if (int rc = ix.alloc(dcap * 8 + 64)) return rc;
+        PoolBuf o, ix;
+        if (int rc = o.alloc(dcap * O + 64, g->stream)) return rc;
+        if (out_index) if (int rc = ix.alloc(dcap * 8 + 64, g->stream)) return rc;
         if (int rc = prepare_scan(g.get(), chunk_rec, parents, nparents, g->stream)) return rc;
         uint64_t *totals = g->scan_ws.totals;     // [0],[1] ping-pong
         CC_CUDA(cudaMemsetAsync(totals, 0, 16, g->stream));
