@@ -402,6 +402,24 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         rl.find_packed(qwords, qflags, res, profile=True)
         out["phase_ms_rank0"] = rl.phase_ms
         del rl
+        # replicas: when the whole table fits every GPU (it does for configs[2]: 3.6 GB of records + 2.1 GB of index), each
+        # rank can hold a full copy and look up its own queries with no exchange at all (SURVEY 8e "alternative mode")
+        try:
+            words_all = synth.random_canonical_keys(SEED_LOOKUP, nt, K, dev)
+            covf, edgf = synth.coverage_and_edges(SEED_LOOKUP, nt, COLORS, dev)
+            full_body = synth.assemble_records(words_all, covf, edgf)
+            del covf, edgf, words_all
+            gfull = cb.CortexGraph.fromDevice(full_body.data_ptr(), K, COLORS, nt, firstIndex=0, device=local_rank, keepalive=full_body)
+            gfull.buildIndex()
+            res4 = torch.empty_like(res)
+            msr = timeit(lambda: N.check(L.cc_find_packed_dev(gfull._h, qwords.data_ptr(), qflags.data_ptr(), nq, res4.data_ptr(), cb.CC_ALGO_AUTO, stream)))
+            out["replicated_table_lookups_per_s"] = nq * world / (msr / 1000.0)
+            out["replicated_agrees"] = bool(torch.equal(res, res4))
+            gfull.dispose()
+            del full_body, res4
+        except Exception as e:          # comparison mode only
+            out["replicated_table_lookups_per_s"] = None
+            out["replicated_error"] = str(e)[:200]
         # the NCCL all-to-all formulation of the same exchange, as the comparison and as a cross-check of the results
         sl = ShardedLookup(g, splitters, rank, world, dev)
         res2 = torch.empty_like(res)

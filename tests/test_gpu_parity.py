@@ -588,3 +588,53 @@ def test_sort_vs_oracle(tmp_path, k, c, n):
         assert sg.findRecord(cr.getKmerAsString()) == cr
         sg.dispose()
     raw.dispose()
+
+
+def test_outputs_stay_inside_their_buffers():
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are hunted with canaries: every device
+    output of the scan (sparse, dense and capped), the column decode, the packer and the lookups is placed between two
+    guard regions that must come back untouched."""
+    k, c, n = 47, 4, 40_000
+    st = torch.cuda.current_stream().cuda_stream
+    L = N.lib()
+    GUARD = 4096
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf.data_ptr() + GUARD
+
+    def intact(buf, nbytes):
+        return bool((buf[:GUARD] == 0xA5).all()) and bool((buf[GUARD + nbytes:] == 0xA5).all())
+
+    for permille, parents in ((10, [1, 2, 3]), (10, [])):                 # sparse path / every chunk dense
+        body, words = synth.make_graph_body(21, n, k, c, device="cuda", novel_permille=permille, adv_period=0)
+        torch.cuda.synchronize()
+        g = cb.CortexGraph.fromDevice(body.data_ptr(), k, c, n, keepalive=body)
+        par = np.asarray(parents, dtype=np.int32)
+        for cap in (n, 100, 1, 0):
+            rb, rp = guarded(cap * 21)
+            ib, ip = guarded(cap * 8)
+            cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            N.check(L.cc_find_novel_dev(g._h, 0, par.ctypes.data if len(par) else None, len(par), rp if cap else None, ip if cap else None, cap,
+                                        cnt.data_ptr(), st))
+            torch.cuda.synchronize()
+            assert intact(rb, cap * 21) and intact(ib, cap * 8), (permille, parents, cap)
+            assert int(cnt[0]) > 0
+        wb, wp = guarded(n * 16); cb_, cp = guarded(n * 16); eb, ep = guarded(n * 4)
+        N.check(L.cc_decode_records_dev(g._h, 0, n, wp, cp, ep, st))
+        qa, canon, valid = synth.make_queries(4, [w.cpu() for w in words], k, 70_000)
+        qa = qa.cuda()
+        for fn in ("ascii", "windows"):
+            nq = 70_000 if fn == "ascii" else qa.numel() - k + 1
+            ob, op = guarded(nq * 8)
+            if fn == "ascii":
+                N.check(L.cc_find_ascii_dev(g._h, qa.data_ptr(), nq, op, 0, st))
+            else:
+                N.check(L.cc_find_windows_dev(g._h, qa.data_ptr(), qa.numel(), op, 0, st))
+            torch.cuda.synchronize()
+            assert intact(ob, nq * 8), fn
+        pb, pp = guarded(70_000 * 16); fb, fp = guarded(70_000)
+        N.check(L.cc_pack_kmers_dev(0, qa.data_ptr(), 70_000, k, pp, fp, st))
+        torch.cuda.synchronize()
+        assert intact(wb, n * 16) and intact(cb_, n * 16) and intact(eb, n * 4) and intact(pb, 70_000 * 16) and intact(fb, 70_000)
+        g.dispose()
