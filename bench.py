@@ -391,7 +391,7 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         out["algorithmic_gb_per_s"] = out["lookups_per_s"] * bpl / 1e9
     else:
         from corticall_b200.host.sharded import RoutedLookup
-        rl = RoutedLookup(g, splitters, rank, world, dev, cap=nq, s=S_WORDS)
+        rl = RoutedLookup(g, splitters, rank, world, dev, cap=nq, k=K)
         ms = timeit(lambda: rl.find_packed(qwords, qflags, res))
         out["lookups_per_s"] = nq * world / (ms / 1000.0)
         out["ms_per_step"] = ms

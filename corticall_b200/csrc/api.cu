@@ -355,6 +355,8 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
     else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
     else if (!strcmp(name, "lookup_queries_per_thread")) o.lookup_queries_per_thread = (int)value;
+    else if (!strcmp(name, "rows_fused")) o.rows_fused = (int)value;
+    else if (!strcmp(name, "rows_rpt2_max_k")) o.rows_rpt2_max_k = (int)value;
     else if (!strcmp(name, "route_blocks_per_sm")) o.route_blocks_per_sm = (int)value;
     else if (!strcmp(name, "routed_search_blocks_per_sm")) o.routed_search_blocks_per_sm = (int)value;
     else if (!strcmp(name, "gather_blocks_per_sm")) o.gather_blocks_per_sm = (int)value;
@@ -363,6 +365,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;
     else if (!strcmp(name, "scan_stage_buf_bytes")) o.scan_stage_buf_bytes = (int)value;
     else if (!strcmp(name, "scan_chunk_tiles")) o.scan_chunk_tiles = (int)value;
+    else if (!strcmp(name, "mlp_grid_per_sm")) o.mlp_grid_per_sm = (int)value;
     else return fail(CC_ERR_ARG, "unknown option '%s'", name);
     return CC_OK;
 }
@@ -926,18 +929,24 @@ int cc_scatter_results_dev(int device, const int64_t *dev_values, const uint32_t
 }
 
 // ---- routed lookups over peer memory (NVLink P2P): no collective library on the data path
-int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
-                         const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap, void *const *peer_inbox,
-                         void *const *peer_counts_in, uint32_t *dev_slots, uint64_t *dev_sent, int64_t *dev_out, void *stream) {
-    if (int rc = check_device(device)) return rc;
-    if (!peer_inbox || !peer_counts_in || !dev_sent || (nq && (!dev_words || !dev_slots || !dev_out)) || (nshards > 1 && !dev_splitters))
-        return fail(CC_ERR_ARG, "null argument");
-    DeviceGuard guard(device);
-    return launch_route(dev_words, dev_flags, nq, s, dev_splitters, nshards, my_rank, cap, peer_inbox, peer_counts_in, dev_slots, dev_sent,
-                        dev_out, static_cast<cudaStream_t>(stream));
+int cc_route_state_bytes(uint64_t max_queries, int nshards, uint64_t *out_bytes) {
+    if (!out_bytes || nshards < 1) return fail(CC_ERR_ARG, "null argument");
+    *out_bytes = route_state_size(max_queries, nshards);
+    return CC_OK;
 }
 
-int cc_find_routed_dev(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k,
+                         const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap, void *const *peer_inbox,
+                         void *const *peer_counts_in, void *dev_route_state, uint64_t max_queries, uint64_t *dev_sent, void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (!peer_inbox || !peer_counts_in || !dev_sent || (nq && (!dev_words || !dev_route_state)) || (nshards > 1 && !dev_splitters))
+        return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_route(dev_words, dev_flags, nq, k, dev_splitters, nshards, my_rank, cap, peer_inbox, peer_counts_in, dev_route_state,
+                        max_queries, dev_sent, static_cast<cudaStream_t>(stream));
+}
+
+int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
                        void *const *peer_ret, void *stream) {
     if (!g || !dev_inbox || !dev_counts_in || !peer_ret) return fail(CC_ERR_ARG, "null argument");
     DeviceGuard guard(g->device);
@@ -945,12 +954,12 @@ int cc_find_routed_dev(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *d
     return launch_find_routed(g, dev_inbox, dev_counts_in, nshards, my_rank, cap, peer_ret, static_cast<cudaStream_t>(stream));
 }
 
-int cc_gather_routed_dev(int device, const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
-                         int64_t *dev_out, void *stream) {
+int cc_gather_routed_dev(int device, const void *dev_ret, const void *dev_route_state, uint64_t max_queries, uint64_t nq,
+                         const uint64_t *dev_shard_first, int nshards, uint64_t cap, int64_t *dev_out, void *stream) {
     if (int rc = check_device(device)) return rc;
-    if (!dev_ret || !dev_slots || !dev_sent || !dev_out) return fail(CC_ERR_ARG, "null argument");
+    if (nq && (!dev_ret || !dev_route_state || !dev_shard_first || !dev_out)) return fail(CC_ERR_ARG, "null argument");
     DeviceGuard guard(device);
-    return launch_gather_routed(dev_ret, dev_slots, dev_sent, nshards, cap, dev_out, static_cast<cudaStream_t>(stream));
+    return launch_gather_routed(dev_ret, dev_route_state, max_queries, nq, dev_shard_first, nshards, cap, dev_out, static_cast<cudaStream_t>(stream));
 }
 
 // ==================================================================== next rows: merged view (CortexCollection / Join)

@@ -34,8 +34,11 @@ struct Options {
     int index_bits = 0;          // 0 = auto
     int lookup_block = 256;
     int lookup_queries_per_thread = 2;
+    int rows_rpt2_max_k = 32;    // cc_pack_kmers: two rows per thread (512-row tiles) up to this k, else one
+    int mlp_grid_per_sm = 8;     // find_packed_mlp_kernel: CTAs per SM (0 = resident CTAs only; measured 10 % slower)
+    int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1
-    int routed_search_blocks_per_sm = 8;  // grid of find_routed_kernel (resident blocks are limited by registers anyway)
+    int routed_search_blocks_per_sm = 3;  // grid of find_routed_kernel per SM (3 = the resident CTAs; measured best of 3/4/8/16)
     int gather_blocks_per_sm = 8;   // 0 = the single-query kernel
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
@@ -83,8 +86,10 @@ struct ScanWorkspace {
 // ------------------------------------------------------------------ lookup index
 struct LookupIndex {
     uint64_t *keys = nullptr;     // [n*s] native words, word 0 first
-    uint32_t *table = nullptr;    // [2^bits + 1] lower bounds
-    int bits = 0;
+    uint32_t *table = nullptr;    // [nbuckets + 2] lower bounds over the array's own key range
+    int bits = 0;                 // requested log2 of the bucket count
+    uint64_t base = 0;            // top 64 bits of the first key
+    uint32_t shift = 0, nbuckets = 1;
     bool built = false;
     bool sorted = true;
     uint64_t unsorted_at = 0;
@@ -158,12 +163,13 @@ int join_pair(const uint8_t *body_a, const uint64_t *keys_a, uint64_t na, uint32
               uint64_t nb, uint32_t cb, uint32_t s, cudaStream_t st, void **out_body, uint64_t *out_n);
 int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t k, cudaStream_t st, uint32_t **perm_out);
 int launch_gather_records(const uint8_t *body, const uint32_t *perm, uint64_t n, uint32_t S, uint8_t *out, cudaStream_t st);
-int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s, const uint64_t *dev_splitters, int nshards,
-                 int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, uint32_t *dev_slots, uint64_t *dev_sent,
-                 int64_t *dev_out, cudaStream_t st);
-int launch_find_routed(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+uint64_t route_state_size(uint64_t max_q, int nshards);
+int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k, const uint64_t *dev_splitters, int nshards,
+                 int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, void *dev_route_state, uint64_t max_q,
+                 uint64_t *dev_sent, cudaStream_t st);
+int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
                        void *const *peer_ret, cudaStream_t st);
-int launch_gather_routed(const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
-                         int64_t *dev_out, cudaStream_t st);
+int launch_gather_routed(const void *dev_ret, const void *dev_route_state, uint64_t max_q, uint64_t nq, const uint64_t *dev_shard_first,
+                         int nshards, uint64_t cap, int64_t *dev_out, cudaStream_t st);
 
 }  // namespace cc

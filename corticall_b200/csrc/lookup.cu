@@ -163,24 +163,32 @@ __device__ __forceinline__ void load_key(const uint64_t *__restrict__ keys, uint
 
 struct IndexView {
     const uint64_t *keys;
-    const uint32_t *table;
+    const uint32_t *table;      // nbuckets + 2 lower bounds; bucket `nbuckets` is the empty "outside the range" bucket
     uint64_t n;
     uint64_t first_index;
-    uint32_t bits;      // table covers the top `bits` bits of the 2k-bit key
-    uint32_t shift;     // 2k - bits
+    uint64_t base;              // top 64 bits (left-aligned) of the first key of THIS array
+    uint32_t nbuckets;
+    uint32_t shift;             // bucket = (top64(q) - base) >> shift
+    uint32_t k;
 };
 
+// The 64 most significant bits of the 2k-bit key, left-aligned.
 template <int S>
-__device__ __forceinline__ uint32_t key_prefix(const uint64_t (&q)[S], uint32_t shift) {
-    const uint32_t wsh = shift >> 6, bsh = shift & 63u;
-    const int hi_w = S - 1 - (int)wsh;
-    uint64_t low = 0;
-#pragma unroll
-    for (int w = 0; w < S; ++w) {
-        if (w == hi_w) low |= q[w] >> bsh;
-        if (w == hi_w - 1 && bsh) low |= q[w] << (64 - bsh);
-    }
-    return (uint32_t)low;
+__host__ __device__ __forceinline__ uint64_t key_top64(const uint64_t *q, uint32_t k) {
+    const uint32_t top_bits = 2u * k - 64u * (S - 1);          // bits used in word 0: 2..64
+    if (S == 1 || top_bits == 64) return q[0] << (64u - top_bits);
+    return (q[0] << (64u - top_bits)) | (q[S > 1 ? 1 : 0] >> top_bits);
+}
+
+// Bucket of a key in the prefix table.  The table spans only [first key, last key] of the array it indexes (a k-mer-range
+// shard covers 1/world of the key space; a table over the global top bits would leave most of its buckets empty and the
+// rest world times too long).  Keys outside the span land in the empty bucket `nbuckets`.
+template <int S>
+__device__ __forceinline__ uint32_t key_bucket(const IndexView &ix, const uint64_t (&q)[S]) {
+    const uint64_t t = key_top64<S>(q, ix.k);
+    if (t < ix.base) return ix.nbuckets;
+    const uint64_t b = (t - ix.base) >> ix.shift;
+    return b < ix.nbuckets ? (uint32_t)b : ix.nbuckets;
 }
 
 constexpr int kMaxShards = 64;
@@ -214,7 +222,7 @@ __device__ __forceinline__ int64_t search_range(const uint64_t *__restrict__ key
 
 template <int S>
 __device__ __forceinline__ int64_t lookup_bucketed(const IndexView &ix, const uint64_t (&q)[S]) {
-    const uint32_t p = key_prefix<S>(q, ix.shift);
+    const uint32_t p = key_bucket<S>(ix, q);
     const uint64_t lo = __ldg(ix.table + p), hi = __ldg(ix.table + p + 1);
     const int64_t r = search_range<S>(ix.keys, lo, hi, q);
     return r < 0 ? r : r + (int64_t)ix.first_index;
@@ -265,80 +273,6 @@ __global__ void __launch_bounds__(kBlock) seq_kernel(SeqJob job, uint64_t *__res
     }
 }
 
-// ------------------------------------------------------------------ K3 for independent k-byte rows (query lists)
-// A warp takes 32 consecutive rows (32*k contiguous bytes): 16-byte coalesced loads of the aligned superset into a
-// per-warp shared buffer, then lane i packs row i base by base.  Same flags and canonical rule as window_canonical.
-template <int S>
-__global__ void __launch_bounds__(kBlock) pack_rows_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
-                                                           uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags) {
-    extern __shared__ __align__(16) uint8_t rows_smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t wbytes = (32u * k + 32u + 15u) & ~15u;
-    uint8_t *buf = rows_smem + (size_t)warp * wbytes;
-    const uint64_t ngroups = (nq + 31) / 32;
-    const uint64_t gstride = (uint64_t)gridDim.x * (kBlock / 32);
-    for (uint64_t grp = (uint64_t)blockIdx.x * (kBlock / 32) + warp; grp < ngroups; grp += gstride) {
-        const uint64_t row0 = grp * 32;
-        const uint32_t rows = (uint32_t)min((uint64_t)32, nq - row0);
-        const uint8_t *src = kmers + row0 * k;
-        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
-        const uint4 *src4 = reinterpret_cast<const uint4 *>(src - shift);
-        const uint32_t n16 = (shift + rows * k + 15u) >> 4;
-        __syncwarp();
-        for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(buf)[i] = __ldg(src4 + i);
-        __syncwarp();
-        if (lane < rows) {
-            const uint8_t *a = buf + shift + lane * k;
-            uint64_t fw[S];
-#pragma unroll
-            for (int w = 0; w < S; ++w) fw[w] = 0;
-            uint32_t bad = 0, low = 0;
-            for (uint32_t i = 0; i < k; ++i) {
-                const uint32_t ch = a[i];
-                const uint32_t f = ch | 0x20u;
-                const bool ok = (f == 'a') | (f == 'c') | (f == 'g') | (f == 't');
-                bad |= ok ? 0u : 1u;
-                low |= (ok && (ch & 0x20u)) ? 1u : 0u;
-                const uint64_t code = ok ? base_code(ch) : 0u;
-#pragma unroll
-                for (int w = 0; w < S - 1; ++w) fw[w] = (fw[w] << 2) | (fw[w + 1] >> 62);
-                fw[S - 1] = (fw[S - 1] << 2) | code;
-            }
-            uint32_t flags = 0;
-            uint64_t outw[S];
-            if (bad) {
-#pragma unroll
-                for (int w = 0; w < S; ++w) outw[w] = 0;
-                flags = 2u;
-            } else {
-                uint64_t rc[S];
-                revcomp_words<S>(fw, rc, k);
-                bool flip = words_less<S>(rc, fw);
-                if (low) {          // mixed / lower case: the reference compares ASCII bytes (SequenceUtils.java:211-219)
-                    flags |= 4u;
-                    flip = false;
-                    for (uint32_t i = 0; i < k; ++i) {
-                        const int8_t f = (int8_t)a[i];
-                        const int8_t r = (int8_t)complement_ascii(a[k - 1 - i]);
-                        if (f < r) break;
-                        if (f > r) { flip = true; break; }
-                    }
-                }
-#pragma unroll
-                for (int w = 0; w < S; ++w) outw[w] = flip ? rc[w] : fw[w];
-                flags |= flip ? 1u : 0u;
-            }
-            const uint64_t row = row0 + lane;
-            if (S == 2) reinterpret_cast<ulonglong2 *>(out_words)[row] = make_ulonglong2(outw[0], outw[1 % S]);
-            else {
-#pragma unroll
-                for (int w = 0; w < S; ++w) out_words[row * S + w] = outw[w];
-            }
-            out_flags[row] = (uint8_t)flags;
-        }
-    }
-}
-
 template <int S, bool BUCKETED>
 __global__ void __launch_bounds__(kBlock) find_packed_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
                                                              uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
@@ -366,7 +300,7 @@ __device__ __forceinline__ void lookup_mlp(const IndexView &ix, const uint64_t (
     for (int j = 0; j < Q; ++j) {
         lo[j] = hi[j] = 0;
         if (live[j]) {
-            const uint32_t p = key_prefix<S>(q[j], ix.shift);
+            const uint32_t p = key_bucket<S>(ix, q[j]);
             lo[j] = __ldg(ix.table + p);
             hi[j] = __ldg(ix.table + p + 1);
         }
@@ -419,6 +353,253 @@ __global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t 
     }
 }
 
+// ------------------------------------------------------------------ K3 (+K4) for independent k-byte rows (query lists)
+// A CTA takes kRowsPerTile consecutive rows = one contiguous byte range.  Phase 1: every thread pulls 16-byte chunks of
+// the 16-byte-aligned superset straight into registers (coalesced LDG.128) and converts each to one 32-bit word of 2-bit
+// codes with byte-parallel arithmetic (4 bases per 32-bit op: code = ((u>>1)^(u>>2))&3 on u = byte & ~0x20, packed by one
+// multiply; validity by rebuilding the letter from its code with PRMT and comparing).  Only the code stream goes to shared
+// memory (0.25 byte per base).  A chunk holding anything but upper-case ACGT marks the rows it overlaps as suspect.
+// Phase 2: thread r cuts row r out of the stream with funnel shifts, reverse-complements in registers, keeps the smaller
+// and either writes words + flags (FIND = false) or searches the index with two rows in flight (FIND = true).
+// Suspect rows (N, lower case, other bytes: rare) take the reference's byte loop on the global bytes instead.
+constexpr uint32_t kRowPadWords = 2;           // 32 zero bases in front of the stream (word 0 of row 0 starts before it)
+
+__device__ __forceinline__ uint32_t codes_of_4(uint32_t w, uint32_t &diff) {
+    const uint32_t u = w & 0xdfdfdfdfu;                                   // upper-cased
+    const uint32_t x = ((u >> 1) ^ (u >> 2)) & 0x03030303u;              // 2-bit code in every byte (A0 C1 G2 T3)
+    const uint32_t y = x | (x >> 4);
+    const uint32_t z = y & 0x00ff00ffu;
+    const uint32_t sel = (z | (z >> 8)) & 0xffffu;                        // the four codes as PRMT selectors
+    diff |= u ^ __byte_perm(0x54474341u, 0u, sel);                        // 'A','C','G','T' rebuilt from the codes
+    return x * 0x40100401u;                                               // byte 3 = c0<<6 | c1<<4 | c2<<2 | c3
+}
+
+// Spread the 32 bits of x to the even bit positions of a 64-bit word.
+__device__ __forceinline__ uint64_t spread_bits(uint32_t x) {
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// Exact path for one row, evaluated by a whole warp (same flags and canonical rule as window_canonical): lane i looks
+// at bytes i, i+32, ...; the 2-bit planes are collected with ballots and interleaved into packed words; the reference's
+// "first differing byte decides" loop (SequenceUtils.java:211-219) becomes two ballots per 32 bytes.  Every lane
+// returns the same flags and words.  `a` may point to shared or global memory.
+template <int S>
+__device__ __forceinline__ uint32_t row_canonical_warp(const uint8_t *a, uint32_t k, uint32_t lane, uint64_t (&out)[S]) {
+    uint64_t t[S];                                   // the sequence left-aligned in 64*S bits
+    uint32_t bad = 0, low = 0;
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+        const uint32_t i = 32u * c + lane;
+        const bool in = i < k;
+        const uint32_t ch = in ? a[i] : (uint32_t)'A';
+        const uint32_t f = ch | 0x20u;
+        const bool ok = (f == 'a') | (f == 'c') | (f == 'g') | (f == 't');
+        bad |= __ballot_sync(0xffffffffu, in && !ok);
+        low |= __ballot_sync(0xffffffffu, in && ok && (ch & 0x20u));
+        const uint32_t code = ok ? base_code(ch) : 0u;
+        const uint32_t p0 = __brev(__ballot_sync(0xffffffffu, code & 1u)), p1 = __brev(__ballot_sync(0xffffffffu, code & 2u));
+        t[c] = (spread_bits(p1) << 1) | spread_bits(p0);     // lane 0 = first base = the two highest bits
+    }
+    if (bad) {
+#pragma unroll
+        for (int w = 0; w < S; ++w) out[w] = 0;
+        return 2u;
+    }
+    uint64_t fw[S], rc[S];
+    const uint32_t sh = 64u * S - 2u * k;                     // right-align (0..62, even)
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        uint64_t v = sh ? (t[i] >> sh) : t[i];
+        if (i > 0 && sh) v |= t[i - 1] << (64u - sh);
+        fw[i] = v;
+    }
+    revcomp_words<S>(fw, rc, k);
+    bool flip = words_less<S>(rc, fw);
+    uint32_t flags = 0;
+    if (low) {                                                // mixed / lower case: ASCII bytes decide, not 2-bit codes
+        flags |= 4u;
+        flip = false;
+#pragma unroll
+        for (int c = 0; c < S; ++c) {
+            const uint32_t i = 32u * c + lane;
+            const bool in = i < k;
+            const int8_t f = in ? (int8_t)a[i] : (int8_t)0;
+            const int8_t r = in ? (int8_t)complement_ascii(a[k - 1u - i]) : (int8_t)0;
+            const uint32_t lt = __ballot_sync(0xffffffffu, in && f < r), gt = __ballot_sync(0xffffffffu, in && f > r);
+            if (lt | gt) {
+                flip = (gt >> (__ffs(lt | gt) - 1)) & 1u;
+                break;
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < S; ++w) out[w] = flip ? rc[w] : fw[w];
+    return flags | (flip ? 1u : 0u);
+}
+
+// Shared memory of rows_kernel: two raw tiles (filled by 1-D bulk copies, the TMA engine) and two code streams.
+__host__ __device__ inline uint32_t rows_tile_bytes(uint32_t rows_per_tile, uint32_t k) { return (rows_per_tile * k + 15u + 15u) & ~15u; }
+__host__ __device__ inline uint32_t rows_stream_words(uint32_t rows_per_tile, uint32_t k) {
+    return ((rows_tile_bytes(rows_per_tile, k) / 16u + kRowPadWords + 3u) + 3u) & ~3u;
+}
+inline size_t rows_smem_bytes(uint32_t rows_per_tile, uint32_t k, bool find) {
+    return (find ? 2u : 3u) * (size_t)rows_tile_bytes(rows_per_tile, k) + 2u * (size_t)rows_stream_words(rows_per_tile, k) * 4u;
+}
+
+template <int S, bool FIND, int RPT>
+__global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
+                                                                                uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags,
+                                                                                IndexView ix, int64_t *__restrict__ out_index) {
+    constexpr uint32_t kRows = RPT * kBlock;                      // rows per tile
+    // Raw tiles in flight.  The pack variant keeps a tile's bytes until its phase 2 is over (the exact path for suspect rows
+    // reads them from shared memory), which takes a third buffer; the find variant reads those rare rows from global
+    // memory instead and keeps the shared memory for occupancy (the search needs the warps).
+    constexpr uint32_t NRAW = FIND ? 2u : 3u;
+    extern __shared__ __align__(128) uint8_t rows_smem[];
+    const uint32_t tile_cap = rows_tile_bytes(kRows, k), stream_cap = rows_stream_words(kRows, k);
+    uint32_t *const codes0 = reinterpret_cast<uint32_t *>(rows_smem + NRAW * tile_cap);   // raw tiles at 0, tile_cap, ...
+    __shared__ uint32_t suspect[3][kRows / 32];    // per tile in flight; see the clearing rule in phase 1
+    __shared__ __align__(8) uint64_t full[NRAW];
+    const uint64_t ntiles = (nq + kRows - 1) / kRows;
+    const uint32_t top_bits = 2u * k - 64u * (S - 1);
+    const uint64_t policy = make_evict_first_policy();
+
+    // tile t of this CTA: rows [row0, row0 + rows); the copy fetches the 16-byte-aligned superset of its bytes
+    auto issue = [&](uint64_t tile, uint32_t buf) {
+        const uint64_t row0 = tile * kRows;
+        const uint32_t rows = (uint32_t)min((uint64_t)kRows, nq - row0);
+        const uint8_t *src = kmers + row0 * k;
+        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint32_t bytes = (off + rows * k + 15u) & ~15u;
+        mbar_arrive_expect_tx(&full[buf], bytes);
+        bulk_g2s(rows_smem + buf * tile_cap, src - off, bytes, &full[buf], policy);
+    };
+
+    if (threadIdx.x == 0) {
+        for (uint32_t b = 0; b < NRAW; ++b) mbar_init(&full[b], 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 3 * (kRows / 32)) (&suspect[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x < kRowPadWords) codes0[threadIdx.x] = codes0[stream_cap + threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blockIdx.x < ntiles) issue(blockIdx.x, 0);
+        if (blockIdx.x + (uint64_t)gridDim.x < ntiles) issue(blockIdx.x + (uint64_t)gridDim.x, 1);
+    }
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1u, rb = it % NRAW;
+        const uint64_t row0 = tile * kRows;
+        const uint32_t rows = (uint32_t)min((uint64_t)kRows, nq - row0);
+        const uint8_t *src = kmers + row0 * k;
+        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint32_t nbytes = rows * k;
+        const uint32_t nchunks = (off + nbytes + 15u) >> 4;
+        const uint32_t sus = it % 3u;
+        // With one barrier per tile, suspect[(it+1)%3] was last read in phase 2 of tile it-2 (every thread is past the
+        // barrier of tile it-1, so done with it) and is next written in phase 1 of tile it+1 (after this tile's barrier).
+        if (threadIdx.x < kRows / 32) suspect[(it + 1u) % 3u][threadIdx.x] = 0;
+        mbar_wait(&full[rb], (it / NRAW) & 1u, nullptr, DEV_TIMEOUT_FULL);
+        // ---- phase 1: 16-byte chunks of the raw tile -> code words
+        const uint4 *raw = reinterpret_cast<const uint4 *>(rows_smem + rb * tile_cap);
+        uint32_t *stream = codes0 + par * stream_cap;
+#pragma unroll 2
+        for (uint32_t j = threadIdx.x; j < nchunks; j += kBlock) {
+            const uint4 v = raw[j];
+            uint32_t diff = 0;
+            const uint32_t m0 = codes_of_4(v.x, diff), m1 = codes_of_4(v.y, diff);
+            const uint32_t m2 = codes_of_4(v.z, diff), m3 = codes_of_4(v.w, diff);
+            const uint32_t lo = __byte_perm(m3, m2, 0x7373u), hi = __byte_perm(m1, m0, 0x7373u);
+            stream[kRowPadWords + j] = __byte_perm(lo, hi, 0x5410u);
+            diff |= (v.x | v.y | v.z | v.w) & 0x20202020u;
+            if (diff) {                                          // rare: mark every row this chunk overlaps
+                const int64_t b_lo = max((int64_t)16 * j - off, (int64_t)0);
+                const int64_t b_hi = min((int64_t)16 * j + 16 - off, (int64_t)nbytes);
+                if (b_lo < b_hi) {
+                    const uint32_t r0 = (uint32_t)b_lo / k, r1 = (uint32_t)(b_hi - 1) / k;
+                    for (uint32_t r = r0; r <= r1; ++r) atomicOr(&suspect[sus][r >> 5], 1u << (r & 31u));
+                }
+            }
+        }
+        if (threadIdx.x < 3) stream[kRowPadWords + nchunks + threadIdx.x] = 0;
+        __syncthreads();                                         // stream complete
+        // the tile after next goes into the raw buffer whose last readers are behind this barrier: this tile's own buffer
+        // (NRAW = 2: its phase 2 does not touch raw bytes) or the previous tile's (NRAW = 3)
+        if (threadIdx.x == 0 && tile + 2ull * gridDim.x < ntiles) issue(tile + 2ull * gridDim.x, (it + 2u) % NRAW);
+        // ---- phase 2: one thread per row
+        uint64_t q[RPT][S];
+        uint32_t flags[RPT];
+        bool have[RPT];
+#pragma unroll
+        for (int h = 0; h < RPT; ++h) {
+            const uint32_t r = threadIdx.x + h * kBlock;
+            have[h] = r < rows;
+            flags[h] = 2u;
+#pragma unroll
+            for (int w = 0; w < S; ++w) q[h][w] = 0;
+            const bool sus_row = have[h] && ((suspect[sus][r >> 5] >> (r & 31u)) & 1u);
+            // suspect rows (rare) are evaluated exactly, one at a time, by the whole warp
+            uint32_t todo = __ballot_sync(0xffffffffu, sus_row);
+            while (todo) {
+                const uint32_t sl = __ffs(todo) - 1u;
+                todo &= todo - 1u;
+                const uint32_t rs = (threadIdx.x & ~31u) + sl + h * kBlock;
+                const uint8_t *a = FIND ? src + (size_t)rs * k : rows_smem + rb * tile_cap + off + (size_t)rs * k;
+                uint64_t exact[S];
+                const uint32_t fl = row_canonical_warp<S>(a, k, threadIdx.x & 31u, exact);
+                if ((threadIdx.x & 31u) == sl) {
+                    flags[h] = fl;
+#pragma unroll
+                    for (int w = 0; w < S; ++w) q[h][w] = exact[w];
+                }
+            }
+            if (have[h] && !sus_row) {
+                const uint32_t p0 = 16u * kRowPadWords + off + r * k;           // stream position (in bases) of the row's first base
+                uint64_t fw[S], rc[S];
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const int32_t b0 = (int32_t)k - 32 * (S - j);                 // word j holds bases [b0, b0 + 32)
+                    fw[j] = extract64(stream, 2u * (uint32_t)((int32_t)p0 + b0));
+                }
+                if (top_bits < 64) fw[0] &= (1ull << top_bits) - 1ull;
+                revcomp_words<S>(fw, rc, k);
+                const bool flip = words_less<S>(rc, fw);
+#pragma unroll
+                for (int w = 0; w < S; ++w) q[h][w] = flip ? rc[w] : fw[w];
+                flags[h] = flip ? 1u : 0u;
+            }
+        }
+        if (FIND) {
+            bool live[RPT];
+            int64_t res[RPT];
+#pragma unroll
+            for (int h = 0; h < RPT; ++h) live[h] = have[h] && (flags[h] & 6u) == 0;
+            lookup_mlp<S, RPT>(ix, q, live, res);
+#pragma unroll
+            for (int h = 0; h < RPT; ++h)
+                if (have[h]) out_index[row0 + threadIdx.x + h * kBlock] = live[h] ? res[h] : -1;
+        } else {
+#pragma unroll
+            for (int h = 0; h < RPT; ++h) {
+                if (!have[h]) continue;
+                const uint64_t row = row0 + threadIdx.x + h * kBlock;
+                if (S == 2) reinterpret_cast<ulonglong2 *>(out_words)[row] = make_ulonglong2(q[h][0], q[h][1 % S]);
+                else {
+#pragma unroll
+                    for (int w = 0; w < S; ++w) out_words[row * S + w] = q[h][w];
+                }
+                out_flags[row] = (uint8_t)flags[h];
+            }
+        }
+    }
+}
+
 template <int S>
 __device__ __forceinline__ uint32_t owner_of(const uint64_t (&q)[S], const uint64_t *__restrict__ splitters, int nshards) {
     // number of splitters <= q  (splitter j = first key of shard j+1)
@@ -435,50 +616,104 @@ __device__ __forceinline__ uint32_t owner_of(const uint64_t (&q)[S], const uint6
 
 // ------------------------------------------------------------------ multi-GPU: routed lookups over peer memory
 // One kernel per leg, each fused with its transfer (no NCCL on the data path; buffers are peer-mapped over NVLink):
-//   route   owner of every query (splitter search) + block-aggregated reservation + P2P STORE of the key into the
-//           owner's inbox segment reserved for this rank; the original slot is kept locally
-//   search  the owner walks all inbox segments, searches its shard and P2P-STORES each result into the origin's
-//           return buffer at the same segment position
-//   gather  the origin scatters the returned indices to the original slots (local)
+//   route   owner of every query (splitter search) + block-aggregated reservation + P2P STORE of the key, in the
+//           compact wire format, into the owner's inbox segment reserved for this rank.  What stays local is only the
+//           tile bookkeeping: the position of every query inside its tile's regrouped order (2 bytes) and, per (tile,
+//           owner), where that run went.
+//   search  the owner walks all inbox segments, searches its shard and P2P-STORES each result (4-byte index local to
+//           the shard) into the origin's return buffer at the same segment position
+//   gather  the origin re-reads, tile by tile, the runs its tile sent (coalesced), rebases them by the owner's first
+//           record index in shared memory and writes out[] in query order (coalesced) -- no scattered global access.
+// Wire format of a key: the KW = ceil(2k/32) low 32-bit words of the 64*S-bit number, most significant first
+// (12 bytes instead of 16 at k = 47).
 constexpr int kRouteQ = 8;                   // queries per thread per tile of the route kernel
+constexpr int kRouteBlock = 256;
+constexpr uint32_t kRouteTile = kRouteBlock * kRouteQ;
+constexpr uint32_t kNotRouted = 0xffffu;
+constexpr uint32_t kWireMiss = 0xffffffffu;
 
 struct PeerPtrs {
     void *p[kMaxShards];
 };
 
-// Tile of BLOCK*kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory so that each
-// owner's run leaves as fully coalesced stores (whole 128-byte lines over NVLink instead of 16-byte fragments).
-template <int S, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
-                                                       const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
-                                                       PeerPtrs inbox, uint32_t *__restrict__ slots, unsigned long long *cursors,
-                                                       int64_t *__restrict__ out) {
-    extern __shared__ __align__(16) uint8_t route_smem[];
-    constexpr uint32_t tile_q = BLOCK * kRouteQ;
-    uint64_t *stage_keys = reinterpret_cast<uint64_t *>(route_smem);                       // [tile_q][S], grouped by owner
-    uint32_t *stage_slot = reinterpret_cast<uint32_t *>(route_smem + (size_t)tile_q * S * 8);   // [tile_q]
+template <int S, int KW>
+__device__ __forceinline__ void key_to_wire(const uint64_t (&q)[S], uint32_t *dst) {
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const int idx = KW - 1 - j;                       // 32-bit word index counted from the least significant end
+        const uint64_t w = q[S - 1 - idx / 2];
+        dst[j] = (idx & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+    }
+}
+template <int S, int KW>
+__device__ __forceinline__ void wire_to_key(const uint32_t *__restrict__ src, uint64_t (&q)[S]) {
+#pragma unroll
+    for (int w = 0; w < S; ++w) q[w] = 0;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const int idx = KW - 1 - j;
+        const uint64_t v = __ldg(src + j);
+        q[S - 1 - idx / 2] |= (idx & 1) ? (v << 32) : v;
+    }
+}
+
+// Route state local to the origin (cc_route_state_bytes): at16[cap_q] | tile_base[ntiles][nshards] | tile_cnt[ntiles][nshards]
+struct RouteState {
+    uint16_t *at16;
+    uint32_t *tile_base;
+    uint32_t *tile_cnt;
+};
+__host__ __device__ inline uint64_t route_tiles(uint64_t nq) { return (nq + kRouteTile - 1) / kRouteTile; }
+inline uint64_t route_state_bytes(uint64_t max_q, int nshards) {
+    const uint64_t at = (max_q * 2 + 15) & ~15ull;
+    return at + 2 * route_tiles(max_q) * (uint64_t)nshards * 4 + 16;
+}
+inline RouteState route_state_of(void *buf, uint64_t max_q, int nshards) {
+    RouteState r;
+    uint8_t *b = static_cast<uint8_t *>(buf);
+    r.at16 = reinterpret_cast<uint16_t *>(b);
+    b += (max_q * 2 + 15) & ~15ull;
+    r.tile_base = reinterpret_cast<uint32_t *>(b);
+    r.tile_cnt = r.tile_base + route_tiles(max_q) * (uint64_t)nshards;
+    return r;
+}
+
+// Tile of kRouteTile queries per block iteration.  The tile is regrouped by owner in shared memory so that each
+// owner's run leaves as fully coalesced stores (whole 128-byte lines over NVLink instead of per-query fragments).
+template <int S, int KW>
+__global__ void __launch_bounds__(kRouteBlock) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
+                                                            const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
+                                                            PeerPtrs inbox, RouteState rs, unsigned long long *cursors) {
+    extern __shared__ __align__(16) uint32_t stage[];     // [kRouteTile * KW] wire keys, grouped by owner
     __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1];
     __shared__ unsigned long long base[kMaxShards];
     __shared__ uint64_t spl[(kMaxShards - 1) * S];
-    for (int i = threadIdx.x; i < (nshards - 1) * S; i += BLOCK) spl[i] = splitters[i];
-    const uint64_t ntiles = (nq + tile_q - 1) / tile_q;
+    for (int i = threadIdx.x; i < (nshards - 1) * S; i += kRouteBlock) spl[i] = splitters[i];
+    const uint64_t ntiles = route_tiles(nq);
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int i = threadIdx.x; i < nshards; i += BLOCK) hist[i] = 0;
+        for (int i = threadIdx.x; i < nshards; i += kRouteBlock) hist[i] = 0;
         __syncthreads();
         uint64_t q[kRouteQ][S];
         uint32_t own[kRouteQ], rank_in[kRouteQ];
+        uint32_t fl[kRouteQ];
+        // all loads of the tile are issued before anything depends on them (one exposed round trip per tile)
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            const uint64_t i = tile * tile_q + (uint64_t)j * BLOCK + threadIdx.x;
-            own[j] = 0xffffffffu;
-            if (i < nq) {
-                if (flags && (flags[i] & 6u)) out[i] = -1;           // never routed: cannot match
-                else {
-                    load_key<S>(words, i, q[j]);
-                    own[j] = owner_of<S>(q[j], spl, nshards);
-                }
+            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            fl[j] = (i < nq) ? ((flags != nullptr) ? (uint32_t)__ldg(flags + i) : 0u) : 6u;
+        }
+#pragma unroll
+        for (int j = 0; j < kRouteQ; ++j) {
+            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            if (i < nq) load_key<S>(words, i, q[j]);
+            else {
+#pragma unroll
+                for (int w = 0; w < S; ++w) q[j][w] = 0;
             }
         }
+#pragma unroll
+        for (int j = 0; j < kRouteQ; ++j)                  // flagged queries are never routed: they cannot match
+            own[j] = (fl[j] & 6u) ? 0xffffffffu : owner_of<S>(q[j], spl, nshards);
         // warp-aggregated ranking: one shared-memory atomic per (warp, owner) instead of one per query -- with few
         // owners the per-query atomics all hit the same two or eight addresses and serialise
         const uint32_t lane = threadIdx.x & 31u, lane_lt = (1u << lane) - 1u;
@@ -492,8 +727,13 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
             rank_in[j] = b + __popc(peers & lane_lt);
         }
         __syncthreads();
-        if (threadIdx.x < (uint32_t)nshards)
-            base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)hist[threadIdx.x]) : 0ull;
+        if (threadIdx.x < (uint32_t)nshards) {
+            const uint32_t cnt = hist[threadIdx.x];
+            const unsigned long long b0 = cnt ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)cnt) : 0ull;
+            base[threadIdx.x] = b0;
+            rs.tile_base[tile * nshards + threadIdx.x] = (uint32_t)b0;
+            rs.tile_cnt[tile * nshards + threadIdx.x] = cnt;
+        }
         if (threadIdx.x == 0) {
             uint32_t acc = 0;
             for (int i = 0; i < nshards; ++i) { loc[i] = acc; acc += hist[i]; }
@@ -502,23 +742,33 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            if (own[j] == 0xffffffffu) continue;
-            const uint32_t at = loc[own[j]] + rank_in[j];
-#pragma unroll
-            for (int w = 0; w < S; ++w) stage_keys[(size_t)at * S + w] = q[j][w];
-            stage_slot[at] = (uint32_t)(tile * tile_q + (uint64_t)j * BLOCK + threadIdx.x);
+            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            if (i >= nq) continue;
+            uint32_t at = kNotRouted;
+            if (own[j] != 0xffffffffu) {
+                at = loc[own[j]] + rank_in[j];
+                key_to_wire<S, KW>(q[j], stage + (size_t)at * KW);
+            }
+            rs.at16[i] = (uint16_t)at;
         }
         __syncthreads();
-        for (int o = 0; o < nshards; ++o) {
-            const uint32_t cnt = hist[o];
-            if (cnt == 0) continue;
-            const uint64_t b0 = base[o];
-            const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)cnt, (unsigned long long)(cap - b0));
-            uint64_t *dst = static_cast<uint64_t *>(inbox.p[o]) + ((uint64_t)my_rank * cap + b0) * S;
-            const uint64_t *src = stage_keys + (size_t)loc[o] * S;
-            for (uint32_t t = threadIdx.x; t < keep * S; t += BLOCK) dst[t] = src[t];
-            uint32_t *sdst = slots + (uint64_t)o * cap + b0;
-            for (uint32_t t = threadIdx.x; t < keep; t += BLOCK) sdst[t] = stage_slot[loc[o] + t];
+        // copy-out: every warp takes whole pieces (an owner's run, split in `nsub` parts when there are fewer owners
+        // than warps), so the stores of a warp are one contiguous stream and nothing is recomputed per word
+        {
+            const uint32_t warp = threadIdx.x >> 5;
+            const uint32_t nsub = max(1u, (uint32_t)(kRouteBlock / 32) / (uint32_t)nshards);
+            for (uint32_t piece = warp; piece < (uint32_t)nshards * nsub; piece += kRouteBlock / 32) {
+                const uint32_t o = piece / nsub, part = piece - o * nsub;
+                const uint32_t cnt = hist[o];
+                const uint64_t b0 = base[o];
+                // a segment holds `cap` keys; keys beyond it are dropped here and reported through sent[o] > cap
+                const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)cnt, (unsigned long long)(cap - b0));
+                const uint32_t nwords = keep * KW, per = ((nwords + nsub - 1) / nsub + 31u) & ~31u;
+                const uint32_t w0 = part * per, w1 = min(nwords, w0 + per);
+                uint32_t *dst = static_cast<uint32_t *>(inbox.p[o]) + ((uint64_t)my_rank * cap + b0) * KW;
+                const uint32_t *src = stage + (size_t)loc[o] * KW;
+                for (uint32_t t = w0 + lane; t < w1; t += 32) dst[t] = src[t];
+            }
         }
         __syncthreads();
     }
@@ -528,20 +778,17 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
 // counts_in[my_rank] on every owner := number of keys this rank routed to it (P2P stores of 8 bytes)
 __global__ void publish_counts_kernel(const unsigned long long *cursors, int nshards, int my_rank, uint64_t cap, PeerPtrs counts_in) {
     const int o = threadIdx.x;
-    if (o < nshards) {
-        const unsigned long long c = cursors[o] < cap ? cursors[o] : cap;
-        static_cast<unsigned long long *>(counts_in.p[o])[my_rank] = c;
-    }
+    if (o < nshards) static_cast<unsigned long long *>(counts_in.p[o])[my_rank] = cursors[o] < cap ? cursors[o] : cap;
     __threadfence_system();
 }
 
-template <int S, int Q>
-__global__ void __launch_bounds__(kBlock) find_routed_kernel(const uint64_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
+template <int S, int KW, int Q>
+__global__ void __launch_bounds__(kBlock, S <= 2 ? 3 : 1) find_routed_kernel(const uint32_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
                                                              int nshards, int my_rank, uint64_t cap, IndexView ix, PeerPtrs ret) {
     __shared__ unsigned long long pre[kMaxShards + 1];
     if (threadIdx.x == 0) {
         unsigned long long acc = 0;
-        for (int i = 0; i < nshards; ++i) { pre[i] = acc; acc += counts_in[i]; }
+        for (int i = 0; i < nshards; ++i) { pre[i] = acc; acc += counts_in[i] < cap ? counts_in[i] : cap; }
         pre[nshards] = acc;
     }
     __syncthreads();
@@ -563,24 +810,54 @@ __global__ void __launch_bounds__(kBlock) find_routed_kernel(const uint64_t *__r
                 while (sgm + 1 < (uint32_t)nshards && f >= pre[sgm + 1]) ++sgm;
                 src[j] = sgm;
                 pos[j] = f - pre[sgm];
-                load_key<S>(inbox, (uint64_t)sgm * cap + pos[j], q[j]);
+                wire_to_key<S, KW>(inbox + ((uint64_t)sgm * cap + pos[j]) * KW, q[j]);
             }
         }
-        lookup_mlp<S, Q>(ix, q, live, r);
+        lookup_mlp<S, Q>(ix, q, live, r);          // ix.first_index is 0 here: results are local to the shard
 #pragma unroll
         for (int j = 0; j < Q; ++j)
-            if (live[j]) static_cast<int64_t *>(ret.p[src[j]])[(uint64_t)my_rank * cap + pos[j]] = r[j];
+            if (live[j]) static_cast<uint32_t *>(ret.p[src[j]])[(uint64_t)my_rank * cap + pos[j]] = r[j] < 0 ? kWireMiss : (uint32_t)r[j];
     }
     __threadfence_system();
 }
 
-__global__ void gather_routed_kernel(const int64_t *__restrict__ ret, const uint32_t *__restrict__ slots,
-                                     const unsigned long long *__restrict__ sent, int nshards, uint64_t cap,
-                                     int64_t *__restrict__ out) {
-    for (int o = 0; o < nshards; ++o) {
-        const uint64_t n = sent[o] < cap ? sent[o] : cap;
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-            out[slots[(uint64_t)o * cap + i]] = ret[(uint64_t)o * cap + i];
+__global__ void __launch_bounds__(kRouteBlock) gather_routed_kernel(const uint32_t *__restrict__ ret, RouteState rs, uint64_t nq,
+                                                                    const uint64_t *__restrict__ shard_first, int nshards, uint64_t cap,
+                                                                    int64_t *__restrict__ out) {
+    __shared__ int64_t staged[kRouteTile];
+    __shared__ uint32_t loc[kMaxShards + 1], base[kMaxShards];
+    __shared__ uint64_t first[kMaxShards];
+    for (int i = threadIdx.x; i < nshards; i += kRouteBlock) first[i] = shard_first[i];
+    const uint64_t ntiles = route_tiles(nq);
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();                                  // previous tile's staged[] fully consumed
+        if (threadIdx.x < (uint32_t)nshards) base[threadIdx.x] = rs.tile_base[tile * nshards + threadIdx.x];
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int i = 0; i < nshards; ++i) { loc[i] = acc; acc += rs.tile_cnt[tile * nshards + i]; }
+            loc[nshards] = acc;
+        }
+        __syncthreads();
+        const uint32_t total = loc[nshards];
+        for (uint32_t p = threadIdx.x; p < total; p += kRouteBlock) {
+            uint32_t lo = 0, hi = (uint32_t)nshards - 1;  // owner o with loc[o] <= p < loc[o+1]
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (loc[mid] <= p) lo = mid; else hi = mid - 1;
+            }
+            const uint64_t at = (uint64_t)base[lo] + (p - loc[lo]);
+            const uint32_t r = at < cap ? __ldg(ret + (uint64_t)lo * cap + at) : kWireMiss;   // dropped by an overflowing segment
+            staged[p] = r == kWireMiss ? -1 : (int64_t)(first[lo] + r);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kRouteQ; ++j) {
+            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            if (i < nq) {
+                const uint32_t at = rs.at16[i];
+                out[i] = at == kNotRouted ? -1 : staged[at];
+            }
+        }
     }
 }
 
@@ -595,14 +872,14 @@ __global__ void check_sorted_kernel(const uint64_t *__restrict__ keys, uint64_t 
     }
 }
 
-// table[b] = number of keys whose prefix is < b  (b in [0, 2^bits]).
+// table[b] = number of keys whose bucket is < b  (b in [0, nbuckets + 1]).
 template <int S>
-__global__ void build_table_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t bits, uint32_t shift, uint32_t *table) {
-    const uint64_t nb = 1ull << bits;
+__global__ void build_table_kernel(IndexView ix, uint32_t *table) {
+    const uint64_t n = ix.n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
-        int64_t prev = -1, cur = (int64_t)nb;
-        if (i > 0) { uint64_t a[S]; load_key<S>(keys, i - 1, a); prev = (int64_t)key_prefix<S>(a, shift); }
-        if (i < n) { uint64_t b[S]; load_key<S>(keys, i, b); cur = (int64_t)key_prefix<S>(b, shift); }
+        int64_t prev = -1, cur = (int64_t)ix.nbuckets + 1;
+        if (i > 0) { uint64_t a[S]; load_key<S>(ix.keys, i - 1, a); prev = (int64_t)key_bucket<S>(ix, a); }
+        if (i < n) { uint64_t b[S]; load_key<S>(ix.keys, i, b); cur = (int64_t)key_bucket<S>(ix, b); }
         for (int64_t b = prev + 1; b <= cur; ++b) table[b] = (uint32_t)i;
     }
 }
@@ -706,6 +983,16 @@ int grid_for(uint64_t work_items, int per_block, int sm_count, int blocks_per_sm
     return (int)std::max<uint64_t>(1, std::min(blocks, cap));
 }
 
+// Grid of a persistent (grid-stride) kernel: exactly the CTAs that are resident at once, so that no second, partial wave
+// trails behind (the occupancy comes from the runtime, not from a guess about registers).
+template <typename Kernel>
+int resident_grid(Kernel kernel, int block, size_t smem, uint64_t work_blocks, int sm_count, int max_per_sm = 32) {
+    int per = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, block, smem) != cudaSuccess || per < 1) per = 1;
+    per = std::min(per, max_per_sm);
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(work_blocks, (uint64_t)sm_count * per));
+}
+
 int sm_count_now() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -718,8 +1005,10 @@ IndexView view_of(const cc_graph *g) {
     v.table = g->index.table;
     v.n = g->h.num_records;
     v.first_index = g->first_index;
-    v.bits = (uint32_t)g->index.bits;
-    v.shift = 2u * g->h.k - (uint32_t)g->index.bits;
+    v.base = g->index.base;
+    v.nbuckets = g->index.nbuckets;
+    v.shift = g->index.shift;
+    v.k = g->h.k;
     return v;
 }
 
@@ -755,21 +1044,26 @@ int launch_pack_windows(const uint8_t *dev_seq, uint64_t /*len*/, uint32_t k, ui
     if (nq == 0) return CC_OK;
     const uint32_t s = (k + 31) / 32;
     if (row_stride == k && row_stride > 1) {       // independent rows
-        const size_t smem = (size_t)(kBlock / 32) * ((32u * k + 32u + 15u) & ~15u);
-        const int per_sm = std::max(1, std::min(8, (int)((200u << 10) / (smem + 1024))));
-        const int grid = grid_for((nq + 31) / 32, kBlock / 32, sm_count_now(), per_sm);
-        CC_DISPATCH_S(s, {
-            CC_CUDA(cudaFuncSetAttribute(pack_rows_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pack_rows_kernel<S_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags);
-        });
+        IndexView none{};
+        // tile = RPT * 256 rows, sized to about 16 KB of sequence (two tiles in flight per CTA, several CTAs per SM)
+#define CC_ROWS_PACK(RPT_) CC_DISPATCH_S(s, {                                                                                  \
+            const size_t smem = rows_smem_bytes(RPT_ * kBlock, k, false);                                                          \
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, false, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+            const int grid = resident_grid(rows_kernel<S_, false, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), sm_count_now()); \
+            rows_kernel<S_, false, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags, none, nullptr); })
+        if (k <= (uint32_t)options().rows_rpt2_max_k) { CC_ROWS_PACK(2); } else { CC_ROWS_PACK(1); }
+#undef CC_ROWS_PACK
         count_launch();
         CC_CUDA(cudaGetLastError());
         return CC_OK;
     }
     SeqJob job = make_job(dev_seq, nq, row_stride, k);
-    const int grid = grid_for((nq + job.per_tile - 1) / job.per_tile, 1, sm_count_now(), 6);
+    const uint64_t ntiles = (nq + job.per_tile - 1) / job.per_tile;
     IndexView none{};
-    CC_DISPATCH_S(s, seq_kernel<S_, false, false><<<grid, kBlock, 0, st>>>(job, dev_words, dev_flags, none, nullptr));
+    CC_DISPATCH_S(s, {
+        const int grid = resident_grid(seq_kernel<S_, false, false>, kBlock, 0, ntiles, sm_count_now());
+        seq_kernel<S_, false, false><<<grid, kBlock, 0, st>>>(job, dev_words, dev_flags, none, nullptr);
+    });
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;
@@ -789,9 +1083,22 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
         cudaFreeAsync(words, st); cudaFreeAsync(flags, st);
         return rc;
     }
-    if (row_stride > 1 && nq >= (1u << 16)) {
-        // Independent rows cost k bytes of staging per query, which leaves the fused kernel at half occupancy for the
-        // latency-bound search; for large batches pack first (streaming), then search at full occupancy.
+    if (row_stride == g->h.k && row_stride > 1) {
+        if (algo == CC_ALGO_AUTO && options().rows_fused) {
+            // independent rows: pack and search in one kernel (the stream of 2-bit codes is all that is staged)
+            IndexView ix = view_of(g);
+            const uint32_t k = g->h.k;
+#define CC_ROWS_FIND(RPT_) CC_DISPATCH_S(g->h.s, {                                                                             \
+                const size_t smem = rows_smem_bytes(RPT_ * kBlock, k, true);                                                       \
+                CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, true, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                const int grid = resident_grid(rows_kernel<S_, true, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), g->sm_count); \
+                rows_kernel<S_, true, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, nullptr, nullptr, ix, dev_index); })
+            if (k <= 64) { CC_ROWS_FIND(2); } else { CC_ROWS_FIND(1); }     // two lookups in flight per thread when the tile fits
+#undef CC_ROWS_FIND
+            count_launch();
+            CC_CUDA(cudaGetLastError());
+            return CC_OK;
+        }
         uint64_t *words = nullptr; uint8_t *flags = nullptr;
         CC_CUDA(cudaMallocAsync(&words, nq * g->h.s * sizeof(uint64_t), st));
         CC_CUDA(cudaMallocAsync(&flags, nq, st));
@@ -801,12 +1108,18 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
         return rc;
     }
     SeqJob job = make_job(dev_seq, nq, row_stride, g->h.k);
-    const int grid = grid_for((nq + job.per_tile - 1) / job.per_tile, 1, g->sm_count, 6);
+    const uint64_t ntiles = (nq + job.per_tile - 1) / job.per_tile;
     IndexView ix = view_of(g);
     if (algo == CC_ALGO_BSEARCH) {
-        CC_DISPATCH_S(g->h.s, seq_kernel<S_, true, false><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index));
+        CC_DISPATCH_S(g->h.s, {
+            const int grid = resident_grid(seq_kernel<S_, true, false>, kBlock, 0, ntiles, g->sm_count);
+            seq_kernel<S_, true, false><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index);
+        });
     } else {
-        CC_DISPATCH_S(g->h.s, seq_kernel<S_, true, true><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index));
+        CC_DISPATCH_S(g->h.s, {
+            const int grid = resident_grid(seq_kernel<S_, true, true>, kBlock, 0, ntiles, g->sm_count);
+            seq_kernel<S_, true, true><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index);
+        });
     }
     count_launch();
     CC_CUDA(cudaGetLastError());
@@ -860,10 +1173,15 @@ int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *de
         count_launch();
     } else {
         const int qpt = options().lookup_queries_per_thread;
-        const int g2 = grid_for((nq + std::max(qpt, 1) - 1) / std::max(qpt, 1), kBlock, g->sm_count, 8);
-        if (qpt >= 4) { CC_DISPATCH_S(s, find_packed_mlp_kernel<S_, 4><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
-        else if (qpt >= 2) { CC_DISPATCH_S(s, find_packed_mlp_kernel<S_, 2><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
-        else if (qpt == 1) { CC_DISPATCH_S(s, find_packed_mlp_kernel<S_, 1><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
+        const uint64_t nblk = ((nq + std::max(qpt, 1) - 1) / std::max(qpt, 1) + kBlock - 1) / kBlock;
+#define CC_MLP(Q_) CC_DISPATCH_S(s, {                                                                                   \
+            const int g2 = options().mlp_grid_per_sm > 0 ? (int)std::min<uint64_t>(nblk, (uint64_t)g->sm_count * options().mlp_grid_per_sm) \
+                                                         : resident_grid(find_packed_mlp_kernel<S_, Q_>, kBlock, 0, nblk, g->sm_count);  \
+            find_packed_mlp_kernel<S_, Q_><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index); })
+        if (qpt >= 4) { CC_MLP(4); }
+        else if (qpt >= 2) { CC_MLP(2); }
+        else if (qpt == 1) { CC_MLP(1); }
+#undef CC_MLP
         else { CC_DISPATCH_S(s, find_packed_kernel<S_, true><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
         count_launch();
     }
@@ -895,17 +1213,33 @@ int build_index(cc_graph *g, int bits_req) {
 
     if (int rc = g->scan_ws.ensure(0, 0)) return rc;
     CC_CUDA(cudaMalloc(&ix.keys, std::max<uint64_t>(n * s, 2) * sizeof(uint64_t) + 64));
-    CC_CUDA(cudaMalloc(&ix.table, ((1ull << bits) + 1) * sizeof(uint32_t)));
     if (int rc = launch_decode_columns(g->dev_body, n, s, g->h.c, ix.keys, nullptr, nullptr, g->scan_ws, g->sm_count, st)) return rc;
+
+    // The table spans [first key, last key] of this array, not the whole 2k-bit key space (see key_bucket).
+    uint64_t first[4] = {0, 0, 0, 0}, last[4] = {0, 0, 0, 0};
+    if (n) {
+        CC_CUDA(cudaMemcpyAsync(first, ix.keys, s * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaMemcpyAsync(last, ix.keys + (n - 1) * s, s * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaStreamSynchronize(st));
+    }
+    uint64_t t0 = 0, t1 = 0;
+    CC_DISPATCH_S(s, { t0 = key_top64<S_>(first, k); t1 = key_top64<S_>(last, k); });
+    const uint64_t span = t1 >= t0 ? t1 - t0 : 0;      // unsorted arrays are rejected below; buckets are clamped anyway
+    uint32_t shift = 0;
+    while (shift < 63 && (span >> shift) >= (1ull << bits)) ++shift;
+    ix.base = t0;
+    ix.shift = shift;
+    ix.nbuckets = (uint32_t)(span >> shift) + 1u;
+    CC_CUDA(cudaMalloc(&ix.table, ((uint64_t)ix.nbuckets + 2) * sizeof(uint32_t)));
 
     unsigned long long *d_unsorted = reinterpret_cast<unsigned long long *>(g->scan_ws.totals + 8);
     const unsigned long long none = ~0ull;
     CC_CUDA(cudaMemcpyAsync(d_unsorted, &none, 8, cudaMemcpyHostToDevice, st));
     const int grid = grid_for(n + 1, 256, g->sm_count, 8);
-    const uint32_t shift = 2u * k - (uint32_t)bits;
     CC_DISPATCH_S(s, check_sorted_kernel<S_><<<grid, 256, 0, st>>>(ix.keys, n, d_unsorted));
     count_launch();
-    CC_DISPATCH_S(s, build_table_kernel<S_><<<grid, 256, 0, st>>>(ix.keys, n, (uint32_t)bits, shift, ix.table));
+    const IndexView view = view_of(g);
+    CC_DISPATCH_S(s, build_table_kernel<S_><<<grid, 256, 0, st>>>(view, ix.table));
     count_launch();
     CC_CUDA(cudaGetLastError());
     unsigned long long at = none;
@@ -949,38 +1283,37 @@ int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots,
 }
 
 // ------------------------------------------------------------------ routed lookups (peer memory) launchers
-int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s, const uint64_t *dev_splitters, int nshards,
-                 int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, uint32_t *dev_slots, uint64_t *dev_sent,
-                 int64_t *dev_out, cudaStream_t st) {
+#define CC_DISPATCH_SKW(s, kw, ...)                                                        \
+    switch ((s) * 2 - (kw)) {                                                              \
+        case 0: CC_DISPATCH_S(s, { constexpr int KW_ = 2 * S_; __VA_ARGS__; }) break;      \
+        case 1: CC_DISPATCH_S(s, { constexpr int KW_ = 2 * S_ - 1; __VA_ARGS__; }) break;  \
+        default: return fail(CC_ERR_ARG, "inconsistent k-mer size for the wire format");   \
+    }
+
+uint64_t route_state_size(uint64_t max_q, int nshards) { return route_state_bytes(max_q, nshards); }
+
+int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k, const uint64_t *dev_splitters, int nshards,
+                 int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, void *dev_route_state, uint64_t max_q,
+                 uint64_t *dev_sent, cudaStream_t st) {
+    if (int rc = check_k(k)) return rc;
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
     if (my_rank < 0 || my_rank >= nshards) return fail(CC_ERR_ARG, "rank %d out of range", my_rank);
-    if (nq >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "routed batches are limited to 2^32-1 queries per rank");
+    if (nq >= (1ull << 32) || cap >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "routed batches are limited to 2^32-1 queries per rank");
+    const uint32_t s = (k + 31) / 32, kw = (2 * k + 31) / 32;
     PeerPtrs inbox{}, counts{};
     for (int i = 0; i < nshards; ++i) { inbox.p[i] = peer_inbox[i]; counts.p[i] = peer_counts[i]; }
     unsigned long long *cursors = reinterpret_cast<unsigned long long *>(dev_sent);
     CC_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * nshards, st));
     if (nq) {
-        // small blocks (128 threads) when the leg is to be overlapped with the search on another stream: one of them
-        // fits next to three resident search blocks
-        const bool small = options().route_blocks_per_sm > 0;
-        const int block = small ? 128 : kBlock;
-        const size_t smem = (size_t)block * kRouteQ * (8 * s + 4);
-        int per_sm = std::max(1, std::min(4, (int)((200u << 10) / (smem + 4096))));
-        if (small) per_sm = std::min(per_sm, options().route_blocks_per_sm);
-        const int grid = grid_for((nq + (uint64_t)block * kRouteQ - 1) / ((uint64_t)block * kRouteQ), 1, sm_count_now(), per_sm);
-        if (small) {
-            CC_DISPATCH_S(s, {
-                CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                route_kernel<S_, 128><<<grid, 128, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox,
-                                                                dev_slots, cursors, dev_out);
-            });
-        } else {
-            CC_DISPATCH_S(s, {
-                CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                route_kernel<S_, kBlock><<<grid, kBlock, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox,
-                                                                      dev_slots, cursors, dev_out);
-            });
-        }
+        if (nq > max_q) return fail(CC_ERR_ARG, "batch of %llu queries exceeds the route state sized for %llu", (unsigned long long)nq, (unsigned long long)max_q);
+        const RouteState rs = route_state_of(dev_route_state, max_q, nshards);
+        const size_t smem = (size_t)kRouteTile * kw * 4;
+        const int per_sm = options().route_blocks_per_sm > 0 ? options().route_blocks_per_sm : 32;
+        CC_DISPATCH_SKW(s, kw, {
+            CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = resident_grid(route_kernel<S_, KW_>, kRouteBlock, smem, route_tiles(nq), sm_count_now(), per_sm);
+            route_kernel<S_, KW_><<<grid, kRouteBlock, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox, rs, cursors);
+        });
         count_launch();
     }
     publish_counts_kernel<<<1, kMaxShards, 0, st>>>(cursors, nshards, my_rank, cap, counts);
@@ -989,27 +1322,32 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     return CC_OK;
 }
 
-int launch_find_routed(cc_graph *g, const uint64_t *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
                        void *const *peer_ret, cudaStream_t st) {
     if (int rc = check_k(g->h.k)) return rc;
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
     PeerPtrs ret{};
     for (int i = 0; i < nshards; ++i) ret.p[i] = peer_ret[i];
     IndexView ix = view_of(g);
-    const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
-    CC_DISPATCH_S(g->h.s, find_routed_kernel<S_, 2><<<grid, kBlock, 0, st>>>(dev_inbox, reinterpret_cast<const unsigned long long *>(dev_counts_in),
-                                                                             nshards, my_rank, cap, ix, ret));
+    ix.first_index = 0;                 // the wire carries indices local to the shard; the origin rebases them
+    const uint32_t kw = (2 * g->h.k + 31) / 32;
+    CC_DISPATCH_SKW(g->h.s, kw, {
+        const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
+        find_routed_kernel<S_, KW_, 2><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t *>(dev_inbox),
+                                                                 reinterpret_cast<const unsigned long long *>(dev_counts_in), nshards, my_rank, cap, ix, ret);
+    });
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;
 }
 
-int launch_gather_routed(const int64_t *dev_ret, const uint32_t *dev_slots, const uint64_t *dev_sent, int nshards, uint64_t cap,
-                         int64_t *dev_out, cudaStream_t st) {
+int launch_gather_routed(const void *dev_ret, const void *dev_route_state, uint64_t max_q, uint64_t nq, const uint64_t *dev_shard_first,
+                         int nshards, uint64_t cap, int64_t *dev_out, cudaStream_t st) {
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
-    const bool small = options().gather_blocks_per_sm > 0 && options().gather_blocks_per_sm < 8;
-    gather_routed_kernel<<<sm_count_now() * std::max(1, options().gather_blocks_per_sm), small ? 128 : kBlock, 0, st>>>(dev_ret, dev_slots, reinterpret_cast<const unsigned long long *>(dev_sent),
-                                                                nshards, cap, dev_out);
+    if (nq == 0) return CC_OK;
+    const RouteState rs = route_state_of(const_cast<void *>(dev_route_state), max_q, nshards);
+    const int grid = resident_grid(gather_routed_kernel, kRouteBlock, 0, route_tiles(nq), sm_count_now(), std::max(1, options().gather_blocks_per_sm));
+    gather_routed_kernel<<<grid, kRouteBlock, 0, st>>>(static_cast<const uint32_t *>(dev_ret), rs, nq, dev_shard_first, nshards, cap, dev_out);
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;

@@ -112,30 +112,49 @@ class RoutedLookup:
     """The same sharded lookup with NO collective library on the data path: every leg is one kernel fused with its
     transfer over peer-mapped memory (NVLink P2P stores):
 
-        cc_route_queries_dev  owner search + block-aggregated reservation + store of each key straight into the owner's
-                              inbox segment for this rank (slots stay local)
+        cc_route_queries_dev  owner search + block-aggregated reservation + store of each key (compact wire format:
+                              ceil(2k/32) 32-bit words) straight into the owner's inbox segment for this rank; only the
+                              tile bookkeeping stays local (2 bytes per query + one run descriptor per tile and owner)
         barrier               (symmetric-memory signal pads; orders the peer stores)
-        cc_find_routed_dev    the owner searches every inbox segment and stores each result straight into the origin's
-                              return buffer, same segment position
+        cc_find_routed_dev    the owner searches every inbox segment and stores each result (4-byte shard-local index)
+                              straight into the origin's return buffer, same segment position
         barrier
-        cc_gather_routed_dev  the origin scatters the returned indices to the original slots
+        cc_gather_routed_dev  the origin re-reads its tiles' runs, rebases by the owner's first record index and writes
+                              out[] in query order -- all coalesced
 
     The host never reads a count, so the whole batch is asynchronous on the current stream.  Buffers are one symmetric
     allocation per rank (torch.distributed._symmetric_memory: plumbing only).  `cap` is the capacity of one
     (source, owner) segment; a rank can route at most `cap` queries to one owner per batch (worst case = its batch size).
     """
 
-    def __init__(self, graph, splitters, rank: int, world: int, device, cap: int, s: int, group=None, emulate=None):
+    def __init__(self, graph, splitters, rank: int, world: int, device, cap: int, k: int, shard_first=None, group=None, emulate=None,
+                 max_batch: int | None = None):
+        """cap: keys one (source, owner) segment can hold.  max_batch: largest batch of this rank (default cap).  With
+        max_batch <= cap (the default) a segment cannot overflow; with max_batch > cap (balanced key ranges, memory-saving)
+        find_packed() checks the sent counts after the batch and raises if a segment overflowed."""
         import ctypes as C
-        self.g, self.rank, self.world, self.cap, self.s = graph, rank, world, int(cap), int(s)
+        self.g, self.rank, self.world, self.cap, self.k = graph, rank, world, int(cap), int(k)
+        self.max_batch = int(max_batch) if max_batch is not None else int(cap)
+        self.kw = (2 * self.k + 31) // 32
         self.device = device
         self.index = device.index if device.index is not None else torch.cuda.current_device()
         self.splitters = splitters.contiguous() if splitters is not None else None
-        # layout of the symmetric block, in int64 elements
+        if shard_first is None:                 # first global record index of every shard
+            mine = torch.tensor([int(graph.firstIndex)], dtype=torch.int64, device=device)
+            if world > 1:
+                parts = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine, group=group)
+                shard_first = torch.cat(parts)
+            else:
+                shard_first = mine
+        self.shard_first = torch.as_tensor(shard_first, dtype=torch.int64).to(device).contiguous()
+        assert self.shard_first.numel() == world
+        # layout of the symmetric block, in bytes (every part 16-byte aligned)
+        al = lambda x: (x + 15) & ~15
         self.off_inbox = 0
-        self.off_ret = world * self.cap * self.s
-        self.off_counts = self.off_ret + world * self.cap
-        total = self.off_counts + max(world, 8)
+        self.off_ret = al(world * self.cap * self.kw * 4)
+        self.off_counts = self.off_ret + al(world * self.cap * 4)
+        total = self.block_elems(world, self.cap, self.k)
         if emulate is None:
             import torch.distributed._symmetric_memory as symm
             self.block = symm.empty(total, dtype=torch.int64, device=device)
@@ -147,39 +166,46 @@ class RoutedLookup:
             bases = [int(t.data_ptr()) for t in emulate]
         self.block.zero_()
         arr = C.c_void_p * world
-        self.p_inbox = arr(*[b + 8 * self.off_inbox for b in bases])
-        self.p_ret = arr(*[b + 8 * self.off_ret for b in bases])
-        self.p_counts = arr(*[b + 8 * self.off_counts for b in bases])
-        self.slots = torch.empty(world * self.cap, dtype=torch.int32, device=device)
+        self.p_inbox = arr(*[b + self.off_inbox for b in bases])
+        self.p_ret = arr(*[b + self.off_ret for b in bases])
+        self.p_counts = arr(*[b + self.off_counts for b in bases])
+        nbytes = C.c_uint64(0)
+        N.check(N.lib().cc_route_state_bytes(self.max_batch, world, C.byref(nbytes)))
+        self.state = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
         self.sent = torch.zeros(max(world, 8), dtype=torch.int64, device=device)
+        self.nq = 0
 
     @staticmethod
-    def block_elems(world: int, cap: int, s: int) -> int:
-        return world * cap * s + world * cap + max(world, 8)
+    def block_elems(world: int, cap: int, k: int) -> int:
+        """int64 elements of one rank's symmetric block."""
+        kw = (2 * k + 31) // 32
+        al = lambda x: (x + 15) & ~15
+        return (al(world * cap * kw * 4) + al(world * cap * 4) + 8 * max(world, 8)) // 8
 
     def _barrier(self):
         if self.hdl is not None:
             self.hdl.barrier()
 
-    def route(self, words, flags, out):
-        if words.shape[0] > self.cap:
-            raise ValueError("batch of %d queries exceeds the segment capacity %d" % (words.shape[0], self.cap))
+    def route(self, words, flags):
+        if words.shape[0] > self.max_batch:
+            raise ValueError("batch of %d queries exceeds the largest batch %d this lookup was sized for" % (words.shape[0], self.max_batch))
         st = torch.cuda.current_stream().cuda_stream
+        self.nq = words.shape[0]
         N.check(N.lib().cc_route_queries_dev(self.index, words.data_ptr(), flags.data_ptr() if flags is not None else None,
-                                             words.shape[0], self.s, self.splitters.data_ptr() if self.splitters is not None else None,
+                                             self.nq, self.k, self.splitters.data_ptr() if self.splitters is not None else None,
                                              self.world, self.rank, self.cap, self.p_inbox, self.p_counts,
-                                             self.slots.data_ptr(), self.sent.data_ptr(), out.data_ptr(), st))
+                                             self.state.data_ptr(), self.max_batch, self.sent.data_ptr(), st))
 
     def search(self):
         st = torch.cuda.current_stream().cuda_stream
         base = self.block.data_ptr()
-        N.check(N.lib().cc_find_routed_dev(self.g._h, base + 8 * self.off_inbox, base + 8 * self.off_counts, self.world, self.rank,
+        N.check(N.lib().cc_find_routed_dev(self.g._h, base + self.off_inbox, base + self.off_counts, self.world, self.rank,
                                            self.cap, self.p_ret, st))
 
     def gather(self, out):
         st = torch.cuda.current_stream().cuda_stream
-        N.check(N.lib().cc_gather_routed_dev(self.index, self.block.data_ptr() + 8 * self.off_ret, self.slots.data_ptr(),
-                                             self.sent.data_ptr(), self.world, self.cap, out.data_ptr(), st))
+        N.check(N.lib().cc_gather_routed_dev(self.index, self.block.data_ptr() + self.off_ret, self.state.data_ptr(), self.max_batch, self.nq,
+                                             self.shard_first.data_ptr(), self.world, self.cap, out.data_ptr(), st))
 
     def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor, profile: bool = False) -> torch.Tensor:
         marks = []
@@ -191,7 +217,7 @@ class RoutedLookup:
                 marks.append((name, ev))
 
         mark("start")
-        self.route(words, flags, out)
+        self.route(words, flags)
         mark("route")
         self._barrier()
         mark("barrier1")
@@ -204,7 +230,15 @@ class RoutedLookup:
         if marks:
             torch.cuda.synchronize()
             self.phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
+        if self.max_batch > self.cap:
+            self.check_overflow()
         return out
+
+    def check_overflow(self):
+        """Only needed when max_batch > cap: a segment that received more than cap keys dropped the rest."""
+        worst = int(self.sent[:self.world].max().item())
+        if worst > self.cap:
+            raise OverflowError("a routed segment overflowed: %d keys for one owner, capacity %d" % (worst, self.cap))
 
 
 class PipelinedRoutedLookup:
@@ -217,9 +251,9 @@ class PipelinedRoutedLookup:
     stream, so they fit beside the three resident blocks of the (latency-bound, full-occupancy) search kernel.
     """
 
-    def __init__(self, graph, splitters, rank: int, world: int, device, sub_batch: int, s: int, group=None):
+    def __init__(self, graph, splitters, rank: int, world: int, device, sub_batch: int, k: int, shard_first=None, group=None):
         self.sub = int(sub_batch)
-        self.sets = [RoutedLookup(graph, splitters, rank, world, device, self.sub, s, group=group) for _ in range(2)]
+        self.sets = [RoutedLookup(graph, splitters, rank, world, device, self.sub, k, shard_first=shard_first, group=group) for _ in range(2)]
         self.sx = torch.cuda.Stream(device=device, priority=-1)     # NVLink legs first: they are short and hide behind the search
         self.sy = torch.cuda.Stream(device=device)
         self.world = world
@@ -249,7 +283,7 @@ class PipelinedRoutedLookup:
         def route(i):
             w, f, o = part(i)
             with torch.cuda.stream(self.sx):
-                self.sets[i & 1].route(w, f, o)
+                self.sets[i & 1].route(w, f)
                 self.sets[i & 1]._barrier()
                 routed[i].record(self.sx)
 

@@ -421,35 +421,37 @@ def test_findrois_command_and_call_helpers(tmp_path):
     graph.dispose(); rois.dispose()
 
 
-@pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_routed_lookup_emulated_ranks(world):
+@pytest.mark.parametrize("world,k", [(1, 47), (2, 47), (4, 47), (8, 47), (3, 16), (3, 31), (2, 63), (3, 65), (5, 96)])
+def test_routed_lookup_emulated_ranks(world, k):
     """The peer-memory lookup path (route -> search -> gather) with all ranks emulated on one device: plain device
     tensors stand in for the symmetric allocations (every 'peer pointer' is a local pointer) and the legs of all ranks
     run one after another on one stream, which is exactly the ordering the cross-rank barriers enforce."""
     from corticall_b200.host.sharded import RoutedLookup
-    k, c, n = 47, 4, 60000
+    c, n = 4, 60000
+    nw = (k + 31) // 32
     ctx = synth.make_ctx_file(31, n, k, c, adv_period=0)
     og = orc.Graph(ctx)
     whole = cb.CortexGraph(ctx)
     words_all, _, _ = whole.decodeRecords(0, n)
     body = torch.from_numpy(whole.getRawRecords(0, n)).cuda()
-    table = [torch.from_numpy(words_all[:, w].copy().view(np.int64)) for w in range(2)]
+    table = [torch.from_numpy(words_all[:, w].copy().view(np.int64)) for w in range(nw)]
     dev = torch.device("cuda", 0)
     spl = torch.stack([torch.stack([t[n * r // world] for t in table]) for r in range(1, world)]).cuda() if world > 1 else None
     nq_per = [5000 + 700 * r for r in range(world)]
     cap = max(nq_per)
-    blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, 2), dtype=torch.int64, device=dev) for _ in range(world)]
+    blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, k), dtype=torch.int64, device=dev) for _ in range(world)]
+    first = [n * r // world for r in range(world)]
     shards, rls, qs = [], [], []
     for r in range(world):
         lo, hi = n * r // world, n * (r + 1) // world
         g = cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body)
         shards.append(g)
-        rls.append(RoutedLookup(g, spl, r, world, dev, cap, 2, emulate=blocks))
+        rls.append(RoutedLookup(g, spl, r, world, dev, cap, k, shard_first=first, emulate=blocks))
         a, canon, valid = synth.make_queries(200 + r, table, k, nq_per[r], corrupt_permille=25)
         qs.append((a, torch.stack(canon, dim=1).contiguous().cuda(), torch.where(valid, 0, 2).to(torch.uint8).cuda(),
                    torch.full((nq_per[r],), -7, dtype=torch.int64, device=dev)))
     for r in range(world):
-        rls[r].route(qs[r][1], qs[r][2], qs[r][3])
+        rls[r].route(qs[r][1], qs[r][2])
     for r in range(world):
         rls[r].search()
     for r in range(world):
@@ -461,7 +463,7 @@ def test_routed_lookup_emulated_ranks(world):
         assert int(rls[r].sent[:world].sum()) == int((qs[r][2] == 0).sum())
     # a second batch through the same buffers (stale segment contents must not leak)
     for r in range(world):
-        rls[r].route(qs[r][1][:100], qs[r][2][:100], qs[r][3][:100])
+        rls[r].route(qs[r][1][:100], qs[r][2][:100])
     for r in range(world):
         rls[r].search()
     for r in range(world):
@@ -469,6 +471,48 @@ def test_routed_lookup_emulated_ranks(world):
     torch.cuda.synchronize()
     for r in range(world):
         assert (qs[r][3][:100].cpu().numpy() == og.find_batch(qs[r][0][:100].numpy())).all()
+    for g in shards:
+        g.dispose()
+    whole.dispose()
+
+
+def test_routed_lookup_reports_segment_overflow():
+    """cap smaller than the batch: balanced batches work, a skewed batch is reported (dropped keys answer -1, sent > cap)."""
+    from corticall_b200.host.sharded import RoutedLookup
+    k, c, n, world = 31, 1, 20000, 2
+    ctx = synth.make_ctx_file(5, n, k, c, adv_period=0)
+    og = orc.Graph(ctx)
+    whole = cb.CortexGraph(ctx)
+    words_all, _, _ = whole.decodeRecords(0, n)
+    body = torch.from_numpy(whole.getRawRecords(0, n)).cuda()
+    table = [torch.from_numpy(words_all[:, 0].copy().view(np.int64))]
+    dev = torch.device("cuda", 0)
+    spl = torch.stack([torch.stack([t[n // 2] for t in table])]).cuda()
+    nq, cap = 6000, 4000
+    blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, k), dtype=torch.int64, device=dev) for _ in range(world)]
+    shards = [cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body) for lo, hi in ((0, n // 2), (n // 2, n))]
+    rls = [RoutedLookup(shards[r], spl, r, world, dev, cap, k, shard_first=[0, n // 2], emulate=blocks, max_batch=nq) for r in range(world)]
+    a, canon, valid = synth.make_queries(1, table, k, nq, hit_fraction_permille=1000, corrupt_permille=0)
+    qw = torch.stack(canon, dim=1).contiguous().cuda(); qf = torch.zeros(nq, dtype=torch.uint8, device=dev)
+    out = torch.empty(nq, dtype=torch.int64, device=dev)
+
+    def run(words):
+        rls[0].route(words, qf); rls[1].route(words[:0], qf[:0])
+        rls[0].search(); rls[1].search()
+        rls[0].gather(out)
+        torch.cuda.synchronize()
+
+    run(qw)                                              # ~3000 per owner: fits
+    rls[0].check_overflow()
+    assert (out.cpu().numpy() == og.find_batch(a.numpy())).all()
+    low = qw[qw[:, 0] < spl[0, 0]][:2500]
+    skew = torch.cat([low, low])[:nq].contiguous()       # 5000 keys for owner 0 > cap
+    qf = torch.zeros(skew.shape[0], dtype=torch.uint8, device=dev)
+    run(skew)
+    with pytest.raises(OverflowError):
+        rls[0].check_overflow()
+    got = out[:skew.shape[0]].cpu().numpy()
+    assert (got >= 0).sum() == cap and ((got >= 0) | (got == -1)).all()
     for g in shards:
         g.dispose()
     whole.dispose()
@@ -497,20 +541,96 @@ def test_pack_rows_vs_oracle(k):
             assert (got_w[i] == ow[0]).all() and got_f[i] == of[0], (k, off, i)
 
 
-def test_large_ascii_batch_uses_two_pass_path():
-    """A query list big enough for the pack-then-search path (>= 65536 rows) returns what the oracle's findRecord does."""
+@pytest.mark.parametrize("k", [1, 7, 16, 47, 64, 97])
+def test_pack_rows_every_row(k):
+    """Every row of a large list (not a sample): flag classes from a numpy classification of the bytes, and for the pure
+    upper-case rows the packed canonical words from an independent torch formulation (tools/synth.py)."""
+    nq = 200_003
+    s = (k + 31) // 32
+    seq = synth.random_genome(5 + k, nq * k + 16, n_permille=1).numpy().copy()
+    rng = np.random.default_rng(k)
+    low_at = rng.integers(0, nq * k, 300)
+    seq[low_at] |= 32                                     # lower case (or 'n')
+    seq[rng.integers(0, nq * k, 50)] = ord("-")
+    for off in (0, 3, 16):
+        rows = seq[off:off + nq * k].reshape(nq, k)
+        buf = torch.from_numpy(seq).cuda()
+        words = torch.full((nq, s), -1, dtype=torch.int64, device="cuda"); flags = torch.full((nq,), 99, dtype=torch.uint8, device="cuda")
+        N.check(N.lib().cc_pack_kmers_dev(0, buf.data_ptr() + off, nq, k, words.data_ptr(), flags.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        got_w, got_f = words.cpu(), flags.cpu().numpy()
+        up = rows & 0xDF
+        is_letter = (up == 65) | (up == 67) | (up == 71) | (up == 84)
+        bad = ~is_letter.all(axis=1)
+        low = ~bad & ((rows & 32) != 0).any(axis=1)
+        assert ((got_f == 2) == bad).all()
+        assert (((got_f & 4) != 0) == low).all()
+        assert (got_w[torch.from_numpy(bad)] == 0).all()
+        clean = ~bad & ~low
+        assert clean.sum() > nq // 2 or k > 64
+        code = np.zeros(256, dtype=np.uint64); code[67] = 1; code[71] = 2; code[84] = 3
+        crow = code[rows[clean]]
+        fw = [np.zeros(crow.shape[0], dtype=np.uint64) for _ in range(s)]
+        for i in range(k):                               # base i sits 2*(k-1-i) bits above the bottom of the s-word number
+            bit = 2 * (k - 1 - i)
+            fw[s - 1 - bit // 64] |= crow[:, i] << np.uint64(bit % 64)
+        canon, flipped = synth.canonical_words([torch.from_numpy(w.view(np.int64)) for w in fw], k)
+        gw = got_w[torch.from_numpy(clean)]
+        for w in range(s):
+            assert torch.equal(gw[:, w], canon[w]), (k, off, w)
+        assert ((got_f[clean] & 1) == flipped.numpy().astype(np.uint8)).all()
+        # the sampled lower-case rows against the oracle's byte rule
+        for i in np.nonzero(low)[0][:40]:
+            ow, of = orc.pack_windows(rows[i], k)
+            assert (got_w[i].numpy().view(np.uint64) == ow[0]).all() and got_f[i] == of[0], (k, off, i)
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_large_ascii_batch(fused):
+    """A large query list through both forms of cc_find_ascii (pack + search in one kernel / pack, then search) returns
+    what the oracle's findRecord does."""
     k, c, n = 47, 4, 30000
     ctx = synth.make_ctx_file(8, n, k, c, adv_period=0)
     g = cb.CortexGraph(ctx)
     og = orc.Graph(ctx)
     words, _, _ = g.decodeRecords(0, n)
     tw = [torch.from_numpy(words[:, w].copy().view(np.int64)) for w in range(2)]
-    q_ascii, _, _ = synth.make_queries(3, tw, k, 90_000, corrupt_permille=20)
-    got = g.findRecordIndices(q_ascii.numpy())
-    sub = np.arange(0, 90_000, 7)
+    q_ascii, _, _ = synth.make_queries(3, tw, k, 90_001, corrupt_permille=20)
+    N.set_option("rows_fused", fused)
+    try:
+        got = g.findRecordIndices(q_ascii.numpy())
+    finally:
+        N.set_option("rows_fused", 1)
+    sub = np.arange(0, 90_001, 7)
     assert (got[sub] == og.find_batch(q_ascii.numpy()[sub])).all()
     assert (got >= 0).sum() > 30000
     g.dispose()
+
+
+@pytest.mark.parametrize("k", [15, 31, 47, 65])
+def test_shard_index_spans_its_own_key_range(k):
+    """A k-mer-range shard opened on its own (cc_open_device, first_index = offset): its prefix table spans only the shard's
+    [first key, last key]; queries below, inside and above that range return the global index or -1."""
+    c, n = 2, 50_000
+    ctx = synth.make_ctx_file(77, n, k, c, adv_period=0)
+    whole = cb.CortexGraph(ctx)
+    og = orc.Graph(ctx)
+    s = whole.getKmerBits()
+    words_all, _, _ = whole.decodeRecords(0, n)
+    body = torch.from_numpy(whole.getRawRecords(0, n)).cuda()
+    tw = [torch.from_numpy(words_all[:, w].copy().view(np.int64)) for w in range(s)]
+    q_ascii, canon, valid = synth.make_queries(9, tw, k, 30_000, hit_fraction_permille=800, corrupt_permille=5)
+    want = og.find_batch(q_ascii.numpy())
+    pw = np.stack([cw.numpy().view(np.uint64) for cw in canon], axis=1)
+    fl = np.where(valid.numpy(), 0, 2).astype(np.uint8)
+    for lo, hi in ((0, n // 7), (n // 3, n // 3 + 1), (n // 3, 2 * n // 3), (n - 5, n), (n // 2, n // 2 + 2)):
+        g = cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body)
+        exp = np.where((want >= lo) & (want < hi), want, -1)
+        for algo in (cb.CC_ALGO_AUTO, cb.CC_ALGO_BSEARCH):
+            assert (g.findPacked(pw, fl, algo) == exp).all(), (lo, hi, algo)
+        assert (g.findRecordIndices(q_ascii.numpy()) == exp).all(), (lo, hi)
+        g.dispose()
+    whole.dispose()
 
 
 # ------------------------------------------------------------------ next row: CortexCollection / Join

@@ -27,7 +27,7 @@ for k, c, n in ((47, 4, 3000), (63, 21, 700), (31, 1, 1500), (31, 45, 300)):
     if words.shape[1] == 2:
         dev = torch.device("cuda", 0)
         world, cap = 3, 2000
-        blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, 2), dtype=torch.int64, device=dev) for _ in range(world)]
+        blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, k), dtype=torch.int64, device=dev) for _ in range(world)]
         spl = torch.stack([torch.stack([t[n * r // world] for t in tw]) for r in range(1, world)]).cuda()
         body = torch.from_numpy(g.getRawRecords(0, n)).cuda()
         rls, shards = [], []
@@ -35,12 +35,12 @@ for k, c, n in ((47, 4, 3000), (63, 21, 700), (31, 1, 1500), (31, 45, 300)):
             lo, hi = n * rnk // world, n * (rnk + 1) // world
             sg = cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body)
             shards.append(sg)
-            rls.append(RoutedLookup(sg, spl, rnk, world, dev, cap, 2, emulate=blocks))
+            rls.append(RoutedLookup(sg, spl, rnk, world, dev, cap, k, shard_first=[n * x // world for x in range(world)], emulate=blocks))
         qw = torch.stack(canon, dim=1).contiguous().cuda(); qf = torch.where(valid, 0, 2).to(torch.uint8).cuda()
         out = torch.empty(2000, dtype=torch.int64, device=dev)
-        rls[0].route(qw, qf, out)
+        rls[0].route(qw, qf)
         for rl in rls[1:]:
-            rl.route(qw[:0], qf[:0], out[:0])
+            rl.route(qw[:0], qf[:0])
         for rl in rls:
             rl.search()
         rls[0].gather(out)
