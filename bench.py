@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=1_000_000_000, help="lookup queries per step, all ranks together (configs[2] = 1e9)")
     ap.add_argument("--no-lookup", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lookup-only", action="store_true", help="experiments: only the lookup object (not a bench line)")
+    ap.add_argument("--pipeline", type=int, default=0, help="experiments: also time the sub-batch pipelined routed lookup with this many sub-batches")
+    ap.add_argument("--no-compare", action="store_true", help="skip the replicated-table and NCCL comparison modes of the lookup leg")
     ap.add_argument("--spinup", type=float, default=1.0, help="seconds of untimed back-to-back scans before warm-up")
     return ap.parse_args()
 
@@ -189,6 +192,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    if args.lookup_only:
+        lookup = bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks)
+        if rank == 0:
+            print(json.dumps({"lookup_only": True, "n_gpus": world, "lookup": lookup}))
+        return
 
     # ------------------------------------------------------------ the scan workload (configs[1]), one shard per rank
     n = args.records
@@ -381,6 +390,12 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         ms = timeit(lambda: N.check(L.cc_find_ascii_dev(g._h, qascii.data_ptr(), n_ascii, res.data_ptr(), cb.CC_ALGO_AUTO, stream)))
         out["ascii_lookups_per_s"] = n_ascii / (ms / 1000.0)
         out["ascii_queries_per_step"] = n_ascii
+        pw = torch.empty((n_ascii, S_WORDS), dtype=torch.int64, device=dev)
+        pf = torch.empty(n_ascii, dtype=torch.uint8, device=dev)
+        ms = timeit(lambda: N.check(L.cc_pack_kmers_dev(local_rank, qascii.data_ptr(), n_ascii, K, pw.data_ptr(), pf.data_ptr(), stream)))
+        out["pack_rows_per_s"] = n_ascii / (ms / 1000.0)                 # K3 on independent k-byte rows
+        out["pack_rows_algorithmic_gb_per_s"] = out["pack_rows_per_s"] * (K + 8 * S_WORDS + 1) / 1e9
+        del pw, pf
         nm = min(nq, 1 << 26)
         ms = timeit(lambda: N.check(L.cc_find_packed_dev(g._h, qwords.data_ptr(), qflags.data_ptr(), nm, res.data_ptr(), cb.CC_ALGO_MERGE, stream)))
         out["packed_sorted_merge_lookups_per_s"] = nm / (ms / 1000.0)
@@ -391,7 +406,9 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         out["algorithmic_gb_per_s"] = out["lookups_per_s"] * bpl / 1e9
     else:
         from corticall_b200.host.sharded import RoutedLookup
-        rl = RoutedLookup(g, splitters, rank, world, dev, cap=nq, k=K)
+        # segments sized for the balanced case (+25 %) instead of the worst case nq: 6x less peer-mapped address space per
+        # rank (the worst-case layout cost 40 % on the search leg of most ranks: TLB reach); overflow is checked per batch
+        rl = RoutedLookup(g, splitters, rank, world, dev, cap=int(nq / world * 1.25) + 4096, k=K, max_batch=nq)
         ms = timeit(lambda: rl.find_packed(qwords, qflags, res))
         out["lookups_per_s"] = nq * world / (ms / 1000.0)
         out["ms_per_step"] = ms
@@ -401,7 +418,25 @@ def bench_lookup(args, rank, world, local_rank, dev, barrier, max_over_ranks):
         barrier()
         rl.find_packed(qwords, qflags, res, profile=True)
         out["phase_ms_rank0"] = rl.phase_ms
+        import torch.distributed as dist
+        allp = [None] * world
+        dist.all_gather_object(allp, {k: round(v, 3) for k, v in rl.phase_ms.items()})
+        out["phase_ms_all_ranks"] = allp
         del rl
+        if args.pipeline > 0:
+            from corticall_b200.host.sharded import PipelinedRoutedLookup
+            for per in ((1, 1, 2), (1, 1, 3), (2, 2, 2)):
+                pl = PipelinedRoutedLookup(g, splitters, rank, world, dev, sub_batch=(nq + args.pipeline - 1) // args.pipeline, k=K)
+                pl.route_per_sm, pl.gather_per_sm, pl.search_per_sm = per
+                res3 = torch.empty_like(res)
+                msp = timeit(lambda: pl.find_packed(qwords, qflags, res3))
+                key = "pipelined_%d_r%d_g%d_s%d" % ((args.pipeline,) + per)
+                out[key + "_lookups_per_s"] = nq * world / (msp / 1000.0)
+                out[key + "_agrees"] = bool(torch.equal(res, res3))
+                del pl, res3
+        if args.no_compare:
+            g.dispose()
+            return out
         # replicas: when the whole table fits every GPU (it does for configs[2]: 3.6 GB of records + 2.1 GB of index), each
         # rank can hold a full copy and look up its own queries with no exchange at all (SURVEY 8e "alternative mode")
         try:

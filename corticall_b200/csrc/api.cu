@@ -353,6 +353,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "scan_tile_bytes")) o.scan_tile_bytes = (int)value;
     else if (!strcmp(name, "scan_ctas_per_sm")) o.scan_ctas_per_sm = (int)value;
     else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
+    else if (!strcmp(name, "index_buckets")) o.index_buckets = (int)value;
     else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
     else if (!strcmp(name, "lookup_queries_per_thread")) o.lookup_queries_per_thread = (int)value;
     else if (!strcmp(name, "rows_fused")) o.rows_fused = (int)value;
@@ -366,6 +367,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "scan_stage_buf_bytes")) o.scan_stage_buf_bytes = (int)value;
     else if (!strcmp(name, "scan_chunk_tiles")) o.scan_chunk_tiles = (int)value;
     else if (!strcmp(name, "mlp_grid_per_sm")) o.mlp_grid_per_sm = (int)value;
+    else if (!strcmp(name, "lookup_l2_hints")) o.lookup_l2_hints = (int)value;
     else return fail(CC_ERR_ARG, "unknown option '%s'", name);
     return CC_OK;
 }
@@ -946,12 +948,12 @@ int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *d
                         max_queries, dev_sent, static_cast<cudaStream_t>(stream));
 }
 
-int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, int my_rank, uint64_t cap,
                        void *const *peer_ret, void *stream) {
     if (!g || !dev_inbox || !dev_counts_in || !peer_ret) return fail(CC_ERR_ARG, "null argument");
     DeviceGuard guard(g->device);
     if (int rc = ensure_index(g)) return rc;
-    return launch_find_routed(g, dev_inbox, dev_counts_in, nshards, my_rank, cap, peer_ret, static_cast<cudaStream_t>(stream));
+    return launch_find_routed(g, dev_inbox, dev_counts_in, world, vsub, my_rank, cap, peer_ret, static_cast<cudaStream_t>(stream));
 }
 
 int cc_gather_routed_dev(int device, const void *dev_ret, const void *dev_route_state, uint64_t max_queries, uint64_t nq,

@@ -32,14 +32,16 @@ struct Options {
     int scan_tile_bytes = 32768;
     int scan_ctas_per_sm = 2;
     int index_bits = 0;          // 0 = auto
+    int index_buckets = 0;       // exact bucket count of the prefix table (overrides index_bits; 0 = 2^bits)
     int lookup_block = 256;
     int lookup_queries_per_thread = 2;
     int rows_rpt2_max_k = 32;    // cc_pack_kmers: two rows per thread (512-row tiles) up to this k, else one
+    int lookup_l2_hints = 3;     // bit0: key loads evict-first in L2, bit1: prefix-table loads evict-last
     int mlp_grid_per_sm = 8;     // find_packed_mlp_kernel: CTAs per SM (0 = resident CTAs only; measured 10 % slower)
     int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1
     int routed_search_blocks_per_sm = 3;  // grid of find_routed_kernel per SM (3 = the resident CTAs; measured best of 3/4/8/16)
-    int gather_blocks_per_sm = 8;   // 0 = the single-query kernel
+    int gather_blocks_per_sm = 16;  // cap on resident gather CTAs per SM
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
     int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)
@@ -89,7 +91,8 @@ struct LookupIndex {
     uint32_t *table = nullptr;    // [nbuckets + 2] lower bounds over the array's own key range
     int bits = 0;                 // requested log2 of the bucket count
     uint64_t base = 0;            // top 64 bits of the first key
-    uint32_t shift = 0, nbuckets = 1;
+    uint64_t scale = 0;           // see key_bucket
+    uint32_t norm = 0, nbuckets = 1;
     bool built = false;
     bool sorted = true;
     uint64_t unsorted_at = 0;
@@ -167,7 +170,7 @@ uint64_t route_state_size(uint64_t max_q, int nshards);
 int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k, const uint64_t *dev_splitters, int nshards,
                  int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, void *dev_route_state, uint64_t max_q,
                  uint64_t *dev_sent, cudaStream_t st);
-int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, int my_rank, uint64_t cap,
                        void *const *peer_ret, cudaStream_t st);
 int launch_gather_routed(const void *dev_ret, const void *dev_route_state, uint64_t max_q, uint64_t nq, const uint64_t *dev_shard_first,
                          int nshards, uint64_t cap, int64_t *dev_out, cudaStream_t st);

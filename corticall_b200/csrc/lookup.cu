@@ -167,10 +167,41 @@ struct IndexView {
     uint64_t n;
     uint64_t first_index;
     uint64_t base;              // top 64 bits (left-aligned) of the first key of THIS array
+    uint64_t scale;             // bucket = mulhi((top64(q) - base) << norm, scale): exactly nbuckets equal slices of the span
     uint32_t nbuckets;
-    uint32_t shift;             // bucket = (top64(q) - base) >> shift
+    uint32_t norm;
     uint32_t k;
+    uint32_t hints;             // bit0: key loads evict-first in L2, bit1: table loads evict-last (keep the table resident)
 };
+
+// L2 cache policies for the search: the key column is touched at random and never again (evict first), the prefix table
+// is the only structure with reuse (evict last).
+struct LookupPolicies {
+    uint64_t keys, table;
+};
+__device__ __forceinline__ LookupPolicies make_lookup_policies(uint32_t hints) {
+    LookupPolicies p;
+    if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.keys));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.keys));
+    if (hints & 2u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.table));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.table));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t policy) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+template <int S>
+__device__ __forceinline__ void load_key_hint(const uint64_t *__restrict__ keys, uint64_t i, uint64_t (&out)[S], uint64_t policy) {
+    if (S == 2) {
+        asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(out[0]), "=l"(out[1 % S]) : "l"(keys + 2 * i), "l"(policy));
+    } else {
+#pragma unroll
+        for (int w = 0; w < S; ++w)
+            asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(out[w]) : "l"(keys + i * S + w), "l"(policy));
+    }
+}
 
 // The 64 most significant bits of the 2k-bit key, left-aligned.
 template <int S>
@@ -187,7 +218,9 @@ template <int S>
 __device__ __forceinline__ uint32_t key_bucket(const IndexView &ix, const uint64_t (&q)[S]) {
     const uint64_t t = key_top64<S>(q, ix.k);
     if (t < ix.base) return ix.nbuckets;
-    const uint64_t b = (t - ix.base) >> ix.shift;
+    const uint64_t d = t - ix.base;
+    if ((d >> (63u - ix.norm)) > 1u) return ix.nbuckets;        // d << norm would overflow: beyond the last key
+    const uint64_t b = __umul64hi(d << ix.norm, ix.scale);
     return b < ix.nbuckets ? (uint32_t)b : ix.nbuckets;
 }
 
@@ -294,15 +327,15 @@ constexpr uint32_t kProbe = 4;
 
 // Q queries per thread: table reads for all, then the first kProbe keys of every bucket, then compare.
 template <int S, int Q>
-__device__ __forceinline__ void lookup_mlp(const IndexView &ix, const uint64_t (&q)[Q][S], const bool (&live)[Q], int64_t (&r)[Q]) {
+__device__ __forceinline__ void lookup_mlp(const IndexView &ix, const LookupPolicies &pol, const uint64_t (&q)[Q][S], const bool (&live)[Q], int64_t (&r)[Q]) {
     uint32_t lo[Q], hi[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         lo[j] = hi[j] = 0;
         if (live[j]) {
             const uint32_t p = key_bucket<S>(ix, q[j]);
-            lo[j] = __ldg(ix.table + p);
-            hi[j] = __ldg(ix.table + p + 1);
+            lo[j] = ldg_u32_hint(ix.table + p, pol.table);
+            hi[j] = ldg_u32_hint(ix.table + p + 1, pol.table);
         }
     }
     uint64_t kk[Q][kProbe][S];
@@ -310,7 +343,7 @@ __device__ __forceinline__ void lookup_mlp(const IndexView &ix, const uint64_t (
     for (int j = 0; j < Q; ++j) {
 #pragma unroll
         for (uint32_t t = 0; t < kProbe; ++t) {
-            if (live[j] && lo[j] + t < hi[j]) load_key<S>(ix.keys, (uint64_t)lo[j] + t, kk[j][t]);
+            if (live[j] && lo[j] + t < hi[j]) load_key_hint<S>(ix.keys, (uint64_t)lo[j] + t, kk[j][t], pol.keys);
             else {
 #pragma unroll
                 for (int w = 0; w < S; ++w) kk[j][t][w] = ~0ull;
@@ -333,6 +366,7 @@ template <int S, int Q>
 __global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
                                                                  uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
     const uint64_t span = (uint64_t)gridDim.x * kBlock;
+    const LookupPolicies pol = make_lookup_policies(ix.hints);
     for (uint64_t base = (uint64_t)blockIdx.x * kBlock + threadIdx.x; base < nq; base += span * Q) {
         uint64_t q[Q][S];
         bool live[Q];
@@ -346,7 +380,7 @@ __global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t 
                 if (flags && (flags[i] & 6u)) live[j] = false, out_index[i] = -1;
             }
         }
-        lookup_mlp<S, Q>(ix, q, live, r);
+        lookup_mlp<S, Q>(ix, pol, q, live, r);
 #pragma unroll
         for (int j = 0; j < Q; ++j)
             if (live[j]) out_index[base + (uint64_t)j * span] = r[j];
@@ -469,6 +503,7 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
     const uint64_t ntiles = (nq + kRows - 1) / kRows;
     const uint32_t top_bits = 2u * k - 64u * (S - 1);
     const uint64_t policy = make_evict_first_policy();
+    const LookupPolicies pol = make_lookup_policies(FIND ? ix.hints : 0u);
 
     // tile t of this CTA: rows [row0, row0 + rows); the copy fetches the 16-byte-aligned superset of its bytes
     auto issue = [&](uint64_t tile, uint32_t buf) {
@@ -580,7 +615,7 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
             int64_t res[RPT];
 #pragma unroll
             for (int h = 0; h < RPT; ++h) live[h] = have[h] && (flags[h] & 6u) == 0;
-            lookup_mlp<S, RPT>(ix, q, live, res);
+            lookup_mlp<S, RPT>(ix, pol, q, live, res);
 #pragma unroll
             for (int h = 0; h < RPT; ++h)
                 if (have[h]) out_index[row0 + threadIdx.x + h * kBlock] = live[h] ? res[h] : -1;
@@ -627,8 +662,10 @@ __device__ __forceinline__ uint32_t owner_of(const uint64_t (&q)[S], const uint6
 // Wire format of a key: the KW = ceil(2k/32) low 32-bit words of the 64*S-bit number, most significant first
 // (12 bytes instead of 16 at k = 47).
 constexpr int kRouteQ = 8;                   // queries per thread per tile of the route kernel
-constexpr int kRouteBlock = 256;
-constexpr uint32_t kRouteTile = kRouteBlock * kRouteQ;
+// Tile = block * kRouteQ queries.  Few owners: 128-thread blocks (1024-query tiles, more independent CTAs per SM for the
+// barrier-heavy tile loop); many owners (virtual shards): 256-thread blocks, so that an owner's run in a tile stays a
+// few hundred bytes.  Route and gather of one batch must agree on it: both derive it from nshards.
+__host__ __device__ inline int route_block_for(int nshards) { return nshards > 16 ? 256 : 128; }
 constexpr uint32_t kNotRouted = 0xffffu;
 constexpr uint32_t kWireMiss = 0xffffffffu;
 
@@ -663,10 +700,10 @@ struct RouteState {
     uint32_t *tile_base;
     uint32_t *tile_cnt;
 };
-__host__ __device__ inline uint64_t route_tiles(uint64_t nq) { return (nq + kRouteTile - 1) / kRouteTile; }
+__host__ __device__ inline uint64_t route_tiles(uint64_t nq, uint32_t tile_q) { return (nq + tile_q - 1) / tile_q; }
 inline uint64_t route_state_bytes(uint64_t max_q, int nshards) {
     const uint64_t at = (max_q * 2 + 15) & ~15ull;
-    return at + 2 * route_tiles(max_q) * (uint64_t)nshards * 4 + 16;
+    return at + 2 * route_tiles(max_q, route_block_for(nshards) * kRouteQ) * (uint64_t)nshards * 4 + 16;
 }
 inline RouteState route_state_of(void *buf, uint64_t max_q, int nshards) {
     RouteState r;
@@ -674,24 +711,79 @@ inline RouteState route_state_of(void *buf, uint64_t max_q, int nshards) {
     r.at16 = reinterpret_cast<uint16_t *>(b);
     b += (max_q * 2 + 15) & ~15ull;
     r.tile_base = reinterpret_cast<uint32_t *>(b);
-    r.tile_cnt = r.tile_base + route_tiles(max_q) * (uint64_t)nshards;
+    r.tile_cnt = r.tile_base + route_tiles(max_q, route_block_for(nshards) * kRouteQ) * (uint64_t)nshards;
     return r;
 }
+// Exclusive prefix sums of up to 64 values by one warp: lane l holds elements 2l and 2l+1; returns their prefixes, and the
+// total in every lane.
+__device__ __forceinline__ void warp_excl_scan64(uint32_t v0, uint32_t v1, uint32_t lane, uint32_t &p0, uint32_t &p1, uint32_t &total) {
+    const uint32_t s2 = v0 + v1;
+    uint32_t inc = s2;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    p0 = inc - s2;
+    p1 = p0 + v0;
+    total = __shfl_sync(0xffffffffu, inc, 31);
+}
 
-// Tile of kRouteTile queries per block iteration.  The tile is regrouped by owner in shared memory so that each
-// owner's run leaves as fully coalesced stores (whole 128-byte lines over NVLink instead of per-query fragments).
-template <int S, int KW>
-__global__ void __launch_bounds__(kRouteBlock) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
-                                                            const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
-                                                            PeerPtrs inbox, RouteState rs, unsigned long long *cursors) {
-    extern __shared__ __align__(16) uint32_t stage[];     // [kRouteTile * KW] wire keys, grouped by owner
-    __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1];
+constexpr uint32_t kOwnerLutBits = 10;         // owner lookup: 2^10 key prefixes -> first candidate owner
+
+// Dynamic shared memory of route_kernel: staged wire keys (each owner's run padded to its destination's 16-byte phase)
+// followed by one owner id per 16-byte slot of that staging area.
+inline uint32_t route_stage_words(uint32_t tile_q, uint32_t kw, int nshards) { return (tile_q * kw + 8u * (uint32_t)nshards + 3u) & ~3u; }
+inline size_t route_smem_bytes(uint32_t tile_q, uint32_t kw, int nshards) {
+    const uint32_t w = route_stage_words(tile_q, kw, nshards);
+    return (size_t)w * 4u + ((w / 4u + 15u) & ~15u);
+}
+
+// Tile of BLOCK * kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory, every owner's run
+// at the 16-byte phase of its destination, and leaves as aligned 16-byte stores (full NVLink write packets instead of
+// per-query fragments).
+template <int S, int KW, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
+                                                      const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
+                                                      PeerPtrs inbox, RouteState rs, unsigned long long *cursors, uint32_t stage_words,
+                                                      uint32_t k_bases) {
+    constexpr uint32_t kTile = BLOCK * kRouteQ;
+    extern __shared__ __align__(16) uint32_t stage[];     // [stage_words] wire keys, then uint8 slot_owner[stage_words / 4]
+    uint8_t *slot_owner = reinterpret_cast<uint8_t *>(stage + stage_words);
+    __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1], locw[kMaxShards], endw[kMaxShards];
     __shared__ unsigned long long base[kMaxShards];
+    __shared__ uint32_t *dptr[kMaxShards];                // dptr[o] + w = destination of staged word w of owner o
     __shared__ uint64_t spl[(kMaxShards - 1) * S];
-    for (int i = threadIdx.x; i < (nshards - 1) * S; i += kRouteBlock) spl[i] = splitters[i];
-    const uint64_t ntiles = route_tiles(nq);
+    __shared__ uint8_t owner_lut[1u << kOwnerLutBits];    // number of splitters below the smallest key of each prefix
+    for (int i = threadIdx.x; i < (nshards - 1) * S; i += BLOCK) spl[i] = splitters[i];
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < (1u << kOwnerLutBits); p += BLOCK) {
+        // smallest key with these top bits, as S right-aligned words of a 2k-bit key
+        uint64_t lowkey[S];
+        const uint32_t kbits = 2u * k_bases;
+#pragma unroll
+        for (int w = 0; w < S; ++w) lowkey[w] = 0;
+        if (kbits >= kOwnerLutBits) {
+            const uint32_t sh = kbits - kOwnerLutBits;          // bit position of the prefix inside the 64*S-bit number
+            const uint32_t wi = S - 1 - sh / 64, bi = sh % 64;
+            lowkey[wi] = (uint64_t)p << bi;
+            if (bi + kOwnerLutBits > 64 && wi > 0) lowkey[wi - 1] = (uint64_t)p >> (64 - bi);
+        }
+        uint32_t o = 0;                                         // splitters strictly below lowkey
+        while (o < (uint32_t)nshards - 1) {
+            uint64_t sp[S];
+#pragma unroll
+            for (int w = 0; w < S; ++w) sp[w] = spl[o * S + w];
+            if (!words_less<S>(sp, lowkey)) break;
+            ++o;
+        }
+        owner_lut[p] = (uint8_t)o;
+    }
+    const uint64_t ntiles = route_tiles(nq, kTile);
+    const uint32_t nslots = stage_words >> 2;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int i = threadIdx.x; i < nshards; i += kRouteBlock) hist[i] = 0;
+        for (int i = threadIdx.x; i < nshards; i += BLOCK) hist[i] = 0;
+        for (uint32_t i = threadIdx.x; i < (nslots + 3u) / 4u; i += BLOCK) reinterpret_cast<uint32_t *>(slot_owner)[i] = 0xffffffffu;
         __syncthreads();
         uint64_t q[kRouteQ][S];
         uint32_t own[kRouteQ], rank_in[kRouteQ];
@@ -699,12 +791,12 @@ __global__ void __launch_bounds__(kRouteBlock) route_kernel(const uint64_t *__re
         // all loads of the tile are issued before anything depends on them (one exposed round trip per tile)
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            const uint64_t i = tile * kTile + (uint64_t)j * BLOCK + threadIdx.x;
             fl[j] = (i < nq) ? ((flags != nullptr) ? (uint32_t)__ldg(flags + i) : 0u) : 6u;
         }
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            const uint64_t i = tile * kTile + (uint64_t)j * BLOCK + threadIdx.x;
             if (i < nq) load_key<S>(words, i, q[j]);
             else {
 #pragma unroll
@@ -712,8 +804,23 @@ __global__ void __launch_bounds__(kRouteBlock) route_kernel(const uint64_t *__re
             }
         }
 #pragma unroll
-        for (int j = 0; j < kRouteQ; ++j)                  // flagged queries are never routed: they cannot match
-            own[j] = (fl[j] & 6u) ? 0xffffffffu : owner_of<S>(q[j], spl, nshards);
+        for (int j = 0; j < kRouteQ; ++j) {                // flagged queries are never routed: they cannot match
+            own[j] = 0xffffffffu;
+            if (!(fl[j] & 6u)) {
+                // owner = number of splitters <= q: the prefix table gives those below the prefix, the rest is a short scan
+                const uint32_t kbits = 2u * k_bases;
+                uint32_t o = 0;
+                if (kbits >= kOwnerLutBits) o = owner_lut[(uint32_t)(key_top64<S>(q[j], k_bases) >> (64u - kOwnerLutBits))];
+                while (o < (uint32_t)nshards - 1) {
+                    uint64_t sp[S];
+#pragma unroll
+                    for (int w = 0; w < S; ++w) sp[w] = spl[o * S + w];
+                    if (words_less<S>(q[j], sp)) break;
+                    ++o;
+                }
+                own[j] = o;
+            }
+        }
         // warp-aggregated ranking: one shared-memory atomic per (warp, owner) instead of one per query -- with few
         // owners the per-query atomics all hit the same two or eight addresses and serialise
         const uint32_t lane = threadIdx.x & 31u, lane_lt = (1u << lane) - 1u;
@@ -727,47 +834,88 @@ __global__ void __launch_bounds__(kRouteBlock) route_kernel(const uint64_t *__re
             rank_in[j] = b + __popc(peers & lane_lt);
         }
         __syncthreads();
-        if (threadIdx.x < (uint32_t)nshards) {
-            const uint32_t cnt = hist[threadIdx.x];
-            const unsigned long long b0 = cnt ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)cnt) : 0ull;
-            base[threadIdx.x] = b0;
-            rs.tile_base[tile * nshards + threadIdx.x] = (uint32_t)b0;
-            rs.tile_cnt[tile * nshards + threadIdx.x] = cnt;
+        // warps 2-3 reserve the owners' segments space (one global atomic per owner with keys in this tile) while warp 0
+        // turns the histogram into the tile's regrouped order
+        if (threadIdx.x >= 64 && threadIdx.x < 64u + (uint32_t)nshards) {
+            const uint32_t o = threadIdx.x - 64;
+            const uint32_t cnt = hist[o];
+            const unsigned long long b0 = cnt ? atomicAdd(&cursors[o], (unsigned long long)cnt) : 0ull;
+            base[o] = b0;
+            rs.tile_base[tile * nshards + o] = (uint32_t)b0;
+            rs.tile_cnt[tile * nshards + o] = cnt;
         }
-        if (threadIdx.x == 0) {
-            uint32_t acc = 0;
-            for (int i = 0; i < nshards; ++i) { loc[i] = acc; acc += hist[i]; }
-            loc[nshards] = acc;
+        if (threadIdx.x < 32) {
+            const uint32_t e0 = 2 * lane, e1 = e0 + 1;
+            const uint32_t v0 = e0 < (uint32_t)nshards ? hist[e0] : 0u, v1 = e1 < (uint32_t)nshards ? hist[e1] : 0u;
+            uint32_t p0, p1, tot;
+            warp_excl_scan64(v0, v1, lane, p0, p1, tot);
+            if (e0 < (uint32_t)nshards) loc[e0] = p0;
+            if (e1 < (uint32_t)nshards) loc[e1] = p1;
+            if (lane == 0) loc[nshards] = tot;
+        }
+        __syncthreads();
+        // staging layout: every owner's run starts in a fresh 16-byte slot, at the 16-byte phase of its destination
+        if (threadIdx.x < 32) {
+            uint32_t len[2], phase[2], keepw[2];
+            uint64_t dw[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t o = 2 * lane + e;
+                len[e] = 0; phase[e] = 0; keepw[e] = 0; dw[e] = 0;
+                if (o < (uint32_t)nshards) {
+                    const uint64_t b0 = base[o];
+                    dw[e] = ((uint64_t)my_rank * cap + b0) * KW;                    // destination word index in the owner's inbox
+                    // a segment holds `cap` keys; keys beyond it are dropped here and reported through sent[o] > cap
+                    const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)hist[o], (unsigned long long)(cap - b0));
+                    phase[e] = (uint32_t)(dw[e] & 3u);
+                    keepw[e] = keep * KW;
+                    len[e] = (phase[e] + hist[o] * KW + 3u) & ~3u;                  // slots taken, in words
+                }
+            }
+            uint32_t p[2], tot;
+            warp_excl_scan64(len[0], len[1], lane, p[0], p[1], tot);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t o = 2 * lane + e;
+                if (o < (uint32_t)nshards) {
+                    locw[o] = p[e] + phase[e];
+                    endw[o] = locw[o] + keepw[e];
+                    dptr[o] = static_cast<uint32_t *>(inbox.p[o]) + dw[e] - locw[o];
+                }
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            const uint64_t i = tile * kTile + (uint64_t)j * BLOCK + threadIdx.x;
             if (i >= nq) continue;
             uint32_t at = kNotRouted;
             if (own[j] != 0xffffffffu) {
-                at = loc[own[j]] + rank_in[j];
-                key_to_wire<S, KW>(q[j], stage + (size_t)at * KW);
+                at = loc[own[j]] + rank_in[j];                       // position in the tile's regrouped order (for the gather)
+                const uint32_t w0 = locw[own[j]] + rank_in[j] * KW;
+                key_to_wire<S, KW>(q[j], stage + w0);
+                slot_owner[w0 >> 2] = (uint8_t)own[j];               // same value from every key of the run: benign
+                slot_owner[(w0 + KW - 1) >> 2] = (uint8_t)own[j];
+                if (KW > 4) {
+#pragma unroll
+                    for (uint32_t w = 4; w < (uint32_t)KW; w += 4) slot_owner[(w0 + w) >> 2] = (uint8_t)own[j];
+                }
             }
             rs.at16[i] = (uint16_t)at;
         }
         __syncthreads();
-        // copy-out: every warp takes whole pieces (an owner's run, split in `nsub` parts when there are fewer owners
-        // than warps), so the stores of a warp are one contiguous stream and nothing is recomputed per word
-        {
-            const uint32_t warp = threadIdx.x >> 5;
-            const uint32_t nsub = max(1u, (uint32_t)(kRouteBlock / 32) / (uint32_t)nshards);
-            for (uint32_t piece = warp; piece < (uint32_t)nshards * nsub; piece += kRouteBlock / 32) {
-                const uint32_t o = piece / nsub, part = piece - o * nsub;
-                const uint32_t cnt = hist[o];
-                const uint64_t b0 = base[o];
-                // a segment holds `cap` keys; keys beyond it are dropped here and reported through sent[o] > cap
-                const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)cnt, (unsigned long long)(cap - b0));
-                const uint32_t nwords = keep * KW, per = ((nwords + nsub - 1) / nsub + 31u) & ~31u;
-                const uint32_t w0 = part * per, w1 = min(nwords, w0 + per);
-                uint32_t *dst = static_cast<uint32_t *>(inbox.p[o]) + ((uint64_t)my_rank * cap + b0) * KW;
-                const uint32_t *src = stage + (size_t)loc[o] * KW;
-                for (uint32_t t = w0 + lane; t < w1; t += 32) dst[t] = src[t];
+        // copy-out, flat over the 16-byte slots of the staging area: a slot belongs to one owner (runs start in a fresh slot)
+        for (uint32_t sl = threadIdx.x; sl < nslots; sl += BLOCK) {
+            const uint32_t o = slot_owner[sl];
+            if (o == 0xffu) continue;
+            const uint32_t w0 = sl << 2, lo = locw[o], hi = endw[o];
+            uint32_t *d = dptr[o] + w0;
+            if (w0 >= lo && w0 + 4u <= hi) {
+                *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(stage + w0);
+            } else {
+#pragma unroll
+                for (uint32_t w = 0; w < 4; ++w)
+                    if (w0 + w >= lo && w0 + w < hi) d[w] = stage[w0 + w];
             }
         }
         __syncthreads();
@@ -782,64 +930,80 @@ __global__ void publish_counts_kernel(const unsigned long long *cursors, int nsh
     __threadfence_system();
 }
 
+// The owner's side.  With vsub > 1 every rank's shard is cut into vsub contiguous sub-ranges ("virtual shards": the route
+// kernel simply sees world * vsub owners) and the sub-ranges are searched one after another, so the slice of the key
+// column and of the prefix table in use at any time fits L2 -- the partitioned (sort-merge-like) form of the lookup for
+// large batches.  inbox: [vsub][world][cap][KW], counts_in: [vsub][world]; ret on the origin: [world * vsub][cap].
 template <int S, int KW, int Q>
 __global__ void __launch_bounds__(kBlock, S <= 2 ? 3 : 1) find_routed_kernel(const uint32_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
-                                                             int nshards, int my_rank, uint64_t cap, IndexView ix, PeerPtrs ret) {
+                                                                             int world, int vsub, int my_rank, uint64_t cap, IndexView ix, PeerPtrs ret) {
+    // all segments in (sub-range, source) order form one flat sequence of keys; the grid sweeps it front to back, so the
+    // CTAs work on the same sub-range at the same time
     __shared__ unsigned long long pre[kMaxShards + 1];
+    const uint32_t nseg = (uint32_t)(world * vsub);
     if (threadIdx.x == 0) {
         unsigned long long acc = 0;
-        for (int i = 0; i < nshards; ++i) { pre[i] = acc; acc += counts_in[i] < cap ? counts_in[i] : cap; }
-        pre[nshards] = acc;
+        for (uint32_t i = 0; i < nseg; ++i) { pre[i] = acc; acc += counts_in[i] < cap ? counts_in[i] : cap; }
+        pre[nseg] = acc;
     }
     __syncthreads();
-    const uint64_t total = pre[nshards];
+    const uint64_t total = pre[nseg];
     const uint64_t span = (uint64_t)gridDim.x * kBlock;
+    const LookupPolicies pol = make_lookup_policies(ix.hints);
     for (uint64_t basei = (uint64_t)blockIdx.x * kBlock + threadIdx.x; basei < total; basei += span * Q) {
         uint64_t q[Q][S];
         bool live[Q];
         int64_t r[Q];
-        uint32_t src[Q];
+        uint32_t seg[Q];
         uint64_t pos[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint64_t f = basei + (uint64_t)j * span;
             live[j] = f < total;
-            src[j] = 0; pos[j] = 0;
+            seg[j] = 0; pos[j] = 0;
             if (live[j]) {
-                uint32_t sgm = 0;
-                while (sgm + 1 < (uint32_t)nshards && f >= pre[sgm + 1]) ++sgm;
-                src[j] = sgm;
-                pos[j] = f - pre[sgm];
-                wire_to_key<S, KW>(inbox + ((uint64_t)sgm * cap + pos[j]) * KW, q[j]);
+                uint32_t lo = 0, hi = nseg - 1;              // segment e with pre[e] <= f < pre[e + 1]
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (pre[mid] <= f) lo = mid; else hi = mid - 1;
+                }
+                seg[j] = lo;
+                pos[j] = f - pre[lo];
+                wire_to_key<S, KW>(inbox + ((uint64_t)lo * cap + pos[j]) * KW, q[j]);
             }
         }
-        lookup_mlp<S, Q>(ix, q, live, r);          // ix.first_index is 0 here: results are local to the shard
+        lookup_mlp<S, Q>(ix, pol, q, live, r);     // ix.first_index is 0 here: results are local to the shard
 #pragma unroll
-        for (int j = 0; j < Q; ++j)
-            if (live[j]) static_cast<uint32_t *>(ret.p[src[j]])[(uint64_t)my_rank * cap + pos[j]] = r[j] < 0 ? kWireMiss : (uint32_t)r[j];
+        for (int j = 0; j < Q; ++j) {
+            if (!live[j]) continue;
+            const uint32_t vv = seg[j] / (uint32_t)world, src = seg[j] - vv * (uint32_t)world;
+            static_cast<uint32_t *>(ret.p[src])[((uint64_t)my_rank * vsub + vv) * cap + pos[j]] = r[j] < 0 ? kWireMiss : (uint32_t)r[j];
+        }
     }
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(kRouteBlock) gather_routed_kernel(const uint32_t *__restrict__ ret, RouteState rs, uint64_t nq,
-                                                                    const uint64_t *__restrict__ shard_first, int nshards, uint64_t cap,
-                                                                    int64_t *__restrict__ out) {
-    __shared__ int64_t staged[kRouteTile];
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) gather_routed_kernel(const uint32_t *__restrict__ ret, RouteState rs, uint64_t nq,
+                                                              const uint64_t *__restrict__ shard_first, int nshards, uint64_t cap,
+                                                              int64_t *__restrict__ out) {
+    constexpr uint32_t kTile = BLOCK * kRouteQ;
+    __shared__ int64_t staged[kTile];
     __shared__ uint32_t loc[kMaxShards + 1], base[kMaxShards];
     __shared__ uint64_t first[kMaxShards];
-    for (int i = threadIdx.x; i < nshards; i += kRouteBlock) first[i] = shard_first[i];
-    const uint64_t ntiles = route_tiles(nq);
+    for (int i = threadIdx.x; i < nshards; i += BLOCK) first[i] = shard_first[i];
+    const uint64_t ntiles = route_tiles(nq, kTile);
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();                                  // previous tile's staged[] fully consumed
         if (threadIdx.x < (uint32_t)nshards) base[threadIdx.x] = rs.tile_base[tile * nshards + threadIdx.x];
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 32) {                          // another warp than the base[] loaders
             uint32_t acc = 0;
             for (int i = 0; i < nshards; ++i) { loc[i] = acc; acc += rs.tile_cnt[tile * nshards + i]; }
             loc[nshards] = acc;
         }
         __syncthreads();
         const uint32_t total = loc[nshards];
-        for (uint32_t p = threadIdx.x; p < total; p += kRouteBlock) {
+        for (uint32_t p = threadIdx.x; p < total; p += BLOCK) {
             uint32_t lo = 0, hi = (uint32_t)nshards - 1;  // owner o with loc[o] <= p < loc[o+1]
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
@@ -852,7 +1016,7 @@ __global__ void __launch_bounds__(kRouteBlock) gather_routed_kernel(const uint32
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kRouteQ; ++j) {
-            const uint64_t i = tile * kRouteTile + (uint64_t)j * kRouteBlock + threadIdx.x;
+            const uint64_t i = tile * kTile + (uint64_t)j * BLOCK + threadIdx.x;
             if (i < nq) {
                 const uint32_t at = rs.at16[i];
                 out[i] = at == kNotRouted ? -1 : staged[at];
@@ -1006,8 +1170,10 @@ IndexView view_of(const cc_graph *g) {
     v.n = g->h.num_records;
     v.first_index = g->first_index;
     v.base = g->index.base;
+    v.scale = g->index.scale;
     v.nbuckets = g->index.nbuckets;
-    v.shift = g->index.shift;
+    v.norm = g->index.norm;
+    v.hints = (uint32_t)options().lookup_l2_hints;
     v.k = g->h.k;
     return v;
 }
@@ -1225,11 +1391,20 @@ int build_index(cc_graph *g, int bits_req) {
     uint64_t t0 = 0, t1 = 0;
     CC_DISPATCH_S(s, { t0 = key_top64<S_>(first, k); t1 = key_top64<S_>(last, k); });
     const uint64_t span = t1 >= t0 ? t1 - t0 : 0;      // unsorted arrays are rejected below; buckets are clamped anyway
-    uint32_t shift = 0;
-    while (shift < 63 && (span >> shift) >= (1ull << bits)) ++shift;
+    // nbuckets equal slices of [0, span]: bucket(d) = floor(d * nbuckets / (span + 1)), evaluated as a 64x64 high multiply
+    // of the normalised distance (top bit of span at bit 63) with scale = floor(2^64 * nbuckets / (span' + 1)).
+    uint64_t nb = options().index_buckets > 0 ? (uint64_t)options().index_buckets : (1ull << bits);
+    nb = std::max<uint64_t>(1, std::min<uint64_t>(nb, 1ull << 30));
+    if (span + 1 != 0 && nb > span + 1) nb = span + 1;  // no finer than the key resolution
+    uint32_t norm = 0;
+    while (norm < 63 && !((span << norm) >> 63)) ++norm;
+    if (span == 0) norm = 0;
+    const unsigned __int128 spanp1 = (unsigned __int128)(span << norm) + 1;
+    const unsigned __int128 sc = (((unsigned __int128)nb) << 64) / spanp1;
     ix.base = t0;
-    ix.shift = shift;
-    ix.nbuckets = (uint32_t)(span >> shift) + 1u;
+    ix.norm = norm;
+    ix.scale = sc > (unsigned __int128)~0ull ? ~0ull : (uint64_t)sc;
+    ix.nbuckets = (uint32_t)nb;
     CC_CUDA(cudaMalloc(&ix.table, ((uint64_t)ix.nbuckets + 2) * sizeof(uint32_t)));
 
     unsigned long long *d_unsorted = reinterpret_cast<unsigned long long *>(g->scan_ws.totals + 8);
@@ -1301,19 +1476,27 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     if (nq >= (1ull << 32) || cap >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "routed batches are limited to 2^32-1 queries per rank");
     const uint32_t s = (k + 31) / 32, kw = (2 * k + 31) / 32;
     PeerPtrs inbox{}, counts{};
-    for (int i = 0; i < nshards; ++i) { inbox.p[i] = peer_inbox[i]; counts.p[i] = peer_counts[i]; }
+    for (int i = 0; i < nshards; ++i) {
+        inbox.p[i] = peer_inbox[i]; counts.p[i] = peer_counts[i];
+        if ((reinterpret_cast<uintptr_t>(peer_inbox[i]) & 15u) || (cap & 3u))
+            return fail(CC_ERR_ARG, "inbox segments must be 16-byte aligned and cap a multiple of 4 keys");
+    }
     unsigned long long *cursors = reinterpret_cast<unsigned long long *>(dev_sent);
     CC_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * nshards, st));
     if (nq) {
         if (nq > max_q) return fail(CC_ERR_ARG, "batch of %llu queries exceeds the route state sized for %llu", (unsigned long long)nq, (unsigned long long)max_q);
         const RouteState rs = route_state_of(dev_route_state, max_q, nshards);
-        const size_t smem = (size_t)kRouteTile * kw * 4;
+        const int block = route_block_for(nshards);
+        const uint32_t tile_q = (uint32_t)block * kRouteQ, stage_words = route_stage_words(tile_q, kw, nshards);
+        const size_t smem = route_smem_bytes(tile_q, kw, nshards);
         const int per_sm = options().route_blocks_per_sm > 0 ? options().route_blocks_per_sm : 32;
-        CC_DISPATCH_SKW(s, kw, {
-            CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = resident_grid(route_kernel<S_, KW_>, kRouteBlock, smem, route_tiles(nq), sm_count_now(), per_sm);
-            route_kernel<S_, KW_><<<grid, kRouteBlock, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox, rs, cursors);
-        });
+#define CC_ROUTE(BLOCK_) CC_DISPATCH_SKW(s, kw, {                                                                                   \
+            CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, KW_, BLOCK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            const int grid = resident_grid(route_kernel<S_, KW_, BLOCK_>, BLOCK_, smem, route_tiles(nq, tile_q), sm_count_now(), per_sm); \
+            route_kernel<S_, KW_, BLOCK_><<<grid, BLOCK_, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox, rs, \
+                                                                      cursors, stage_words, k); })
+        if (block == 256) { CC_ROUTE(256); } else { CC_ROUTE(128); }
+#undef CC_ROUTE
         count_launch();
     }
     publish_counts_kernel<<<1, kMaxShards, 0, st>>>(cursors, nshards, my_rank, cap, counts);
@@ -1322,19 +1505,23 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     return CC_OK;
 }
 
-int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int nshards, int my_rank, uint64_t cap,
+int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, int my_rank, uint64_t cap,
                        void *const *peer_ret, cudaStream_t st) {
     if (int rc = check_k(g->h.k)) return rc;
-    if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
+    if (world < 1 || vsub < 1 || world * vsub > kMaxShards) return fail(CC_ERR_ARG, "world * vsub must be in 1..%d", kMaxShards);
+    if (my_rank < 0 || my_rank >= world) return fail(CC_ERR_ARG, "rank %d out of range", my_rank);
     PeerPtrs ret{};
-    for (int i = 0; i < nshards; ++i) ret.p[i] = peer_ret[i];
+    for (int i = 0; i < world; ++i) ret.p[i] = peer_ret[i];
     IndexView ix = view_of(g);
     ix.first_index = 0;                 // the wire carries indices local to the shard; the origin rebases them
+    // a sub-range that fits L2 must stay there: no evict-first on its keys
+    const uint64_t slice_bytes = g->h.num_records / (uint64_t)vsub * (8ull * g->h.s + 4ull);
+    if (vsub > 1 && slice_bytes <= (48ull << 20)) ix.hints = 0;
     const uint32_t kw = (2 * g->h.k + 31) / 32;
+    const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
     CC_DISPATCH_SKW(g->h.s, kw, {
-        const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
         find_routed_kernel<S_, KW_, 2><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t *>(dev_inbox),
-                                                                 reinterpret_cast<const unsigned long long *>(dev_counts_in), nshards, my_rank, cap, ix, ret);
+                                                                 reinterpret_cast<const unsigned long long *>(dev_counts_in), world, vsub, my_rank, cap, ix, ret);
     });
     count_launch();
     CC_CUDA(cudaGetLastError());
@@ -1346,8 +1533,14 @@ int launch_gather_routed(const void *dev_ret, const void *dev_route_state, uint6
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
     if (nq == 0) return CC_OK;
     const RouteState rs = route_state_of(const_cast<void *>(dev_route_state), max_q, nshards);
-    const int grid = resident_grid(gather_routed_kernel, kRouteBlock, 0, route_tiles(nq), sm_count_now(), std::max(1, options().gather_blocks_per_sm));
-    gather_routed_kernel<<<grid, kRouteBlock, 0, st>>>(static_cast<const uint32_t *>(dev_ret), rs, nq, dev_shard_first, nshards, cap, dev_out);
+    const int cap_sm = std::max(1, options().gather_blocks_per_sm);
+    if (route_block_for(nshards) == 256) {
+        const int grid = resident_grid(gather_routed_kernel<256>, 256, 0, route_tiles(nq, 256 * kRouteQ), sm_count_now(), cap_sm);
+        gather_routed_kernel<256><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(dev_ret), rs, nq, dev_shard_first, nshards, cap, dev_out);
+    } else {
+        const int grid = resident_grid(gather_routed_kernel<128>, 128, 0, route_tiles(nq, 128 * kRouteQ), sm_count_now(), cap_sm);
+        gather_routed_kernel<128><<<grid, 128, 0, st>>>(static_cast<const uint32_t *>(dev_ret), rs, nq, dev_shard_first, nshards, cap, dev_out);
+    }
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;

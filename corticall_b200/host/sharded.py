@@ -128,18 +128,23 @@ class RoutedLookup:
     """
 
     def __init__(self, graph, splitters, rank: int, world: int, device, cap: int, k: int, shard_first=None, group=None, emulate=None,
-                 max_batch: int | None = None):
+                 max_batch: int | None = None, vsub: int = 1):
         """cap: keys one (source, owner) segment can hold.  max_batch: largest batch of this rank (default cap).  With
         max_batch <= cap (the default) a segment cannot overflow; with max_batch > cap (balanced key ranges, memory-saving)
-        find_packed() checks the sent counts after the batch and raises if a segment overflowed."""
+        find_packed() checks the sent counts after the batch and raises if a segment overflowed.
+        vsub: virtual shards per rank (see corticall_cuda.h): splitters then holds world * vsub - 1 keys (first key of every
+        sub-range but the first; `virtual_splitters` builds them) and the search walks L2-sized sub-ranges."""
         import ctypes as C
-        self.g, self.rank, self.world, self.cap, self.k = graph, rank, world, int(cap), int(k)
+        self.g, self.rank, self.world, self.cap, self.k = graph, rank, world, self.round_cap(cap), int(k)
+        self.vsub = int(vsub)
+        self.nv = world * self.vsub
         self.max_batch = int(max_batch) if max_batch is not None else int(cap)
         self.kw = (2 * self.k + 31) // 32
         self.device = device
         self.index = device.index if device.index is not None else torch.cuda.current_device()
         self.splitters = splitters.contiguous() if splitters is not None else None
-        if shard_first is None:                 # first global record index of every shard
+        assert (self.splitters.shape[0] if self.splitters is not None else 0) == self.nv - 1, "need world * vsub - 1 splitters"
+        if shard_first is None:                 # first global record index of every rank's shard
             mine = torch.tensor([int(graph.firstIndex)], dtype=torch.int64, device=device)
             if world > 1:
                 parts = [torch.empty_like(mine) for _ in range(world)]
@@ -147,17 +152,14 @@ class RoutedLookup:
                 shard_first = torch.cat(parts)
             else:
                 shard_first = mine
-        self.shard_first = torch.as_tensor(shard_first, dtype=torch.int64).to(device).contiguous()
-        assert self.shard_first.numel() == world
+        shard_first = torch.as_tensor(shard_first, dtype=torch.int64).to(device)
+        assert shard_first.numel() == world
+        self.shard_first = shard_first.repeat_interleave(self.vsub).contiguous()      # per virtual owner
         # layout of the symmetric block, in bytes (every part 16-byte aligned)
-        al = lambda x: (x + 15) & ~15
-        self.off_inbox = 0
-        self.off_ret = al(world * self.cap * self.kw * 4)
-        self.off_counts = self.off_ret + al(world * self.cap * 4)
-        total = self.block_elems(world, self.cap, self.k)
+        self.off_inbox, self.off_ret, self.off_counts, total = self._layout(world, self.vsub, self.cap, self.kw)
         if emulate is None:
             import torch.distributed._symmetric_memory as symm
-            self.block = symm.empty(total, dtype=torch.int64, device=device)
+            self.block = symm.empty(total // 8, dtype=torch.int64, device=device)
             self.hdl = symm.rendezvous(self.block, (group or dist.group.WORLD).group_name)
             bases = [int(p) for p in self.hdl.buffer_ptrs]
         else:                                   # single-process emulation of all ranks on one device (tests)
@@ -165,22 +167,59 @@ class RoutedLookup:
             self.hdl = None
             bases = [int(t.data_ptr()) for t in emulate]
         self.block.zero_()
-        arr = C.c_void_p * world
-        self.p_inbox = arr(*[b + self.off_inbox for b in bases])
-        self.p_ret = arr(*[b + self.off_ret for b in bases])
-        self.p_counts = arr(*[b + self.off_counts for b in bases])
+        seg_inbox = world * self.cap * self.kw * 4          # one sub-range's [world][cap][kw] block
+        self.p_inbox = (C.c_void_p * self.nv)(*[bases[v // self.vsub] + self.off_inbox + (v % self.vsub) * seg_inbox for v in range(self.nv)])
+        self.p_counts = (C.c_void_p * self.nv)(*[bases[v // self.vsub] + self.off_counts + (v % self.vsub) * world * 8 for v in range(self.nv)])
+        self.p_ret = (C.c_void_p * world)(*[b + self.off_ret for b in bases])
         nbytes = C.c_uint64(0)
-        N.check(N.lib().cc_route_state_bytes(self.max_batch, world, C.byref(nbytes)))
+        N.check(N.lib().cc_route_state_bytes(self.max_batch, self.nv, C.byref(nbytes)))
         self.state = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
-        self.sent = torch.zeros(max(world, 8), dtype=torch.int64, device=device)
+        self.sent = torch.zeros(max(self.nv, 8), dtype=torch.int64, device=device)
         self.nq = 0
 
     @staticmethod
-    def block_elems(world: int, cap: int, k: int) -> int:
-        """int64 elements of one rank's symmetric block."""
-        kw = (2 * k + 31) // 32
+    def round_cap(cap: int) -> int:
+        """Segment capacities are multiples of 4 keys so that every segment starts 16-byte aligned."""
+        return (int(cap) + 3) & ~3
+
+    @staticmethod
+    def _layout(world, vsub, cap, kw):
         al = lambda x: (x + 15) & ~15
-        return (al(world * cap * kw * 4) + al(world * cap * 4) + 8 * max(world, 8)) // 8
+        off_inbox = 0
+        off_ret = al(vsub * world * cap * kw * 4)
+        off_counts = off_ret + al(world * vsub * cap * 4)
+        total = off_counts + 8 * max(world * vsub, 8)
+        return off_inbox, off_ret, off_counts, (total + 7) & ~7
+
+    @staticmethod
+    def virtual_splitters(graph, rank: int, world: int, vsub: int, device, group=None, emulate_graphs=None):
+        """[world * vsub - 1, s] int64: the first key of every sub-range except the very first.  Sub-range j of a rank's
+        shard starts at local record n * j // vsub.  An empty shard contributes the largest key (nothing routes to it)."""
+        def local(g):
+            n, s = g.getNumRecords(), g.getKmerBits()
+            rows = []
+            for j in range(vsub):
+                if n == 0:
+                    rows.append(np.full(s, np.iinfo(np.int64).max, dtype=np.int64))
+                else:
+                    w, _, _ = g.decodeRecords(n * j // vsub, 1)
+                    rows.append(w[0].view(np.int64).copy())
+            return torch.from_numpy(np.stack(rows)).to(device)
+        if emulate_graphs is not None:
+            allk = torch.cat([local(g) for g in emulate_graphs])
+        elif world > 1:
+            mine = local(graph)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            allk = torch.cat(parts)
+        else:
+            allk = local(graph)
+        return allk[1:].contiguous() if allk.shape[0] > 1 else None
+
+    @staticmethod
+    def block_elems(world: int, cap: int, k: int, vsub: int = 1) -> int:
+        """int64 elements of one rank's symmetric block."""
+        return RoutedLookup._layout(world, vsub, RoutedLookup.round_cap(cap), (2 * k + 31) // 32)[3] // 8
 
     def _barrier(self):
         if self.hdl is not None:
@@ -193,19 +232,19 @@ class RoutedLookup:
         self.nq = words.shape[0]
         N.check(N.lib().cc_route_queries_dev(self.index, words.data_ptr(), flags.data_ptr() if flags is not None else None,
                                              self.nq, self.k, self.splitters.data_ptr() if self.splitters is not None else None,
-                                             self.world, self.rank, self.cap, self.p_inbox, self.p_counts,
+                                             self.nv, self.rank, self.cap, self.p_inbox, self.p_counts,
                                              self.state.data_ptr(), self.max_batch, self.sent.data_ptr(), st))
 
     def search(self):
         st = torch.cuda.current_stream().cuda_stream
         base = self.block.data_ptr()
-        N.check(N.lib().cc_find_routed_dev(self.g._h, base + self.off_inbox, base + self.off_counts, self.world, self.rank,
+        N.check(N.lib().cc_find_routed_dev(self.g._h, base + self.off_inbox, base + self.off_counts, self.world, self.vsub, self.rank,
                                            self.cap, self.p_ret, st))
 
     def gather(self, out):
         st = torch.cuda.current_stream().cuda_stream
         N.check(N.lib().cc_gather_routed_dev(self.index, self.block.data_ptr() + self.off_ret, self.state.data_ptr(), self.max_batch, self.nq,
-                                             self.shard_first.data_ptr(), self.world, self.cap, out.data_ptr(), st))
+                                             self.shard_first.data_ptr(), self.nv, self.cap, out.data_ptr(), st))
 
     def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor, profile: bool = False) -> torch.Tensor:
         marks = []
@@ -236,7 +275,7 @@ class RoutedLookup:
 
     def check_overflow(self):
         """Only needed when max_batch > cap: a segment that received more than cap keys dropped the rest."""
-        worst = int(self.sent[:self.world].max().item())
+        worst = int(self.sent[:self.nv].max().item())
         if worst > self.cap:
             raise OverflowError("a routed segment overflowed: %d keys for one owner, capacity %d" % (worst, self.cap))
 
@@ -247,8 +286,8 @@ class PipelinedRoutedLookup:
     Two RoutedLookup buffer sets (parity = sub-batch & 1) and two streams: X carries route_i and gather_i, Y carries
     search_i.  Order on X: R0 R1 G0 R2 G1 R3 G2 ... ; on Y: S0 S1 S2 ...  Cross-rank barriers follow R_i (on X) and S_i
     (on Y), so every rank issues the same sequence per stream and a buffer set is never overwritten while a peer still
-    reads it.  The route / gather kernels are launched as one 128-thread block per SM on a high-priority
-    stream, so they fit beside the three resident blocks of the (latency-bound, full-occupancy) search kernel.
+    reads it.  The route / gather kernels run as one persistent CTA per SM on a high-priority
+    stream beside two persistent search CTAs per SM.
     """
 
     def __init__(self, graph, splitters, rank: int, world: int, device, sub_batch: int, k: int, shard_first=None, group=None):
@@ -257,6 +296,7 @@ class PipelinedRoutedLookup:
         self.sx = torch.cuda.Stream(device=device, priority=-1)     # NVLink legs first: they are short and hide behind the search
         self.sy = torch.cuda.Stream(device=device)
         self.world = world
+        self.route_per_sm, self.gather_per_sm, self.search_per_sm = 1, 1, 2
 
     def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
         nq = words.shape[0]
@@ -273,8 +313,11 @@ class PipelinedRoutedLookup:
         self.sy.wait_stream(cur)
         routed = [torch.cuda.Event() for _ in range(nsub)]
         searched = [torch.cuda.Event() for _ in range(nsub)]
-        N.set_option("route_blocks_per_sm", 1)          # 128-thread blocks: one fits beside three resident search blocks
-        N.set_option("gather_blocks_per_sm", 1)
+        # one route / gather CTA per SM beside two (instead of three) resident search CTAs: all three kernels are
+        # persistent, so they are co-resident by construction (registers: 2 x 78 x 256 + 72 x 256 < 64 K)
+        N.set_option("route_blocks_per_sm", self.route_per_sm)
+        N.set_option("gather_blocks_per_sm", self.gather_per_sm)
+        N.set_option("routed_search_blocks_per_sm", self.search_per_sm)
 
         def part(i):
             lo, hi = min(i * self.sub, nq), min((i + 1) * self.sub, nq)
@@ -309,7 +352,8 @@ class PipelinedRoutedLookup:
             gather(nsub - 1)
         finally:
             N.set_option("route_blocks_per_sm", 0)
-            N.set_option("gather_blocks_per_sm", 8)
+            N.set_option("gather_blocks_per_sm", 16)
+            N.set_option("routed_search_blocks_per_sm", 3)
         cur.wait_stream(self.sx)
         cur.wait_stream(self.sy)
         return out

@@ -421,8 +421,9 @@ def test_findrois_command_and_call_helpers(tmp_path):
     graph.dispose(); rois.dispose()
 
 
-@pytest.mark.parametrize("world,k", [(1, 47), (2, 47), (4, 47), (8, 47), (3, 16), (3, 31), (2, 63), (3, 65), (5, 96)])
-def test_routed_lookup_emulated_ranks(world, k):
+@pytest.mark.parametrize("world,k,vsub", [(1, 47, 1), (2, 47, 1), (4, 47, 1), (8, 47, 1), (3, 16, 1), (3, 31, 1), (2, 63, 1), (3, 65, 1), (5, 96, 1),
+                                          (1, 47, 64), (2, 47, 32), (8, 47, 8), (3, 31, 5), (4, 65, 16)])
+def test_routed_lookup_emulated_ranks(world, k, vsub):
     """The peer-memory lookup path (route -> search -> gather) with all ranks emulated on one device: plain device
     tensors stand in for the symmetric allocations (every 'peer pointer' is a local pointer) and the legs of all ranks
     run one after another on one stream, which is exactly the ordering the cross-rank barriers enforce."""
@@ -436,17 +437,21 @@ def test_routed_lookup_emulated_ranks(world, k):
     body = torch.from_numpy(whole.getRawRecords(0, n)).cuda()
     table = [torch.from_numpy(words_all[:, w].copy().view(np.int64)) for w in range(nw)]
     dev = torch.device("cuda", 0)
-    spl = torch.stack([torch.stack([t[n * r // world] for t in table]) for r in range(1, world)]).cuda() if world > 1 else None
     nq_per = [5000 + 700 * r for r in range(world)]
     cap = max(nq_per)
-    blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, k), dtype=torch.int64, device=dev) for _ in range(world)]
+    blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, k, vsub), dtype=torch.int64, device=dev) for _ in range(world)]
     first = [n * r // world for r in range(world)]
     shards, rls, qs = [], [], []
     for r in range(world):
         lo, hi = n * r // world, n * (r + 1) // world
-        g = cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body)
-        shards.append(g)
-        rls.append(RoutedLookup(g, spl, r, world, dev, cap, k, shard_first=first, emulate=blocks))
+        shards.append(cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), k, c, hi - lo, firstIndex=lo, keepalive=body))
+    # splitters: first key of every (virtual) shard but the first; with vsub = 1 these are the rank boundaries
+    spl = RoutedLookup.virtual_splitters(None, 0, world, vsub, dev, emulate_graphs=shards)
+    if vsub == 1 and world > 1:
+        assert torch.equal(spl.cpu(), torch.stack([torch.stack([t[n * r // world] for t in table]) for r in range(1, world)]))
+    for r in range(world):
+        g = shards[r]
+        rls.append(RoutedLookup(g, spl, r, world, dev, cap, k, shard_first=first, emulate=blocks, vsub=vsub))
         a, canon, valid = synth.make_queries(200 + r, table, k, nq_per[r], corrupt_permille=25)
         qs.append((a, torch.stack(canon, dim=1).contiguous().cuda(), torch.where(valid, 0, 2).to(torch.uint8).cuda(),
                    torch.full((nq_per[r],), -7, dtype=torch.int64, device=dev)))
@@ -460,7 +465,7 @@ def test_routed_lookup_emulated_ranks(world, k):
     for r in range(world):
         want = og.find_batch(qs[r][0].numpy())
         assert (qs[r][3].cpu().numpy() == want).all(), r
-        assert int(rls[r].sent[:world].sum()) == int((qs[r][2] == 0).sum())
+        assert int(rls[r].sent[:world * vsub].sum()) == int((qs[r][2] == 0).sum())
     # a second batch through the same buffers (stale segment contents must not leak)
     for r in range(world):
         rls[r].route(qs[r][1][:100], qs[r][2][:100])

@@ -17,6 +17,7 @@ st = torch.cuda.current_stream().cuda_stream
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 nt = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000_000
 nq = int(float(sys.argv[3])) if len(sys.argv) > 3 else 125_000_000
+vsub = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 K, C = 47, 4
 dev = torch.device("cuda", 0)
 
@@ -78,30 +79,26 @@ ms = timeit(lambda: N.check(L.cc_find_packed_dev(whole._h, qw1.data_ptr(), qf1.d
 print("find packed whole table   q=%.2e  %.3f ms  %.3g lookups/s" % (na, ms, na / ms * 1e3), flush=True)
 assert torch.equal(r1, res[:na]), "ascii and packed lookups disagree"
 if os.environ.get("LEGS_SWEEP") == "1":
-    for per in (0, 4, 8, 16):
-        N.set_option("mlp_grid_per_sm", per)
+    for hints in (0, 1, 2, 3):
+        N.set_option("lookup_l2_hints", hints)
         ms = timeit(lambda: N.check(L.cc_find_packed_dev(whole._h, qw1.data_ptr(), qf1.data_ptr(), na, res.data_ptr(), 0, st)))
-        print("   find packed, grid/SM %2d: %.3f ms  %.3g lookups/s" % (per, ms, na / ms * 1e3), flush=True)
-    N.set_option("mlp_grid_per_sm", 8)
-    for mk in (32, 64):
-        N.set_option("rows_rpt2_max_k", mk)
-        ms = timeit(lambda: N.check(L.cc_pack_kmers_dev(0, a.data_ptr(), na, K, pw.data_ptr(), pf.data_ptr(), st)))
-        print("   pack rows, two rows per thread up to k=%d: %.3f ms  %.3g rows/s" % (mk, ms, na / ms * 1e3), flush=True)
-    N.set_option("rows_rpt2_max_k", 32)
+        ms2 = timeit(lambda: N.check(L.cc_find_ascii_dev(whole._h, a.data_ptr(), na, res.data_ptr(), 0, st)))
+        print("   whole table, L2 hints %d: packed %.3f ms  %.3g lookups/s; ascii %.3f ms  %.3g lookups/s" % (hints, ms, na / ms * 1e3, ms2, na / ms2 * 1e3), flush=True)
+    N.set_option("lookup_l2_hints", 3)
 del a, canon, valid, pw, pf, want_w, qw1, qf1, r1
 
 # ---- shards + routed legs, all ranks on this device
 first = [nt * r // world for r in range(world)]
-splitters = torch.stack([torch.stack([w[first[r]] for w in words]) for r in range(1, world)]) if world > 1 else None
 shards = []
 for r in range(world):
     lo, hi = first[r], nt * (r + 1) // world
     g = cb.CortexGraph.fromDevice(body[lo:hi].data_ptr(), K, C, hi - lo, firstIndex=lo, keepalive=body)
     g.buildIndex()
     shards.append(g)
-cap = int(nq / world * 1.1) + 4096 if world > 1 else nq
-blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, K), dtype=torch.int64, device=dev) for _ in range(world)]
-rls = [RoutedLookup(shards[r], splitters, r, world, dev, cap, K, shard_first=first, emulate=blocks, max_batch=nq) for r in range(world)]
+splitters = RoutedLookup.virtual_splitters(None, 0, world, vsub, dev, emulate_graphs=shards)
+cap = int(nq / (world * vsub) * 1.15) + 4096 if world * vsub > 1 else nq
+blocks = [torch.zeros(RoutedLookup.block_elems(world, cap, K, vsub), dtype=torch.int64, device=dev) for _ in range(world)]
+rls = [RoutedLookup(shards[r], splitters, r, world, dev, cap, K, shard_first=first, emulate=blocks, max_batch=nq, vsub=vsub) for r in range(world)]
 qs = []
 chunk = 1 << 24
 for r in range(world):
@@ -121,7 +118,7 @@ for r in range(1, world):
 ms_s = timeit(lambda: rls[0].search(), prof=True)
 out = res[:nq]
 ms_g = timeit(lambda: rls[0].gather(out), prof=True)
-print("routed legs of one rank, world=%d, %d queries per rank, table %.1e (shard %.2e records):" % (world, nq, nt, nt / world))
+print("routed legs of one rank, world=%d, vsub=%d, %d queries per rank, table %.1e (shard %.2e records):" % (world, vsub, nq, nt, nt / world))
 print("   route  %.3f ms  (%.3g q/s)\n   search %.3f ms  (%.3g q/s)\n   gather %.3f ms  (%.3g q/s)" % (
     ms_r, nq / ms_r * 1e3, ms_s, nq / ms_s * 1e3, ms_g, nq / ms_g * 1e3), flush=True)
 print("   sum %.3f ms -> %.3g lookups/s per rank, x%d ranks = %.3g (no NVLink time)" % (
@@ -136,8 +133,13 @@ for rl in rls:
     rl.check_overflow()
 print("routed == whole-table lookup: ok")
 if os.environ.get("LEGS_SWEEP") == "1":
-    for per in (3, 4, 8, 16):
-        N.set_option("routed_search_blocks_per_sm", per)
-        ms_s = timeit(lambda: rls[0].search())
-        print("   shard search, grid/SM %2d: %.3f ms (%.3g q/s)" % (per, ms_s, nq / ms_s * 1e3), flush=True)
-    N.set_option("routed_search_blocks_per_sm", 8)
+    for hints in (0, 1, 2, 3):
+        N.set_option("lookup_l2_hints", hints)
+        for nb in (8_388_608, 12_500_000, 16_777_216, 25_000_000):
+            N.set_option("index_buckets", nb)
+            shards[0].buildIndex()
+            ms_s = timeit(lambda: rls[0].search())
+            print("   shard 0 search, L2 hints %d, %.3g buckets (%.2f keys/bucket, table %.0f MB): %.3f ms (%.3g q/s)" % (
+                hints, nb, nt / world / nb, nb * 4 / 1e6, ms_s, nq / ms_s * 1e3), flush=True)
+    N.set_option("index_buckets", 0)
+    N.set_option("lookup_l2_hints", 3)
