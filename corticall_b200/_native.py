@@ -84,6 +84,10 @@ SIGNATURES = {
     "cc_join": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "cc_sort": (C.c_int, [_P, C.POINTER(_P)]),
     "cc_write_graph": (C.c_int, [_P, C.c_char_p]),
+    "cc_find_low_coverage": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "cc_find_shared": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int, _P, C.c_int, C.POINTER(_P)]),
+    "cc_recover_excluded_kmers": (C.c_int, [_P, _P, C.c_int32, C.POINTER(_P), _U64P]),
+    "cc_cov_stats": (C.c_int, [_P, C.c_int32, _P, C.c_int, _P, _P, C.c_uint64, _U64P]),
     "cc_last_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "cc_launch_count": (C.c_uint64, []),
     "cc_device_body": (C.c_int, [_P, C.POINTER(_P), _U64P]),

@@ -1063,6 +1063,203 @@ int cc_sort(cc_graph *g_in, cc_graph **out) {
     return CC_OK;
 }
 
+// ==================================================================== next rows: scan-shaped pre-filters
+namespace {
+
+// A new device-resident graph made of the records of `src` listed in `sel`, projected to the first c_out colours.
+int make_selected_graph(cc_graph *src, const Header &hdr, uint32_t c_out, const uint32_t *sel, uint64_t m, const uint8_t *flags,
+                        const int32_t *patch, uint32_t patch_color, cudaStream_t st, cc_graph **out) {
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> g(new cc_graph(), destroy);
+    g->path = "<filter>";
+    g->h = hdr;
+    g->h.data_offset = 0;
+    g->h.c = c_out;
+    g->h.record_size = 8ull * hdr.s + 5ull * c_out;
+    g->h.num_records = m;
+    if (int rc = init_handle(g.get(), src->device)) return rc;
+    void *body = nullptr;
+    CC_CUDA(cudaMalloc(&body, m * g->h.record_size + 256));
+    g->dev_alloc = body;
+    g->dev_body = static_cast<const uint8_t *>(body);
+    if (int rc = launch_project_records(src->dev_body, src->h.s, src->h.c, sel, m, c_out, flags, patch, patch_color,
+                                        static_cast<uint8_t *>(body), src->sm_count, st)) return rc;
+    CC_CUDA(cudaMemsetAsync(static_cast<uint8_t *>(body) + m * g->h.record_size, 0, 256, st));
+    CC_CUDA(cudaStreamSynchronize(st));
+    *out = g.release();
+    return CC_OK;
+}
+
+struct StreamBuf {                      // stream-ordered scratch, freed on scope exit
+    cudaStream_t st;
+    std::vector<void *> p;
+    explicit StreamBuf(cudaStream_t s) : st(s) {}
+    ~StreamBuf() { for (void *q : p) cudaFreeAsync(q, st); }
+    int alloc_bytes(void **out, uint64_t bytes) {
+        void *q = nullptr;
+        CC_CUDA(cudaMallocAsync(&q, bytes + 64, st));
+        p.push_back(q);
+        *out = q;
+        return CC_OK;
+    }
+};
+
+// Bit mask over the colours of g from a list that may hold -1 / out-of-range entries (a sample name that did not resolve:
+// the reference's HashSet<Integer> then simply never matches, FindShared.java:45-46, CovStats.java:78-86).
+std::vector<uint32_t> color_mask(const cc_graph *g, const int32_t *list, int n) {
+    std::vector<uint32_t> m((g->h.c + 31) / 32 + 1, 0u);
+    for (int i = 0; i < n; ++i)
+        if (list[i] >= 0 && (uint32_t)list[i] < g->h.c) m[list[i] >> 5] |= 1u << (list[i] & 31);
+    return m;
+}
+
+#define CC_SB_ALLOC(sb, ptr, count) (sb).alloc_bytes(reinterpret_cast<void **>(&(ptr)), (uint64_t)(count) * sizeof(*(ptr)))
+
+}  // namespace
+
+// FindLowCoverage (S/commands/prefilter/FindLowCoverage.java:33-66): the records whose coverage(0) is below the limit, under the
+// input's header.
+int cc_find_low_coverage(cc_graph *roi, int32_t min_coverage, cc_graph **out) {
+    if (!roi || !out) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (roi->h.c == 0) return fail(CC_ERR_ARG, "graph has no colours");
+    DeviceGuard guard(roi->device);
+    cudaStream_t st = roi->stream;
+    const uint64_t n = roi->h.num_records;
+    StreamBuf sb(st);
+    int32_t *cov = nullptr; uint8_t *flags = nullptr;
+    if (int rc = CC_SB_ALLOC(sb, cov, n * roi->h.c)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, flags, n)) return rc;
+    if (int rc = roi->scan_ws.ensure(0, 0)) return rc;
+    if (int rc = launch_decode_columns(roi->dev_body, n, roi->h.s, roi->h.c, nullptr, cov, nullptr, roi->scan_ws, roi->sm_count, st)) return rc;
+    if (int rc = launch_lowcov_flags(cov, n, roi->h.c, min_coverage, flags, roi->sm_count, st)) return rc;
+    uint32_t *sel = nullptr; uint64_t m = 0;
+    if (int rc = select_flagged(flags, n, &sel, &m, st)) return rc;
+    sb.p.push_back(sel);
+    return make_selected_graph(roi, roi->h, roi->h.c, sel, m, nullptr, nullptr, 0, st, out);
+}
+
+// FindShared (S/commands/prefilter/FindShared.java:40-118): the ROI records whose k-mer, looked up in the pedigree graph, has
+// coverage in a colour that is neither the child, a parent nor ignored.
+int cc_find_shared(cc_graph *graph, cc_graph *roi, int32_t child, const int32_t *parents, int nparents, const int32_t *ignore, int nignore,
+                   cc_graph **out) {
+    if (!graph || !roi || !out || (nparents > 0 && !parents) || (nignore > 0 && !ignore) || nparents < 0 || nignore < 0)
+        return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (graph->device != roi->device) return fail(CC_ERR_ARG, "graph and ROI must live on one device");
+    if (graph->h.k != roi->h.k) return fail(CC_ERR_ARG, "Graph kmer sizes are not equal.  Expected k=%u, but found k=%u", graph->h.k, roi->h.k);
+    DeviceGuard guard(graph->device);
+    if (int rc = ensure_index(graph)) return rc;
+    cudaStream_t st = graph->stream;
+    const uint64_t n = roi->h.num_records;
+    StreamBuf sb(st);
+    uint64_t *words = nullptr; int64_t *idx = nullptr; uint8_t *flags = nullptr; uint32_t *dmask = nullptr; unsigned long long *missing = nullptr;
+    if (int rc = CC_SB_ALLOC(sb, words, n * roi->h.s)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, idx, n)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, flags, n)) return rc;
+    std::vector<uint32_t> mask = color_mask(graph, parents, nparents);
+    for (int i = 0; i < nignore; ++i)
+        if (ignore[i] >= 0 && (uint32_t)ignore[i] < graph->h.c) mask[ignore[i] >> 5] |= 1u << (ignore[i] & 31);
+    if (child >= 0 && (uint32_t)child < graph->h.c) mask[child >> 5] |= 1u << (child & 31);
+    if (int rc = CC_SB_ALLOC(sb, dmask, mask.size())) return rc;
+    if (int rc = CC_SB_ALLOC(sb, missing, 1)) return rc;
+    const unsigned long long none = ~0ull;
+    CC_CUDA(cudaMemcpyAsync(dmask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, st));
+    CC_CUDA(cudaMemcpyAsync(missing, &none, 8, cudaMemcpyHostToDevice, st));
+    if (int rc = roi->scan_ws.ensure(0, 0)) return rc;
+    if (int rc = launch_decode_columns(roi->dev_body, n, roi->h.s, roi->h.c, words, nullptr, nullptr, roi->scan_ws, roi->sm_count, st)) return rc;
+    if (int rc = launch_find_packed(graph, words, nullptr, n, idx, CC_ALGO_AUTO, st)) return rc;      // records hold canonical k-mers
+    if (int rc = launch_shared_flags(idx, graph->dev_body, (uint32_t)graph->h.record_size, graph->h.s, graph->h.c, graph->first_index, dmask, n,
+                                     flags, missing, graph->sm_count, st)) return rc;
+    unsigned long long at = none;
+    CC_CUDA(cudaMemcpyAsync(&at, missing, 8, cudaMemcpyDeviceToHost, st));
+    CC_CUDA(cudaStreamSynchronize(st));
+    if (at != none)
+        return fail(CC_ERR_ARG, "ROI record %llu is not in the graph (java.lang.NullPointerException at FindShared.java:69 in the reference)", at);
+    uint32_t *sel = nullptr; uint64_t m = 0;
+    if (int rc = select_flagged(flags, n, &sel, &m, st)) return rc;
+    sb.p.push_back(sel);
+    return make_selected_graph(roi, roi->h, roi->h.c, sel, m, nullptr, nullptr, 0, st, out);
+}
+
+// RecoverExcludedKmers (S/commands/discover/recover/RecoverExcludedKmers.java:31-106).  The output header has ONE colour (the
+// child's metadata, makeHeader :98-106) and CortexGraphWriter.addRecord writes header.getNumColors() colours of each record:
+// the k-mer, coverage[0] and edges[0] of the pedigree record -- colour 0, whichever colour the child is.  The recovered
+// coverage lands in coverage[child], so it is visible in the output only when the child is colour 0.  Reproduced as is.
+int cc_recover_excluded_kmers(cc_graph *graph, cc_graph *dirty, int32_t child, cc_graph **out, uint64_t *out_recovered) {
+    if (!graph || !dirty || !out) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (graph->device != dirty->device) return fail(CC_ERR_ARG, "graphs must live on one device");
+    if (graph->h.k != dirty->h.k) return fail(CC_ERR_ARG, "Graph kmer sizes are not equal.  Expected k=%u, but found k=%u", graph->h.k, dirty->h.k);
+    if (child < 0 || (uint32_t)child >= graph->h.c) return fail(CC_ERR_ARG, "Sample not found in pedigree graph (colour %d)", child);
+    if (dirty->h.c == 0) return fail(CC_ERR_ARG, "dirty graph has no colours");
+    DeviceGuard guard(graph->device);
+    if (int rc = ensure_index(dirty)) return rc;
+    cudaStream_t st = graph->stream;
+    const uint64_t n = graph->h.num_records;
+    const uint32_t c = graph->h.c, s = graph->h.s;
+    StreamBuf sb(st);
+    uint64_t *words = nullptr; int32_t *cov = nullptr, *patch = nullptr; int64_t *idx = nullptr;
+    uint8_t *cls = nullptr, *fflags = nullptr, *flags = nullptr; unsigned long long *recovered = nullptr;
+    if (int rc = CC_SB_ALLOC(sb, words, n * s)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, cov, n * c)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, patch, n)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, idx, n)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, cls, n)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, fflags, n)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, flags, n)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, recovered, 1)) return rc;
+    CC_CUDA(cudaMemsetAsync(recovered, 0, 8, st));
+    if (int rc = graph->scan_ws.ensure(0, 0)) return rc;
+    if (int rc = launch_decode_columns(graph->dev_body, n, s, c, words, cov, nullptr, graph->scan_ws, graph->sm_count, st)) return rc;
+    if (int rc = launch_recover_classes(cov, n, c, (uint32_t)child, cls, fflags, graph->sm_count, st)) return rc;
+    if (int rc = launch_find_packed(dirty, words, fflags, n, idx, CC_ALGO_AUTO, st)) return rc;
+    if (int rc = launch_recover_finalize(cls, idx, dirty->dev_body, (uint32_t)dirty->h.record_size, dirty->h.s, dirty->first_index, n, flags, patch,
+                                         recovered, graph->sm_count, st)) return rc;
+    uint32_t *sel = nullptr; uint64_t m = 0;
+    if (int rc = select_flagged(flags, n, &sel, &m, st)) return rc;
+    sb.p.push_back(sel);
+    if (out_recovered) {
+        unsigned long long r = 0;
+        CC_CUDA(cudaMemcpyAsync(&r, recovered, 8, cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaStreamSynchronize(st));
+        *out_recovered = r;
+    }
+    Header hdr = graph->h;
+    hdr.colors.clear();
+    hdr.colors.push_back(graph->h.colors.at((size_t)child));
+    return make_selected_graph(graph, hdr, 1, sel, m, flags, patch, (uint32_t)child, st, out);
+}
+
+// CovStats (S/commands/utils/CovStats.java:33-72): child coverage -> sum over the records (present in the child, in a parent and in
+// another sample) of numberOfParents + numberOfChildren, ascending coverage.  Counts are Java ints (they wrap).
+int cc_cov_stats(cc_graph *g, int32_t child, const int32_t *parents, int nparents, int32_t *out_cov, int32_t *out_count, uint64_t cap,
+                 uint64_t *out_n) {
+    if (!g || !out_n || (nparents > 0 && !parents) || nparents < 0 || (cap && (!out_cov || !out_count))) return fail(CC_ERR_ARG, "null argument");
+    *out_n = 0;
+    // getCoverage(childColor) with childColor = -1 / out of range is an ArrayIndexOutOfBoundsException (CovStats.java:49)
+    if (child < 0 || (uint32_t)child >= g->h.c) return fail(CC_ERR_ARG, "child colour %d out of range (graph has %u colours)", child, g->h.c);
+    DeviceGuard guard(g->device);
+    cudaStream_t st = g->stream;
+    const uint64_t n = g->h.num_records;
+    StreamBuf sb(st);
+    int32_t *cov = nullptr; uint32_t *dmask = nullptr;
+    if (int rc = CC_SB_ALLOC(sb, cov, n * g->h.c)) return rc;
+    std::vector<uint32_t> mask = color_mask(g, parents, nparents);
+    if (int rc = CC_SB_ALLOC(sb, dmask, mask.size())) return rc;
+    CC_CUDA(cudaMemcpyAsync(dmask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = g->scan_ws.ensure(0, 0)) return rc;
+    if (int rc = launch_decode_columns(g->dev_body, n, g->h.s, g->h.c, nullptr, cov, nullptr, g->scan_ws, g->sm_count, st)) return rc;
+    std::vector<int32_t> hc;
+    std::vector<long long> hn;
+    if (int rc = cov_stats(cov, n, g->h.c, child, dmask, g->sm_count, st, hc, hn)) return rc;
+    *out_n = hc.size();
+    for (uint64_t i = 0; i < hc.size() && i < cap; ++i) {
+        out_cov[i] = hc[i];
+        out_count[i] = (int32_t)(uint32_t)(unsigned long long)hn[i];      // Java int arithmetic
+    }
+    return CC_OK;
+}
+
 // CortexGraphWriter.initialize :31-104 + one write of the whole body.  total_sequence is emitted the way the reference
 // does after ITS round trip: it reads the field big-endian (BinaryFile.readUnsignedLong :34-38) and writes it
 // little-endian (:60-63), i.e. byte-reversed with respect to the input file.

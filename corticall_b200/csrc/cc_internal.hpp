@@ -166,6 +166,19 @@ int join_pair(const uint8_t *body_a, const uint64_t *keys_a, uint64_t na, uint32
               uint64_t nb, uint32_t cb, uint32_t s, cudaStream_t st, void **out_body, uint64_t *out_n);
 int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t k, cudaStream_t st, uint32_t **perm_out);
 int launch_gather_records(const uint8_t *body, const uint32_t *perm, uint64_t n, uint32_t S, uint8_t *out, cudaStream_t st);
+// prefilter.cu
+int launch_lowcov_flags(const int32_t *cov, uint64_t n, uint32_t c, int32_t min_cov, uint8_t *flags, int sm_count, cudaStream_t st);
+int launch_recover_classes(const int32_t *cov, uint64_t n, uint32_t c, uint32_t child, uint8_t *cls, uint8_t *find_flags, int sm_count,
+                           cudaStream_t st);
+int launch_recover_finalize(const uint8_t *cls, const int64_t *idx, const uint8_t *dirty_body, uint32_t dirty_S, uint32_t s, uint64_t dirty_first,
+                            uint64_t n, uint8_t *flags, int32_t *patch, unsigned long long *recovered, int sm_count, cudaStream_t st);
+int launch_shared_flags(const int64_t *idx, const uint8_t *graph_body, uint32_t S, uint32_t s, uint32_t c, uint64_t graph_first,
+                        const uint32_t *excluded, uint64_t nroi, uint8_t *flags, unsigned long long *missing_at, int sm_count, cudaStream_t st);
+int select_flagged(const uint8_t *flags, uint64_t n, uint32_t **sel_out, uint64_t *m_out, cudaStream_t st);
+int launch_project_records(const uint8_t *body, uint32_t s, uint32_t c_in, const uint32_t *sel, uint64_t m, uint32_t c_out,
+                           const uint8_t *flags, const int32_t *patch, uint32_t patch_color, uint8_t *out, int sm_count, cudaStream_t st);
+int cov_stats(const int32_t *cov, uint64_t n, uint32_t c, int32_t child, const uint32_t *dev_parent_mask, int sm_count, cudaStream_t st,
+              std::vector<int32_t> &out_cov, std::vector<long long> &out_count);
 uint64_t route_state_size(uint64_t max_q, int nshards);
 int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k, const uint64_t *dev_splitters, int nshards,
                  int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, void *dev_route_state, uint64_t max_q,

@@ -14,6 +14,7 @@ import os
 
 import numpy as np
 
+from .._native import CortexJDKException
 from .cortex import CortexGraph, CortexRecord
 from .kmer import CanonicalKmer
 
@@ -85,6 +86,74 @@ class Sort:
         n = sg.getNumRecords()
         sg.dispose()
         return n
+
+
+class FindLowCoverage:
+    """`FindLowCoverage -r roi.ctx -m 10 -o low.ctx` (S/commands/prefilter/FindLowCoverage.java:18-67): writes the records
+    BELOW the limit (the excluded ones), as the reference does."""
+
+    def __init__(self, ROI: CortexGraph, out, MIN_COVERAGE: int = 10):
+        self.ROI, self.out, self.MIN_COVERAGE = ROI, out, MIN_COVERAGE
+
+    def execute(self) -> tuple[int, int]:
+        low = self.ROI.findLowCoverage(self.MIN_COVERAGE)
+        low.writeGraph(self.out)
+        excluded = low.getNumRecords()
+        low.dispose()
+        return self.ROI.getNumRecords() - excluded, excluded            # (numKept, numExcluded) of the log line
+
+
+class FindShared:
+    """`FindShared -g pedigree.ctx -p mom -p dad -i ref -r roi.ctx -o shared.ctx` (S/commands/prefilter/FindShared.java:23-119)."""
+
+    def __init__(self, GRAPH: CortexGraph, PARENTS: list[str], IGNORE: list[str], ROI: CortexGraph, out):
+        self.GRAPH, self.PARENTS, self.IGNORE, self.ROI, self.out = GRAPH, list(PARENTS), list(IGNORE), ROI, out
+
+    def execute(self) -> tuple[int, int]:
+        child = self.GRAPH.getColorForSampleName(self.ROI.getSampleName(0))          # :42-43 (may be -1: then nothing is excluded for it)
+        parents = self.GRAPH.getColorsForSampleNames(self.PARENTS)
+        ignore = self.GRAPH.getColorsForSampleNames(self.IGNORE)
+        shared = self.GRAPH.findShared(self.ROI, child, parents, ignore)
+        shared.writeGraph(self.out)
+        excluded = shared.getNumRecords()
+        shared.dispose()
+        return self.ROI.getNumRecords() - excluded, excluded
+
+
+class RecoverExcludedKmers:
+    """`RecoverExcludedKmers -g pedigree.ctx -d dirty.ctx -o recovered.ctx` (S/commands/discover/recover/RecoverExcludedKmers.java:17-107)."""
+
+    def __init__(self, GRAPH: CortexGraph, DIRTY: CortexGraph, out):
+        self.GRAPH, self.DIRTY, self.out = GRAPH, DIRTY, out
+
+    def execute(self) -> int:
+        name = self.DIRTY.getSampleName(0)
+        child = self.GRAPH.getColorForSampleName(name)
+        if child < 0:                                                                # :33-36
+            raise CortexJDKException("Sample '%s' not found in pedigree graph" % name)
+        rec, recovered = self.GRAPH.recoverExcludedKmers(self.DIRTY, child)
+        rec.writeGraph(self.out)
+        rec.dispose()
+        return recovered
+
+
+class CovStats:
+    """`CovStats -g pedigree.ctx -c kid -p mom -p dad -o stats.txt` (S/commands/utils/CovStats.java:14-87)."""
+
+    def __init__(self, GRAPH: CortexGraph, CHILD: str, PARENTS, out):
+        self.GRAPH, self.CHILD, self.PARENTS, self.out = GRAPH, CHILD, list(PARENTS), out
+
+    def execute(self) -> list[tuple[int, int]]:
+        child = self.GRAPH.getColorForSampleName(self.CHILD)
+        parents = {self.GRAPH.getColorForSampleName(p) for p in self.PARENTS}        # :78-86
+        rows = self.GRAPH.covStats(child, sorted(parents))
+        text = "".join("%d\t%d\n" % r for r in rows)                                 # :68-70
+        if hasattr(self.out, "write"):
+            self.out.write(text)
+        else:
+            with open(self.out, "w") as f:
+                f.write(text)
+        return rows
 
 
 class CortexVertex:

@@ -475,6 +475,51 @@ class CortexGraph:
         other._nextRecord = other._record_at(0)
         return other
 
+    @classmethod
+    def _adopt(cls, handle, device) -> "CortexGraph":
+        """Wraps a handle returned by the library (a new device-resident graph)."""
+        other = cls.__new__(cls)
+        other._h, other._device, other._keep, other.cortexFile = handle, device, None, None
+        other.firstIndex = 0
+        other._load_header()
+        other.recordsSeen = 0
+        other._block = None
+        other._nextRecord = other._record_at(0)
+        return other
+
+    # ---- scan-shaped pre-filters / recovery (SURVEY 8f row 3); each returns a new graph
+    def findLowCoverage(self, minCoverage: int) -> "CortexGraph":
+        """FindLowCoverage.java:33-66: the records with coverage(0) < minCoverage."""
+        h = N._P()
+        N.check(N.lib().cc_find_low_coverage(self._h, int(minCoverage), C.byref(h)))
+        return CortexGraph._adopt(h, self._device)
+
+    def findShared(self, roi: "CortexGraph", child: int, parents, ignore) -> "CortexGraph":
+        """FindShared.java:40-118: records of `roi` with coverage in a colour of this graph outside child/parents/ignore."""
+        pa = np.ascontiguousarray(list(parents), dtype=np.int32)
+        ig = np.ascontiguousarray(list(ignore), dtype=np.int32)
+        h = N._P()
+        N.check(N.lib().cc_find_shared(self._h, roi._h, int(child), _ptr(pa) if pa.size else None, pa.size,
+                                       _ptr(ig) if ig.size else None, ig.size, C.byref(h)))
+        return CortexGraph._adopt(h, self._device)
+
+    def recoverExcludedKmers(self, dirty: "CortexGraph", child: int):
+        """RecoverExcludedKmers.java:31-106 -> (new one-colour graph, number of recovered records)."""
+        h = N._P()
+        rec = C.c_uint64(0)
+        N.check(N.lib().cc_recover_excluded_kmers(self._h, dirty._h, int(child), C.byref(h), C.byref(rec)))
+        return CortexGraph._adopt(h, self._device), int(rec.value)
+
+    def covStats(self, child: int, parents) -> list[tuple[int, int]]:
+        """CovStats.java:33-72 -> [(child coverage, count)] in ascending coverage."""
+        pa = np.ascontiguousarray(list(parents), dtype=np.int32)
+        nrows = C.c_uint64(0)
+        N.check(N.lib().cc_cov_stats(self._h, int(child), _ptr(pa) if pa.size else None, pa.size, None, None, 0, C.byref(nrows)))
+        cov = np.zeros(max(nrows.value, 1), dtype=np.int32)
+        cnt = np.zeros(max(nrows.value, 1), dtype=np.int32)
+        N.check(N.lib().cc_cov_stats(self._h, int(child), _ptr(pa) if pa.size else None, pa.size, _ptr(cov), _ptr(cnt), cov.size, C.byref(nrows)))
+        return [(int(a), int(b)) for a, b in zip(cov[:nrows.value], cnt[:nrows.value])]
+
     def writeGraph(self, out_path) -> None:
         """CortexGraphWriter over the whole graph (header from the colours, then every record)."""
         N.check(N.lib().cc_write_graph(self._h, os.fspath(out_path).encode()))

@@ -229,6 +229,25 @@ CC_API int cc_sort(cc_graph *g, cc_graph **out);
 /* CortexGraphWriter (S/utils/io/graph/cortex/CortexGraphWriter.java:31-138): header from the colours, then every record. */
 CC_API int cc_write_graph(const cc_graph *g, const char *path);
 
+/* ---------------------------------------------------------------- next rows: scan-shaped pre-filters / recovery */
+/* Each returns a new device-resident graph (cc_dispose it; cc_write_graph writes what the reference command writes).
+ * FindLowCoverage (S/commands/prefilter/FindLowCoverage.java:33-66): the records with coverage(0) < min_coverage, input header. */
+CC_API int cc_find_low_coverage(cc_graph *roi, int32_t min_coverage, cc_graph **out);
+/* FindShared (S/commands/prefilter/FindShared.java:40-118): ROI records whose k-mer has coverage > 0 in a colour of `graph` that is
+ * neither child, parent nor ignored.  Colour lists may hold -1 (unresolved sample names never match).  A ROI k-mer absent
+ * from `graph` is an error (NullPointerException in the reference). */
+CC_API int cc_find_shared(cc_graph *graph, cc_graph *roi, int32_t child, const int32_t *parents, int nparents,
+                          const int32_t *ignore, int nignore, cc_graph **out);
+/* RecoverExcludedKmers (S/commands/discover/recover/RecoverExcludedKmers.java:31-106): records of `graph` with child coverage > 0,
+ * plus those with coverage elsewhere whose k-mer the `dirty` graph holds with coverage(0) > 0 (their child coverage becomes the
+ * dirty one).  One-colour output: k-mer, coverage[0], edges[0] of the pedigree record under the child's colour header, as the
+ * reference's writer emits it. */
+CC_API int cc_recover_excluded_kmers(cc_graph *graph, cc_graph *dirty, int32_t child, cc_graph **out, uint64_t *out_recovered);
+/* CovStats (S/commands/utils/CovStats.java:33-72): rows (child coverage, count) in ascending coverage; *out_n = number of rows
+ * (only the first cap are stored).  Counts wrap like Java ints. */
+CC_API int cc_cov_stats(cc_graph *g, int32_t child, const int32_t *parents, int nparents,
+                        int32_t *out_cov, int32_t *out_count, uint64_t cap, uint64_t *out_n);
+
 /* ---------------------------------------------------------------- instrumentation */
 CC_API int cc_last_stats(const cc_graph *g, cc_stats *out);
 /* Total kernels this library has launched in this process (bench.py's gpu_launches). */

@@ -420,3 +420,85 @@ def sort_graph(buf: bytes) -> bytes:
         col["total_sequence"] = int.from_bytes(int(col["total_sequence"]).to_bytes(8, "little"), "big")
         colors.append(col)
     return write_header(h["kmer_size"], h["kmer_bits"], colors) + rec[order].tobytes()
+
+
+# ----------------------------------------------------------------------------- scan-shaped pre-filters
+
+def _rewritten_header(h: dict, colors: list[dict]) -> bytes:
+    """What CortexGraphWriter emits for colours that were READ by CortexGraph: total_sequence byte-reversed (see join())."""
+    out = []
+    for col in colors:
+        col = dict(col)
+        col["total_sequence"] = int.from_bytes(int(col["total_sequence"]).to_bytes(8, "little"), "big")
+        out.append(col)
+    return write_header(h["kmer_size"], h["kmer_bits"], out)
+
+
+def find_low_coverage(buf: bytes, min_coverage: int) -> bytes:
+    """S/commands/prefilter/FindLowCoverage.java:33-66: `if (cr.getCoverage(0) >= MIN_COVERAGE) numKept++ else cgw.addRecord(cr)`
+    -- the file holds the records BELOW the limit, under the input header."""
+    h = parse_header(buf)
+    rec = records_view(buf, h)
+    low = java_coverage(rec["cov"][:, 0]) < min_coverage
+    return _rewritten_header(h, h["colors"]) + rec[low].tobytes()
+
+
+def find_shared(graph_buf: bytes, roi_buf: bytes, child: int, parents: list[int], ignore: list[int]) -> bytes:
+    """S/commands/prefilter/FindShared.java:40-118: a ROI record is shared when GRAPH.findRecord(its k-mer) has coverage > 0 in a
+    colour c with c != childColor, c not in parentColors, c not in ignoreColors (:67); shared ROI records are written in order
+    under the ROI header.  A k-mer missing from GRAPH dereferences null (:67) -> raised here as KeyError."""
+    hg, hr = parse_header(graph_buf), parse_header(roi_buf)
+    g, r = records_view(graph_buf, hg), records_view(roi_buf, hr)
+    idx = find_packed(np.ascontiguousarray(g["kmer"]), np.ascontiguousarray(r["kmer"]))
+    if (idx < 0).any():
+        raise KeyError("ROI record %d is not in the graph" % int(np.nonzero(idx < 0)[0][0]))
+    cov = java_coverage(g["cov"][idx])
+    free = np.array([c != child and c not in set(parents) and c not in set(ignore) for c in range(hg["num_colors"])], dtype=bool)
+    shared = (cov[:, free] > 0).any(axis=1) if free.any() else np.zeros(len(r), dtype=bool)
+    return _rewritten_header(hr, hr["colors"]) + r[shared].tobytes()
+
+
+def recover_excluded_kmers(graph_buf: bytes, dirty_buf: bytes, child: int) -> tuple[bytes, int]:
+    """S/commands/discover/recover/RecoverExcludedKmers.java:31-106.  Records with coverage(child) > 0 are written as they are
+    (:50-52); otherwise, if another colour has coverage (:53-61) and DIRTY.findRecord(k-mer) exists with coverage(0) > 0 (:63-65),
+    a copy with coverages[child] = that coverage is written (:74,:80).  The header has ONE colour (makeHeader :98-106) and
+    CortexGraphWriter.addRecord (CortexGraphWriter.java:106-138) writes header.getNumColors() = 1 coverage and edge of the
+    record it is given: coverage[0] and edges[0] of the pedigree record."""
+    hg, hd = parse_header(graph_buf), parse_header(dirty_buf)
+    g, d = records_view(graph_buf, hg), records_view(dirty_buf, hd)
+    cov = java_coverage(g["cov"]).copy()
+    keep = cov[:, child] > 0
+    others = np.ones(hg["num_colors"], dtype=bool); others[child] = False
+    cand = ~keep & (cov[:, others] > 0).any(axis=1)
+    idx = np.full(len(g), -1, dtype=np.int64)
+    if cand.any():
+        idx[cand] = find_packed(np.ascontiguousarray(d["kmer"]), np.ascontiguousarray(g["kmer"][cand]))
+    dcov = np.where(idx >= 0, java_coverage(d["cov"][:, 0])[np.maximum(idx, 0)], 0)
+    recovered = cand & (idx >= 0) & (dcov > 0)
+    cov[recovered, child] = dcov[recovered]
+    sel = keep | recovered
+    out = np.zeros(int(sel.sum()), dtype=record_dtype(hg["kmer_bits"], 1))
+    out["kmer"] = g["kmer"][sel]
+    out["cov"][:, 0] = np.ascontiguousarray(cov[sel, 0]).view(np.uint32)
+    out["edges"][:, 0] = g["edges"][sel, 0]
+    return _rewritten_header(hg, [hg["colors"][child]]) + out.tobytes(), int(recovered.sum())
+
+
+def cov_stats(buf: bytes, child: int, parents: list[int]) -> list[tuple[int, int]]:
+    """S/commands/utils/CovStats.java:33-72: for every record with coverage(child) > 0, numberOfParents > 0 and
+    numberOfChildren > 0 (colours with coverage > 0 that are parents / neither child nor parent, :50-58):
+    hist[coverage(child)] += numberOfParents + numberOfChildren (Java int); rows printed in ascending coverage (TreeMap)."""
+    h = parse_header(buf)
+    cov = java_coverage(records_view(buf, h)["cov"])
+    c = h["num_colors"]
+    is_parent = np.array([cc in set(parents) and cc != child for cc in range(c)], dtype=bool)
+    is_other = np.array([cc not in set(parents) and cc != child for cc in range(c)], dtype=bool)
+    pos = cov > 0
+    npar = pos[:, is_parent].sum(axis=1)
+    noth = pos[:, is_other].sum(axis=1)
+    counts = (cov[:, child] > 0) & (npar > 0) & (noth > 0)
+    hist: dict[int, int] = {}
+    for cv, w in zip(cov[counts, child].tolist(), (npar + noth)[counts].tolist()):
+        hist[cv] = hist.get(cv, 0) + w
+    wrap = lambda v: ((v + 2 ** 31) % 2 ** 32) - 2 ** 31
+    return [(cv, wrap(hist[cv])) for cv in sorted(hist)]

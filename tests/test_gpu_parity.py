@@ -763,3 +763,97 @@ def test_outputs_stay_inside_their_buffers():
         torch.cuda.synchronize()
         assert intact(wb, n * 16) and intact(cb_, n * 16) and intact(eb, n * 4) and intact(pb, 70_000 * 16) and intact(fb, 70_000)
         g.dispose()
+
+
+# ------------------------------------------------------------------ next row: scan-shaped pre-filters / recovery
+
+def _one_colour_graph(words, cov, edges, k, name):
+    from oracle import oracle_np as onp
+    s = words.shape[1]
+    rec = np.zeros(len(words), dtype=onp.record_dtype(s, 1))
+    rec["kmer"], rec["cov"][:, 0], rec["edges"][:, 0] = words, cov, edges
+    col = dict(sample_name=name, mean_read_length=0, total_sequence=0, graph_name="", tip_clipping=0, low_covg_supernodes_removed=0,
+               low_covg_kmers_removed=0, cleaned_against_graph=0, low_cov_supernodes_threshold=0, low_cov_kmer_threshold=0)
+    return onp.write_header(k, s, [col]) + rec.tobytes()
+
+
+@pytest.mark.parametrize("k,c,n", [(47, 4, 60_000), (31, 3, 20_000), (63, 21, 4_000), (95, 2, 3_000)])
+def test_prefilters_vs_oracle(tmp_path, k, c, n):
+    """FindLowCoverage, FindShared, RecoverExcludedKmers and CovStats end to end (files bit-exact against the numpy oracle)."""
+    from oracle import oracle_np as onp
+    ctx = synth.make_ctx_file(900 + k, n, k, c, novel_permille=40, adv_period=53)
+    graph = cb.CortexGraph(ctx)
+    names = [graph.getSampleName(i) for i in range(c)]
+    parents = names[1:3] if c >= 3 else names[1:2]
+    # ROI graph: the child's novel k-mers w.r.t. the parents only (so that some have coverage in the remaining colours)
+    roi_path = tmp_path / "roi.ctx"
+    cb.FindROIs(graph, parents, names[0], roi_path).execute()
+    roi_bytes = roi_path.read_bytes()
+    roi = cb.CortexGraph(str(roi_path))
+    assert roi.getNumRecords() > 50
+
+    # FindLowCoverage
+    for m in (10, 1, 61, -5):
+        kept, excluded = cb.FindLowCoverage(roi, tmp_path / "low.ctx", m).execute()
+        want = onp.find_low_coverage(roi_bytes, m)
+        assert (tmp_path / "low.ctx").read_bytes() == want, m
+        assert excluded == onp.parse_header(want)["num_records"] and kept + excluded == roi.getNumRecords()
+
+    # FindShared: free colours = everything but child, parents and the ignored ones
+    pcols = graph.getColorsForSampleNames(parents)
+    for ignore in ([], names[-1:], ["no-such-sample"]):
+        cb.FindShared(graph, parents, ignore, roi, tmp_path / "shared.ctx").execute()
+        icols = [x for x in graph.getColorsForSampleNames(ignore)]
+        want = onp.find_shared(ctx, roi_bytes, 0, pcols, icols)
+        assert (tmp_path / "shared.ctx").read_bytes() == want, ignore
+    if c > 3:
+        assert onp.parse_header(onp.find_shared(ctx, roi_bytes, 0, pcols, []))["num_records"] > 0
+    # a ROI k-mer that is not in the graph: NullPointerException in the reference, an error here
+    stray = cb.CortexGraph(_one_colour_graph(np.full((1, graph.getKmerBits()), 3, dtype=np.uint64), [1], [0], k, names[0]))
+    with pytest.raises(cb.CortexJDKException):
+        graph.findShared(stray, 0, pcols, [])
+    stray.dispose()
+
+    # RecoverExcludedKmers: the dirty graph holds every third k-mer of the pedigree graph plus strangers, coverage 0 / small / >= 2^31
+    words, cov, edges = graph.decodeRecords(0, n)
+    rng = np.random.default_rng(k)
+    pick = np.arange(0, n, 3)
+    dcov = rng.integers(0, 4, len(pick)).astype(np.uint32)
+    dcov[::17] = 0x80000005
+    for child_color in (0, min(1, c - 1)):
+        dirty_bytes = _one_colour_graph(words[pick], dcov, rng.integers(0, 256, len(pick)).astype(np.uint8), k, names[child_color])
+        dirty = cb.CortexGraph(dirty_bytes)
+        recovered = cb.RecoverExcludedKmers(graph, dirty, tmp_path / "rec.ctx").execute()
+        want, nrec = onp.recover_excluded_kmers(ctx, dirty_bytes, child_color)
+        assert (tmp_path / "rec.ctx").read_bytes() == want, child_color
+        assert recovered == nrec and (nrec > 0 or n < 5000)
+        dirty.dispose()
+    with pytest.raises(cb.CortexJDKException):
+        d2 = cb.CortexGraph(_one_colour_graph(words[:5], [1] * 5, [0] * 5, k, "stranger"))
+        try:
+            cb.RecoverExcludedKmers(graph, d2, tmp_path / "x.ctx").execute()
+        finally:
+            d2.dispose()
+
+    # CovStats
+    import io
+    for child_name, pnames in ((names[0], parents), (names[1], [names[0]]), (names[0], ["no-such-sample"])):
+        buf = io.StringIO()
+        rows = cb.CovStats(graph, child_name, pnames, buf).execute()
+        ccol = graph.getColorForSampleName(child_name)
+        want = onp.cov_stats(ctx, ccol, [graph.getColorForSampleName(p) for p in pnames])
+        assert rows == want and buf.getvalue() == "".join("%d\t%d\n" % r for r in want)
+    assert len(onp.cov_stats(ctx, 0, graph.getColorsForSampleNames(parents))) > 0 or c < 4
+    roi.dispose(); graph.dispose()
+
+
+def test_prefilters_empty_graph(tmp_path):
+    ctx = synth.make_ctx_file(3, 0, 31, 3)
+    g = cb.CortexGraph(ctx)
+    low = g.findLowCoverage(5)
+    assert low.getNumRecords() == 0
+    low.dispose()
+    assert g.covStats(0, [1]) == []
+    rec, nrec = g.recoverExcludedKmers(g, 0)
+    assert rec.getNumRecords() == 0 and nrec == 0
+    rec.dispose(); g.dispose()

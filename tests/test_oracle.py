@@ -334,3 +334,57 @@ def test_join_oracle_matches_assembler():
     assert (rw["edges"] == rj["edges"]).all()
     one = onp.join([parts[0]])
     assert onp.records_view(one, onp.parse_header(one)).tobytes() == onp.records_view(parts[0], onp.parse_header(parts[0])).tobytes()
+
+
+# ------------------------------------------------------------------ scan-shaped pre-filters: hand-checked cases
+
+def _tiny_graph(kmers, covs, names, k=5):
+    """A .ctx image from ASCII k-mers (already canonical, ascending) and per-colour coverages; edges = colour index + 1."""
+    s = 1
+    words, _ = onp.encode_kmers(np.array([list(x.encode()) for x in kmers], dtype=np.uint8))
+    rec = np.zeros(len(kmers), dtype=onp.record_dtype(s, len(names)))
+    rec["kmer"] = words.reshape(-1, s)
+    rec["cov"] = np.array(covs, dtype=np.int64).astype(np.uint32).reshape(len(kmers), len(names))
+    rec["edges"] = np.arange(1, len(names) + 1, dtype=np.uint8)[None, :]
+    colors = [dict(sample_name=n, mean_read_length=100, total_sequence=7 + i, graph_name="undefined", tip_clipping=0,
+                   low_covg_supernodes_removed=0, low_covg_kmers_removed=0, cleaned_against_graph=0,
+                   low_cov_supernodes_threshold=0, low_cov_kmer_threshold=0) for i, n in enumerate(names)]
+    return onp.write_header(k, s, colors) + rec.tobytes()
+
+
+def test_prefilter_oracles_hand_checked():
+    km = ["AAAAA", "AAACC", "ACGTA", "CCCAA", "GATTA"]
+    #            kid  mom  dad  ref
+    covs = [[3, 0, 0, 0],          # child only
+            [0, 2, 0, 5],          # not in child; in mom and ref
+            [9, 1, 0, 4],          # child + mom + ref
+            [0, 0, 0, 0],          # nowhere
+            [2 ** 31, 1, 1, 1]]    # child coverage wraps negative in Java
+    g = _tiny_graph(km, covs, ["kid", "mom", "dad", "ref"])
+    # FindLowCoverage on a one-colour ROI: keeps coverage(0) < 4, signed
+    roi = _tiny_graph(km, [[3], [0], [9], [4], [2 ** 31]], ["kid"])
+    low = onp.find_low_coverage(roi, 4)
+    hl = onp.parse_header(low)
+    assert onp.decode_kmers(onp.records_view(low, hl)["kmer"], 5).tobytes().decode() == "AAAAA" + "AAACC" + "GATTA"
+    # FindShared: free colours = {ref} when child=0, parents={1,2}; shared where ref coverage > 0
+    sh = onp.find_shared(g, roi, 0, [1, 2], [])
+    assert onp.records_view(sh, onp.parse_header(sh))["cov"][:, 0].tolist() == [0, 9, 2 ** 31]
+    assert onp.parse_header(onp.find_shared(g, roi, 0, [1, 2], [3]))["num_records"] == 0        # ref ignored: nothing is free
+    with pytest.raises(KeyError):
+        onp.find_shared(g, _tiny_graph(["TTTTT"], [[1]], ["kid"]), 0, [1], [])
+    # RecoverExcludedKmers: dirty graph holds AAACC (cov 6) and CCCAA (cov 8) and GATTA (cov 0)
+    dirty = _tiny_graph(["AAACC", "CCCAA", "GATTA"], [[6], [8], [0]], ["kid"])
+    rec, nrec = onp.recover_excluded_kmers(g, dirty, 0)
+    hr = onp.parse_header(rec)
+    rv = onp.records_view(rec, hr)
+    assert hr["num_colors"] == 1 and hr["colors"][0]["sample_name"] == "kid" and nrec == 1
+    assert onp.decode_kmers(rv["kmer"], 5).tobytes().decode() == "AAAAA" + "AAACC" + "ACGTA"     # CCCAA has no coverage anywhere; GATTA: child <= 0, dirty 0
+    assert rv["cov"][:, 0].tolist() == [3, 6, 9] and rv["edges"][:, 0].tolist() == [1, 1, 1]
+    rec1, n1 = onp.recover_excluded_kmers(g, _tiny_graph(["AAAAA"], [[5]], ["mom"]), 1)             # child = colour 1: output still shows colour 0
+    r1 = onp.records_view(rec1, onp.parse_header(rec1))
+    assert n1 == 1 and onp.parse_header(rec1)["colors"][0]["sample_name"] == "mom"
+    assert onp.decode_kmers(r1["kmer"], 5).tobytes().decode() == "AAAAA" + "AAACC" + "ACGTA" + "GATTA"
+    assert r1["cov"][:, 0].tolist() == [3, 0, 9, 2 ** 31]
+    # CovStats: only ACGTA counts (child 9 > 0, one parent, one other): weight 2
+    assert onp.cov_stats(g, 0, [1, 2]) == [(9, 2)]
+    assert onp.cov_stats(g, 1, [0]) == [(1, 2)]              # child = mom, parent = kid: only ACGTA (kid + ref); GATTA's kid coverage is negative

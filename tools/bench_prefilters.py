@@ -1,0 +1,46 @@
+"""Times the scan-shaped pre-filters on a configs[1]-sized pedigree graph (GPU box only)."""
+import sys, time
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+import corticall_b200 as cb
+from tools import synth
+
+k, c, n = 47, 4, 25_000_000
+body, words = synth.make_graph_body(20261018, n, k, c, device="cuda")
+g = cb.CortexGraph.fromDevice(body.data_ptr(), k, c, n, keepalive=body)
+S = 8 * 2 + 5 * c
+
+
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3, r
+
+
+ms, rows = timed(lambda: g.covStats(0, [1, 2]))
+print("CovStats                n=%.1e  %.2f ms  %.3g records/s  (%d rows)" % (n, ms, n / ms * 1e3, len(rows)))
+# dirty graph: every 4th k-mer, one colour
+pick = torch.arange(0, n, 4, device="cuda")
+dcov = torch.randint(0, 5, (len(pick), 1), device="cuda", dtype=torch.int32)
+dedg = torch.zeros((len(pick), 1), dtype=torch.uint8, device="cuda")
+dbody = synth.assemble_records([w[pick] for w in words], dcov, dedg)
+dirty = cb.CortexGraph.fromDevice(dbody.data_ptr(), k, 1, len(pick), keepalive=dbody)
+dirty.buildIndex()
+
+
+def rec():
+    out, nrec = g.recoverExcludedKmers(dirty, 0)
+    m = out.getNumRecords()
+    out.dispose()
+    return m, nrec
+
+
+ms, (m, nrec) = timed(rec)
+print("RecoverExcludedKmers    n=%.1e  %.2f ms  %.3g records/s  (%d written, %d recovered; %.0f MB in, %.0f MB out)" % (
+    n, ms, n / ms * 1e3, m, nrec, n * S / 1e6, m * 21 / 1e6))
+cnt, recs, idx = g.findNovel(0, [1, 2])
+print("novel vs parents only: %d" % cnt)
