@@ -234,7 +234,10 @@ void destroy(cc_graph *g) {
     if (g->index.table) cudaFree(g->index.table);
     if (g->novel_buf) cudaFree(g->novel_buf);
     if (g->novel_idx) cudaFree(g->novel_idx);
-    if (g->dev_alloc) cudaFree(g->dev_alloc);
+    if (g->dev_alloc) {
+        if (g->dev_alloc_pooled && g->stream) { cudaFreeAsync(g->dev_alloc, g->stream); cudaStreamSynchronize(g->stream); }
+        else cudaFree(g->dev_alloc);
+    }
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -1078,9 +1081,13 @@ int make_selected_graph(cc_graph *src, const Header &hdr, uint32_t c_out, const 
     g->h.num_records = m;
     if (int rc = init_handle(g.get(), src->device)) return rc;
     void *body = nullptr;
-    CC_CUDA(cudaMalloc(&body, m * g->h.record_size + 256));
+    // from the stream-ordered pool: filter outputs are created and disposed per command, and a cudaMalloc / cudaFree pair of
+    // half a gigabyte costs more than the whole scan
+    CC_CUDA(cudaMallocAsync(&body, m * g->h.record_size + 256, g->stream));
     g->dev_alloc = body;
+    g->dev_alloc_pooled = true;
     g->dev_body = static_cast<const uint8_t *>(body);
+    CC_CUDA(cudaStreamSynchronize(g->stream));            // the projection below runs on the source graph's stream
     if (int rc = launch_project_records(src->dev_body, src->h.s, src->h.c, sel, m, c_out, flags, patch, patch_color,
                                         static_cast<uint8_t *>(body), src->sm_count, st)) return rc;
     CC_CUDA(cudaMemsetAsync(static_cast<uint8_t *>(body) + m * g->h.record_size, 0, 256, st));

@@ -113,6 +113,7 @@ struct cc_graph {
     // device body
     const uint8_t *dev_body = nullptr;   // record 0
     void *dev_alloc = nullptr;           // owned allocation (null when wrapping a caller buffer)
+    bool dev_alloc_pooled = false;       // dev_alloc came from the stream-ordered pool (cudaFreeAsync)
     uint64_t first_index = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
