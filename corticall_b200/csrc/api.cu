@@ -951,20 +951,20 @@ int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *d
                         max_queries, dev_sent, static_cast<cudaStream_t>(stream));
 }
 
-int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, int my_rank, uint64_t cap,
-                       void *const *peer_ret, void *stream) {
-    if (!g || !dev_inbox || !dev_counts_in || !peer_ret) return fail(CC_ERR_ARG, "null argument");
+int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, uint64_t cap,
+                       void *dev_res, void *stream) {
+    if (!g || !dev_inbox || !dev_counts_in || !dev_res) return fail(CC_ERR_ARG, "null argument");
     DeviceGuard guard(g->device);
     if (int rc = ensure_index(g)) return rc;
-    return launch_find_routed(g, dev_inbox, dev_counts_in, world, vsub, my_rank, cap, peer_ret, static_cast<cudaStream_t>(stream));
+    return launch_find_routed(g, dev_inbox, dev_counts_in, world, vsub, cap, dev_res, static_cast<cudaStream_t>(stream));
 }
 
-int cc_gather_routed_dev(int device, const void *dev_ret, const void *dev_route_state, uint64_t max_queries, uint64_t nq,
+int cc_gather_routed_dev(int device, void *const *peer_res, const void *dev_route_state, uint64_t max_queries, uint64_t nq,
                          const uint64_t *dev_shard_first, int nshards, uint64_t cap, int64_t *dev_out, void *stream) {
     if (int rc = check_device(device)) return rc;
-    if (nq && (!dev_ret || !dev_route_state || !dev_shard_first || !dev_out)) return fail(CC_ERR_ARG, "null argument");
+    if (nq && (!peer_res || !dev_route_state || !dev_shard_first || !dev_out)) return fail(CC_ERR_ARG, "null argument");
     DeviceGuard guard(device);
-    return launch_gather_routed(dev_ret, dev_route_state, max_queries, nq, dev_shard_first, nshards, cap, dev_out, static_cast<cudaStream_t>(stream));
+    return launch_gather_routed(peer_res, dev_route_state, max_queries, nq, dev_shard_first, nshards, cap, dev_out, static_cast<cudaStream_t>(stream));
 }
 
 // ==================================================================== next rows: merged view (CortexCollection / Join)

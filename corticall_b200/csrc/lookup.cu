@@ -936,7 +936,7 @@ __global__ void publish_counts_kernel(const unsigned long long *cursors, int nsh
 // large batches.  inbox: [vsub][world][cap][KW], counts_in: [vsub][world]; ret on the origin: [world * vsub][cap].
 template <int S, int KW, int Q>
 __global__ void __launch_bounds__(kBlock, S <= 2 ? 3 : 1) find_routed_kernel(const uint32_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
-                                                                             int world, int vsub, int my_rank, uint64_t cap, IndexView ix, PeerPtrs ret) {
+                                                                             int world, int vsub, uint64_t cap, IndexView ix, uint32_t *__restrict__ res) {
     // all segments in (sub-range, source) order form one flat sequence of keys; the grid sweeps it front to back, so the
     // CTAs work on the same sub-range at the same time
     __shared__ unsigned long long pre[kMaxShards + 1];
@@ -954,37 +954,34 @@ __global__ void __launch_bounds__(kBlock, S <= 2 ? 3 : 1) find_routed_kernel(con
         uint64_t q[Q][S];
         bool live[Q];
         int64_t r[Q];
-        uint32_t seg[Q];
-        uint64_t pos[Q];
+        uint64_t slot[Q];                                    // segment * cap + position: same index in the inbox and in res
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint64_t f = basei + (uint64_t)j * span;
             live[j] = f < total;
-            seg[j] = 0; pos[j] = 0;
+            slot[j] = 0;
             if (live[j]) {
                 uint32_t lo = 0, hi = nseg - 1;              // segment e with pre[e] <= f < pre[e + 1]
                 while (lo < hi) {
                     const uint32_t mid = (lo + hi + 1) >> 1;
                     if (pre[mid] <= f) lo = mid; else hi = mid - 1;
                 }
-                seg[j] = lo;
-                pos[j] = f - pre[lo];
-                wire_to_key<S, KW>(inbox + ((uint64_t)lo * cap + pos[j]) * KW, q[j]);
+                slot[j] = (uint64_t)lo * cap + (f - pre[lo]);
+                wire_to_key<S, KW>(inbox + slot[j] * KW, q[j]);
             }
         }
         lookup_mlp<S, Q>(ix, pol, q, live, r);     // ix.first_index is 0 here: results are local to the shard
+        // results stay on the owner, in the inbox's own layout; the origin pulls its runs in the gather leg.  (Storing them
+        // straight into the origins' buffers cost up to 1.4 ms per batch on most ranks at 8 GPUs: see DESIGN.md section 5.)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            if (!live[j]) continue;
-            const uint32_t vv = seg[j] / (uint32_t)world, src = seg[j] - vv * (uint32_t)world;
-            static_cast<uint32_t *>(ret.p[src])[((uint64_t)my_rank * vsub + vv) * cap + pos[j]] = r[j] < 0 ? kWireMiss : (uint32_t)r[j];
-        }
+        for (int j = 0; j < Q; ++j)
+            if (live[j]) res[slot[j]] = r[j] < 0 ? kWireMiss : (uint32_t)r[j];
     }
     __threadfence_system();
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) gather_routed_kernel(const uint32_t *__restrict__ ret, RouteState rs, uint64_t nq,
+__global__ void __launch_bounds__(BLOCK) gather_routed_kernel(PeerPtrs res, RouteState rs, uint64_t nq,
                                                               const uint64_t *__restrict__ shard_first, int nshards, uint64_t cap,
                                                               int64_t *__restrict__ out) {
     constexpr uint32_t kTile = BLOCK * kRouteQ;
@@ -1010,7 +1007,8 @@ __global__ void __launch_bounds__(BLOCK) gather_routed_kernel(const uint32_t *__
                 if (loc[mid] <= p) lo = mid; else hi = mid - 1;
             }
             const uint64_t at = (uint64_t)base[lo] + (p - loc[lo]);
-            const uint32_t r = at < cap ? __ldg(ret + (uint64_t)lo * cap + at) : kWireMiss;   // dropped by an overflowing segment
+            // res.p[o] = this origin's result segment on owner o (peer memory: read over NVLink, never cached in L1)
+            const uint32_t r = at < cap ? __ldcv(static_cast<const uint32_t *>(res.p[lo]) + at) : kWireMiss;   // >= cap: dropped by an overflowing segment
             staged[p] = r == kWireMiss ? -1 : (int64_t)(first[lo] + r);
         }
         __syncthreads();
@@ -1505,13 +1503,10 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     return CC_OK;
 }
 
-int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, int my_rank, uint64_t cap,
-                       void *const *peer_ret, cudaStream_t st) {
+int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, uint64_t cap,
+                       void *dev_res, cudaStream_t st) {
     if (int rc = check_k(g->h.k)) return rc;
     if (world < 1 || vsub < 1 || world * vsub > kMaxShards) return fail(CC_ERR_ARG, "world * vsub must be in 1..%d", kMaxShards);
-    if (my_rank < 0 || my_rank >= world) return fail(CC_ERR_ARG, "rank %d out of range", my_rank);
-    PeerPtrs ret{};
-    for (int i = 0; i < world; ++i) ret.p[i] = peer_ret[i];
     IndexView ix = view_of(g);
     ix.first_index = 0;                 // the wire carries indices local to the shard; the origin rebases them
     // a sub-range that fits L2 must stay there: no evict-first on its keys
@@ -1521,25 +1516,28 @@ int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_c
     const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
     CC_DISPATCH_SKW(g->h.s, kw, {
         find_routed_kernel<S_, KW_, 2><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t *>(dev_inbox),
-                                                                 reinterpret_cast<const unsigned long long *>(dev_counts_in), world, vsub, my_rank, cap, ix, ret);
+                                                                 reinterpret_cast<const unsigned long long *>(dev_counts_in), world, vsub, cap, ix,
+                                                                 static_cast<uint32_t *>(dev_res));
     });
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;
 }
 
-int launch_gather_routed(const void *dev_ret, const void *dev_route_state, uint64_t max_q, uint64_t nq, const uint64_t *dev_shard_first,
+int launch_gather_routed(void *const *peer_res, const void *dev_route_state, uint64_t max_q, uint64_t nq, const uint64_t *dev_shard_first,
                          int nshards, uint64_t cap, int64_t *dev_out, cudaStream_t st) {
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
     if (nq == 0) return CC_OK;
     const RouteState rs = route_state_of(const_cast<void *>(dev_route_state), max_q, nshards);
+    PeerPtrs res{};
+    for (int i = 0; i < nshards; ++i) res.p[i] = peer_res[i];
     const int cap_sm = std::max(1, options().gather_blocks_per_sm);
     if (route_block_for(nshards) == 256) {
         const int grid = resident_grid(gather_routed_kernel<256>, 256, 0, route_tiles(nq, 256 * kRouteQ), sm_count_now(), cap_sm);
-        gather_routed_kernel<256><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(dev_ret), rs, nq, dev_shard_first, nshards, cap, dev_out);
+        gather_routed_kernel<256><<<grid, 256, 0, st>>>(res, rs, nq, dev_shard_first, nshards, cap, dev_out);
     } else {
         const int grid = resident_grid(gather_routed_kernel<128>, 128, 0, route_tiles(nq, 128 * kRouteQ), sm_count_now(), cap_sm);
-        gather_routed_kernel<128><<<grid, 128, 0, st>>>(static_cast<const uint32_t *>(dev_ret), rs, nq, dev_shard_first, nshards, cap, dev_out);
+        gather_routed_kernel<128><<<grid, 128, 0, st>>>(res, rs, nq, dev_shard_first, nshards, cap, dev_out);
     }
     count_launch();
     CC_CUDA(cudaGetLastError());

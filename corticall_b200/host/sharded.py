@@ -116,11 +116,11 @@ class RoutedLookup:
                               ceil(2k/32) 32-bit words) straight into the owner's inbox segment for this rank; only the
                               tile bookkeeping stays local (2 bytes per query + one run descriptor per tile and owner)
         barrier               (symmetric-memory signal pads; orders the peer stores)
-        cc_find_routed_dev    the owner searches every inbox segment and stores each result (4-byte shard-local index)
-                              straight into the origin's return buffer, same segment position
+        cc_find_routed_dev    the owner searches every inbox segment; each result (4-byte shard-local index) stays on the
+                              owner, same segment and position
         barrier
-        cc_gather_routed_dev  the origin re-reads its tiles' runs, rebases by the owner's first record index and writes
-                              out[] in query order -- all coalesced
+        cc_gather_routed_dev  the origin pulls its tiles' runs from the owners (P2P reads), rebases by the owner's first
+                              record index and writes out[] in query order -- all coalesced
 
     The host never reads a count, so the whole batch is asynchronous on the current stream.  Buffers are one symmetric
     allocation per rank (torch.distributed._symmetric_memory: plumbing only).  `cap` is the capacity of one
@@ -170,7 +170,9 @@ class RoutedLookup:
         seg_inbox = world * self.cap * self.kw * 4          # one sub-range's [world][cap][kw] block
         self.p_inbox = (C.c_void_p * self.nv)(*[bases[v // self.vsub] + self.off_inbox + (v % self.vsub) * seg_inbox for v in range(self.nv)])
         self.p_counts = (C.c_void_p * self.nv)(*[bases[v // self.vsub] + self.off_counts + (v % self.vsub) * world * 8 for v in range(self.nv)])
-        self.p_ret = (C.c_void_p * world)(*[b + self.off_ret for b in bases])
+        # results stay on the owner in the inbox's layout; entry v = this rank's result segment on virtual owner v
+        self.p_res = (C.c_void_p * self.nv)(*[bases[v // self.vsub] + self.off_ret + ((v % self.vsub) * world + rank) * self.cap * 4
+                                              for v in range(self.nv)])
         nbytes = C.c_uint64(0)
         N.check(N.lib().cc_route_state_bytes(self.max_batch, self.nv, C.byref(nbytes)))
         self.state = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
@@ -238,12 +240,12 @@ class RoutedLookup:
     def search(self):
         st = torch.cuda.current_stream().cuda_stream
         base = self.block.data_ptr()
-        N.check(N.lib().cc_find_routed_dev(self.g._h, base + self.off_inbox, base + self.off_counts, self.world, self.vsub, self.rank,
-                                           self.cap, self.p_ret, st))
+        N.check(N.lib().cc_find_routed_dev(self.g._h, base + self.off_inbox, base + self.off_counts, self.world, self.vsub,
+                                           self.cap, base + self.off_ret, st))
 
     def gather(self, out):
         st = torch.cuda.current_stream().cuda_stream
-        N.check(N.lib().cc_gather_routed_dev(self.index, self.block.data_ptr() + self.off_ret, self.state.data_ptr(), self.max_batch, self.nq,
+        N.check(N.lib().cc_gather_routed_dev(self.index, self.p_res, self.state.data_ptr(), self.max_batch, self.nq,
                                              self.shard_first.data_ptr(), self.nv, self.cap, out.data_ptr(), st))
 
     def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor, profile: bool = False) -> torch.Tensor:

@@ -189,8 +189,8 @@ CC_API int cc_scatter_results_dev(int device, const int64_t *dev_values, const u
 /* Routed lookups over PEER MEMORY (NVLink P2P; buffers are symmetric allocations mapped into every rank, e.g. with
  * torch.distributed._symmetric_memory or cudaIpc): each leg is one kernel fused with its transfer, no collective
  * library on the data path.  Keys travel in a compact wire format (kw = ceil(2k/32) 32-bit words, most significant
- * first: 12 bytes at k = 47) and results as 4-byte indices local to the owner's shard (0xffffffff = miss), rebased by
- * the origin.
+ * first: 12 bytes at k = 47); results are 4-byte indices local to the owner's shard (0xffffffff = miss) that stay on the
+ * owner and are pulled (P2P reads) and rebased by the origin.
  * Virtual shards: every rank's shard may be cut into `vsub` contiguous sub-ranges; the route and gather legs then see
  * nshards = world * vsub owners (owner v lives on rank v / vsub) and the search leg walks its vsub sub-ranges one after
  * another, so that the slice of the key column in use fits L2 (the partitioned form of the lookup for large batches;
@@ -198,14 +198,14 @@ CC_API int cc_scatter_results_dev(int device, const int64_t *dev_values, const u
  * Layout, identical on every rank (cap = capacity of one (source, owner) segment):
  *   inbox     uint32 [vsub][world][cap][kw] on the OWNER : keys routed to it, segment = (sub-range, source rank)
  *   counts_in uint64 [vsub][world]          on the OWNER : keys in each segment
- *   ret       uint32 [world * vsub][cap]    on the ORIGIN: results, segment = owner v, same positions as sent
+ *   res       uint32 [vsub][world][cap]     on the OWNER : results, same segments and positions as the inbox
  *   route_state (cc_route_state_bytes(max_queries, nshards) bytes), sent uint64 [nshards]   local to the origin
  *   shard_first uint64 [nshards]            first global record index of the RANK SHARD owner v belongs to
  *   splitters   uint64 [nshards - 1][s]     first key of owners 1..nshards-1
  * Order of use per batch on one stream: cc_route_queries_dev -> cross-rank barrier -> cc_find_routed_dev -> barrier ->
  * cc_gather_routed_dev (writes every out[i], -1 for misses and flagged queries).  peer_inbox / peer_counts_in are HOST
- * arrays of nshards DEVICE pointers (entry v = the [world][cap][kw] / [world] block of owner v on its rank); peer_ret is a
- * HOST array of world DEVICE pointers (entry r = rank r's ret buffer).  With cap >= the batch size no segment can
+ * arrays of nshards DEVICE pointers (entry v = the [world][cap][kw] / [world] block of owner v on its rank); peer_res is a
+ * HOST array of nshards DEVICE pointers (entry v = the [cap] result segment (owner v, source = this rank) on owner v's rank).  With cap >= the batch size no segment can
  * overflow; with a smaller cap the caller must check sent[v] <= cap after the batch (keys beyond cap are dropped and
  * their queries report -1). */
 CC_API int cc_route_state_bytes(uint64_t max_queries, int nshards, uint64_t *out_bytes);
@@ -213,9 +213,9 @@ CC_API int cc_route_queries_dev(int device, const uint64_t *dev_words, const uin
                                 const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap,
                                 void *const *peer_inbox, void *const *peer_counts_in,
                                 void *dev_route_state, uint64_t max_queries, uint64_t *dev_sent, void *stream);
-CC_API int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, int my_rank,
-                              uint64_t cap, void *const *peer_ret, void *stream);
-CC_API int cc_gather_routed_dev(int device, const void *dev_ret, const void *dev_route_state, uint64_t max_queries, uint64_t nq,
+CC_API int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub,
+                              uint64_t cap, void *dev_res, void *stream);
+CC_API int cc_gather_routed_dev(int device, void *const *peer_res, const void *dev_route_state, uint64_t max_queries, uint64_t nq,
                                 const uint64_t *dev_shard_first, int nshards, uint64_t cap, int64_t *dev_out, void *stream);
 
 /* ---------------------------------------------------------------- next rows: merged view of several graphs */
