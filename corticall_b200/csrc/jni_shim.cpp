@@ -141,4 +141,59 @@ JFN(void, packCanonical)(JNIEnv *env, jclass, jint device, jbyteArray seq, jint 
     env->ReleaseByteArrayElements(outFlags, f, 0);
     check(env, rc);
 }
+
+// ---- next rows: whole-graph operations returning a new device-resident graph
+JFN(jlong, join)(JNIEnv *env, jclass, jlongArray handles) {
+    const jsize n = env->GetArrayLength(handles);
+    jlong *h = env->GetLongArrayElements(handles, nullptr);
+    std::vector<cc_graph *> gs(n);
+    for (jsize i = 0; i < n; ++i) gs[i] = G(h[i]);
+    env->ReleaseLongArrayElements(handles, h, JNI_ABORT);
+    cc_graph *out = nullptr;
+    return check(env, cc_join(gs.data(), (int)n, &out)) ? reinterpret_cast<jlong>(out) : 0;
+}
+JFN(jlong, sort)(JNIEnv *env, jclass, jlong h) {
+    cc_graph *out = nullptr;
+    return check(env, cc_sort(G(h), &out)) ? reinterpret_cast<jlong>(out) : 0;
+}
+JFN(void, writeGraph)(JNIEnv *env, jclass, jlong h, jstring outPath) {
+    const char *path = env->GetStringUTFChars(outPath, nullptr);
+    const int rc = cc_write_graph(G(h), path);
+    env->ReleaseStringUTFChars(outPath, path);
+    check(env, rc);
+}
+JFN(jlong, findLowCoverage)(JNIEnv *env, jclass, jlong roi, jint minCoverage) {
+    cc_graph *out = nullptr;
+    return check(env, cc_find_low_coverage(G(roi), minCoverage, &out)) ? reinterpret_cast<jlong>(out) : 0;
+}
+JFN(jlong, findShared)(JNIEnv *env, jclass, jlong graph, jlong roi, jint child, jintArray parents, jintArray ignore) {
+    const jsize np = env->GetArrayLength(parents), ni = env->GetArrayLength(ignore);
+    jint *p = env->GetIntArrayElements(parents, nullptr);
+    jint *g = env->GetIntArrayElements(ignore, nullptr);
+    cc_graph *out = nullptr;
+    const int rc = cc_find_shared(G(graph), G(roi), child, reinterpret_cast<int32_t *>(p), np, reinterpret_cast<int32_t *>(g), ni, &out);
+    env->ReleaseIntArrayElements(parents, p, JNI_ABORT);
+    env->ReleaseIntArrayElements(ignore, g, JNI_ABORT);
+    return check(env, rc) ? reinterpret_cast<jlong>(out) : 0;
+}
+JFN(jlong, recoverExcludedKmers)(JNIEnv *env, jclass, jlong graph, jlong dirty, jint child) {
+    cc_graph *out = nullptr;
+    uint64_t recovered = 0;
+    return check(env, cc_recover_excluded_kmers(G(graph), G(dirty), child, &out, &recovered)) ? reinterpret_cast<jlong>(out) : 0;
+}
+JFN(jintArray, covStats)(JNIEnv *env, jclass, jlong h, jint child, jintArray parents) {
+    const jsize np = env->GetArrayLength(parents);
+    jint *p = env->GetIntArrayElements(parents, nullptr);
+    uint64_t rows = 0;
+    int rc = cc_cov_stats(G(h), child, reinterpret_cast<int32_t *>(p), np, nullptr, nullptr, 0, &rows);
+    std::vector<int32_t> cov(rows ? rows : 1), cnt(rows ? rows : 1);
+    if (rc == CC_OK) rc = cc_cov_stats(G(h), child, reinterpret_cast<int32_t *>(p), np, cov.data(), cnt.data(), rows, &rows);
+    env->ReleaseIntArrayElements(parents, p, JNI_ABORT);
+    if (!check(env, rc)) return nullptr;
+    std::vector<jint> flat(2 * rows);
+    for (uint64_t i = 0; i < rows; ++i) { flat[2 * i] = cov[i]; flat[2 * i + 1] = cnt[i]; }
+    jintArray out = env->NewIntArray((jsize)flat.size());
+    env->SetIntArrayRegion(out, 0, (jsize)flat.size(), flat.data());
+    return out;
+}
 #endif  // __has_include(<jni.h>)

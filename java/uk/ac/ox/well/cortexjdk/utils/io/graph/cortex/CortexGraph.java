@@ -47,8 +47,13 @@ public class CortexGraph implements DeBruijnGraph {
     public CortexGraph(String cortexFilePath) { this(new File(cortexFilePath)); }
 
     public CortexGraph(File cortexFile) {
+        this(cortexFile, NativeCortex.open(cortexFile.getAbsolutePath(), Integer.getInteger("corticall.cuda.device", 0)));
+    }
+
+    /** Wraps a device-resident graph the library returned (join, sort, the pre-filters); cortexFile is null until it is written. */
+    private CortexGraph(File cortexFile, long nativeHandle) {
         this.cortexFile = cortexFile;
-        this.handle = NativeCortex.open(cortexFile.getAbsolutePath(), Integer.getInteger("corticall.cuda.device", 0));
+        this.handle = nativeHandle;
         long[] h = NativeCortex.header(handle);
         header.setVersion((int) h[0]);
         header.setKmerSize((int) h[1]);
@@ -180,6 +185,48 @@ public class CortexGraph implements DeBruijnGraph {
         int[] p = new int[parentColors.size()];
         for (int i = 0; i < p.length; i++) { p[i] = parentColors.get(i); }
         return NativeCortex.writeRoiFile(handle, childColor, p, out.getAbsolutePath());
+    }
+
+    // ------------------------------------------------------------------------------------------ next rows: whole-graph operations
+    private static int[] toArray(Collection<Integer> colors) {
+        int[] a = new int[colors.size()];
+        int i = 0;
+        for (int c : colors) { a[i++] = c; }
+        return a;
+    }
+
+    /** CortexCollection / Join (CortexCollection.java:34-62,245-293; commands/utils/Join.java:23-57): the sorted union, colours concatenated. */
+    public static CortexGraph join(List<CortexGraph> graphs) {
+        long[] hs = new long[graphs.size()];
+        for (int i = 0; i < hs.length; i++) { hs[i] = graphs.get(i).handle; }
+        return new CortexGraph(null, NativeCortex.join(hs));
+    }
+
+    /** Sort (commands/utils/Sort.java:19-50): the same records in ascending k-mer order. */
+    public CortexGraph sorted() { return new CortexGraph(null, NativeCortex.sort(handle)); }
+
+    /** CortexGraphWriter over the whole graph (CortexGraphWriter.java:31-138). */
+    public void write(File out) { NativeCortex.writeGraph(handle, out.getAbsolutePath()); }
+
+    /** FindLowCoverage.execute :47-58: the records with coverage(0) below the limit. */
+    public CortexGraph findLowCoverage(int minCoverage) { return new CortexGraph(null, NativeCortex.findLowCoverage(handle, minCoverage)); }
+
+    /** FindShared.execute :60-109 with this = the pedigree graph: ROI records with coverage in a colour outside child / parents / ignored. */
+    public CortexGraph findShared(CortexGraph roi, int childColor, Collection<Integer> parentColors, Collection<Integer> ignoreColors) {
+        return new CortexGraph(null, NativeCortex.findShared(handle, roi.handle, childColor, toArray(parentColors), toArray(ignoreColors)));
+    }
+
+    /** RecoverExcludedKmers.execute :49-92 with this = the pedigree graph. */
+    public CortexGraph recoverExcludedKmers(CortexGraph dirty, int childColor) {
+        return new CortexGraph(null, NativeCortex.recoverExcludedKmers(handle, dirty.handle, childColor));
+    }
+
+    /** CovStats.execute :46-66: rows {coverage, count} in ascending coverage. */
+    public int[][] covStats(int childColor, Collection<Integer> parentColors) {
+        int[] flat = NativeCortex.covStats(handle, childColor, toArray(parentColors));
+        int[][] rows = new int[flat.length / 2][2];
+        for (int i = 0; i < rows.length; i++) { rows[i][0] = flat[2 * i]; rows[i][1] = flat[2 * i + 1]; }
+        return rows;
     }
 
     // ------------------------------------------------------------------------------------------ header getters

@@ -74,4 +74,17 @@ public final class NativeCortex {
     static native void containsWindows(long handle, byte[] seq, boolean[] outPresent);
     /** cc_pack_canonical: canonical packed words (Java long[] convention) and flags for every window of seq. */
     static native void packCanonical(int device, byte[] seq, int kmerSize, long[] outBinaryKmers, byte[] outFlags);
+
+    // next rows -------------------------------------------------------------------------------- cc_join / cc_sort / cc_write_graph
+    /** Each returns the handle of a NEW device-resident graph (dispose it). */
+    static native long join(long[] handles);
+    static native long sort(long handle);
+    static native void writeGraph(long handle, String outPath);
+
+    // pre-filters / recovery ------------------------------------------------------------------- cc_find_low_coverage / cc_find_shared / ...
+    static native long findLowCoverage(long roiHandle, int minCoverage);
+    static native long findShared(long graphHandle, long roiHandle, int child, int[] parents, int[] ignore);
+    static native long recoverExcludedKmers(long graphHandle, long dirtyHandle, int child);
+    /** {coverage0, count0, coverage1, count1, ...} in ascending coverage (cc_cov_stats). */
+    static native int[] covStats(long handle, int child, int[] parents);
 }

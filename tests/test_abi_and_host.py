@@ -160,3 +160,22 @@ def test_synth_header_matches_abi_parser():
     assert og.ok and og.h.num_records == 100 and og.h.record_size == 36 and og.h.data_offset % 16 != 0
     rc, _ = open_status(ctx)
     assert rc == (0 if HAS_GPU else N.CC_ERR_CUDA)              # parsed fine; only the device is missing
+
+
+def test_jni_shim_matches_the_java_natives_and_compiles_against_a_stub():
+    """The Java drop-in cannot be built here (no JDK): check what can be checked -- every `static native` of NativeCortex.java has
+    exactly one JNI function in the shim (and vice versa), every cc_* function the shim calls is declared in the header, and the shim
+    is valid C++ against a stand-in jni.h."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    java = open(os.path.join(root, "java/uk/ac/ox/well/cortexjdk/utils/io/graph/cortex/NativeCortex.java")).read()
+    shim_path = os.path.join(root, "corticall_b200/csrc/jni_shim.cpp")
+    shim = open(shim_path).read()
+    header = open(os.path.join(root, "include/corticall_cuda.h")).read()
+    natives = set(re.findall(r"static native [\w\[\]]+ (\w+)\(", java))
+    shims = set(re.findall(r"^JFN\([\w ]+, (\w+)\)", shim, flags=re.M))          # definitions only, not the macro itself
+    assert natives == shims and len(natives) >= 20, (natives ^ shims)
+    for fn in set(re.findall(r"\b(cc_\w+)\(", shim)):
+        assert re.search(r"\b%s\(" % fn, header), fn
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(root, "tests/jni_stub"), shim_path])
