@@ -179,3 +179,40 @@ def test_jni_shim_matches_the_java_natives_and_compiles_against_a_stub():
     for fn in set(re.findall(r"\b(cc_\w+)\(", shim)):
         assert re.search(r"\b%s\(" % fn, header), fn
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(root, "tests/jni_stub"), shim_path])
+
+
+def _build_abi_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "abi_example")
+    libdir = os.path.join(root, "corticall_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tools", "abi_example.c"),
+                           "-L", libdir, "-lcorticall_cuda", "-Wl,-rpath," + libdir, "-o", exe])
+    return exe, os.path.join(root, "tests", "golden", "two_short_contigs.ctx")
+
+
+def test_c_abi_from_plain_c_fails_loudly_without_a_device(tmp_path):
+    """The header is valid C11 and the library links from plain C; without a CUDA device the first compute call reports CC_ERR_CUDA
+    (there is no CPU fallback)."""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", os.path.join(root, "include", "corticall_cuda.h")])
+    exe, fixture = _build_abi_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: covered by the GPU test")
+    p = subprocess.run([exe, fixture, "0", "1"], capture_output=True, text=True)
+    assert p.returncode == 7 and "no CUDA device" in p.stderr and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.gpu
+def test_c_abi_from_plain_c_on_the_fixture(tmp_path):
+    """tools/abi_example.c on the reference's fixture: 66 records, 19 novel k-mers for colour 0 against colour 1 (47 the other
+    way round), each found again at the index the scan reported."""
+    import subprocess
+    exe, fixture = _build_abi_example(tmp_path)
+    for child, parent, novel in ((0, 1, 19), (1, 0, 47)):
+        p = subprocess.run([exe, fixture, str(child), str(parent)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert "version 6 k 31 words 1 colours 2 records 66" in p.stdout
+        assert "novel %d\n" % novel in p.stdout and "found %d of %d at the reported index" % (novel, novel) in p.stdout
