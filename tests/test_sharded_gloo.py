@@ -121,3 +121,29 @@ def test_sharded_lookup_exchange(tmp_path, world, skew):
         assert ok == "1", (r, nq, hits, sent)
         total_hits += int(hits)
     assert total_hits > 0
+
+
+def test_routed_block_layout_is_aligned_and_disjoint():
+    """Host-side layout of the symmetric block of the routed lookup (no device needed): every part starts 16-byte aligned, the
+    parts do not overlap, and a segment capacity is a multiple of 4 keys so that every (sub-range, source) segment of the inbox
+    starts 16-byte aligned whatever the wire width (the route kernel stores aligned 16-byte vectors)."""
+    from corticall_b200.host.sharded import RoutedLookup
+    for world in (1, 2, 3, 8):
+        for vsub in (1, 5, 8):
+            if world * vsub > 64:
+                continue
+            for k in (16, 31, 47, 63, 65, 128):
+                for cap_req in (1, 5, 4097, 19_535_346):
+                    cap = RoutedLookup.round_cap(cap_req)
+                    kw = (2 * k + 31) // 32
+                    assert cap % 4 == 0 and cap >= cap_req
+                    off_inbox, off_ret, off_counts, total = RoutedLookup._layout(world, vsub, cap, kw)
+                    assert off_inbox == 0 and off_ret % 16 == 0 and off_counts % 16 == 0 and total % 8 == 0
+                    assert off_ret >= vsub * world * cap * kw * 4                      # inbox fits before the results
+                    assert off_counts >= off_ret + world * vsub * cap * 4             # results fit before the counts
+                    assert total >= off_counts + 8 * world * vsub
+                    assert RoutedLookup.block_elems(world, cap_req, k, vsub) * 8 == total
+                    for v in range(vsub):                                              # sub-range blocks of the inbox
+                        assert (v * world * cap * kw * 4) % 16 == 0
+                        for src in range(world):                                       # and every segment inside them
+                            assert ((v * world + src) * cap * kw * 4) % 16 == 0
