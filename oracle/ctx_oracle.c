@@ -422,3 +422,101 @@ void orc_pack_windows(const uint8_t *seq, uint64_t len, uint32_t k, uint64_t *wo
     }
     free(canon); free(jl);
 }
+
+
+/* ------------------------------------------------------------------ scan-shaped pre-filters */
+#define ORC_MAX_WORDS 64          /* k <= 2048 */
+static int in_list(const int32_t *list, int n, int32_t v) {
+    for (int i = 0; i < n; ++i) if (list[i] == v) return 1;
+    return 0;
+}
+
+void orc_find_low_coverage(orc_graph *roi, int32_t min_coverage, uint8_t *written) {   /* FindLowCoverage.java:47-58 */
+    int64_t bk[ORC_MAX_WORDS]; int32_t *cov = malloc(4 * (roi->h.num_colors + 1)); uint8_t *ed = malloc(roi->h.num_colors + 1);
+    for (uint64_t i = 0; i < roi->h.num_records; ++i) {                 /* for (CortexRecord cr : ROI) */
+        orc_get_record(roi, i, bk, cov, ed);
+        if (cov[0] >= min_coverage) written[i] = 0;                      /* numKept++ */
+        else written[i] = 1;                                             /* cgw.addRecord(cr) */
+    }
+    free(cov); free(ed);
+}
+
+int orc_find_shared(orc_graph *graph, orc_graph *roi, int32_t child, const int32_t *parents, int nparents,
+                    const int32_t *ignore, int nignore, uint8_t *written) {            /* FindShared.java:60-109 */
+    int64_t bk[ORC_MAX_WORDS], gk[ORC_MAX_WORDS];
+    int32_t *rcov = malloc(4 * (roi->h.num_colors + 1)), *gcov = malloc(4 * (graph->h.num_colors + 1));
+    uint8_t *red = malloc(roi->h.num_colors + 1), *ged = malloc(graph->h.num_colors + 1);
+    uint8_t *kmer = malloc(roi->h.kmer_size + 1);
+    int rc = 0;
+    for (uint64_t i = 0; i < roi->h.num_records && rc == 0; ++i) {
+        orc_get_record(roi, i, bk, rcov, red);
+        orc_decode_binary_kmer(bk, roi->h.kmer_size, roi->h.kmer_bits, kmer);           /* rr.getCanonicalKmer() */
+        const int64_t at = orc_find_record(graph, kmer);                                /* GRAPH.findRecord(...) :65 */
+        if (at < 0) { rc = -1; break; }                                                 /* cr == null -> NPE at :67 */
+        orc_get_record(graph, (uint64_t)at, gk, gcov, ged);
+        int shared = 0;
+        for (uint32_t c = 0; c < graph->h.num_colors; ++c) {                            /* :67-73 */
+            if ((int32_t)c != child && !in_list(parents, nparents, (int32_t)c) && !in_list(ignore, nignore, (int32_t)c) && gcov[c] > 0) {
+                shared = 1;
+                break;
+            }
+        }
+        written[i] = (uint8_t)shared;                                                   /* second loop :95-104 writes the shared ones */
+    }
+    free(rcov); free(gcov); free(red); free(ged); free(kmer);
+    return rc;
+}
+
+uint64_t orc_recover_excluded_kmers(orc_graph *graph, orc_graph *dirty, int32_t child, uint8_t *written, int32_t *cov0) {
+    int64_t bk[ORC_MAX_WORDS], dk[ORC_MAX_WORDS];                                       /* RecoverExcludedKmers.java:49-92 */
+    int32_t *cov = malloc(4 * (graph->h.num_colors + 1)), *dcov = malloc(4 * (dirty->h.num_colors + 1));
+    uint8_t *ed = malloc(graph->h.num_colors + 1), *ded = malloc(dirty->h.num_colors + 1);
+    uint8_t *kmer = malloc(graph->h.kmer_size + 1);
+    uint64_t recovered = 0;
+    for (uint64_t i = 0; i < graph->h.num_records; ++i) {
+        orc_get_record(graph, i, bk, cov, ed);
+        written[i] = 0;
+        cov0[i] = cov[0];
+        if (cov[child] > 0) { written[i] = 1; continue; }                              /* :50-52 */
+        int others = 0;
+        for (uint32_t c = 0; c < graph->h.num_colors; ++c)                              /* :55-59 */
+            if ((int32_t)c != child && cov[c] > 0) ++others;
+        if (others > 0) {
+            orc_decode_binary_kmer(bk, graph->h.kmer_size, graph->h.kmer_bits, kmer);
+            const int64_t at = orc_find_record(dirty, kmer);                            /* DIRTY.findRecord(cr.getCanonicalKmer()) :63 */
+            if (at >= 0) {
+                orc_get_record(dirty, (uint64_t)at, dk, dcov, ded);
+                if (dcov[0] > 0) {                                                      /* :65 */
+                    cov[child] = dcov[0];                                               /* coverages[childColor] = dr.getCoverage(0) :74 */
+                    written[i] = 2;
+                    cov0[i] = cov[0];                                                   /* the writer emits colour 0 only (1-colour header) */
+                    ++recovered;
+                }
+            }
+        }
+    }
+    free(cov); free(dcov); free(ed); free(ded); free(kmer);
+    return recovered;
+}
+
+void orc_cov_stats_pairs(orc_graph *graph, int32_t child, const int32_t *parents, int nparents, int32_t *key, int32_t *weight) {
+    int64_t bk[ORC_MAX_WORDS];                                                          /* CovStats.java:46-66 */
+    int32_t *cov = malloc(4 * (graph->h.num_colors + 1));
+    uint8_t *ed = malloc(graph->h.num_colors + 1);
+    for (uint64_t i = 0; i < graph->h.num_records; ++i) {
+        orc_get_record(graph, i, bk, cov, ed);
+        int is_in_child = cov[child] > 0;                                               /* :47 */
+        int np = 0, nc = 0;
+        for (uint32_t c = 0; c < graph->h.num_colors; ++c) {                            /* :51-57 */
+            if (cov[c] > 0) {
+                if (child == (int32_t)c) is_in_child = 1;
+                else if (in_list(parents, nparents, (int32_t)c)) ++np;
+                else ++nc;
+            }
+        }
+        const int counts = is_in_child && np > 0 && nc > 0;                            /* :61 */
+        key[i] = counts ? cov[child] : 0;
+        weight[i] = counts ? np + nc : 0;
+    }
+    free(cov); free(ed);
+}

@@ -8,7 +8,10 @@
  * Parity status: PINNED.  The restatement is checked (tests/test_oracle.py) against the reference's
  * own golden vectors: the 66-record table of CortexGraphTest.java:71-136, the find hits/miss of
  * :310-331, the encode/decode round trip of :267-280, SequenceUtilsTest.java:19-72 and the
- * TempGraphAssembler record strings of TraversalEngineTest.java:48-95.  The reference itself (Java)
+ * TempGraphAssembler record strings of TraversalEngineTest.java:48-95.  The novelty predicate and the
+ * pre-filter commands (FindLowCoverage, FindShared, RecoverExcludedKmers, CovStats) have NO tests in the
+ * reference: for them parity is unpinned by reference vectors and rests on the cited source lines, a
+ * hand-computed case and the agreement of this C restatement with the numpy one.  The reference itself (Java)
  * cannot be compiled or run in this image (no JDK, jars not vendored), so there is no oracle/_ref.
  *
  * Path prefix used in citations:  S/ = public/java/src/uk/ac/ox/well/cortexjdk/
@@ -105,6 +108,24 @@ void orc_find_batch(orc_graph *g, const uint8_t *kmers, uint64_t nq, int64_t *ou
 /* canonicalise + 2-bit pack every window: words[(len-k+1)*s] NATIVE order (word0 most significant,
  * == byteswap of the Java long), flags bit0 flipped, bit1 not packable (non-ACGT; words zeroed). */
 void orc_pack_windows(const uint8_t *seq, uint64_t len, uint32_t kmer_size, uint64_t *words, uint8_t *flags);
+
+/* ---- scan-shaped pre-filters, restated record by record through orc_get_record / orc_find_record.
+ * Each fills one decision per record of the iterated graph; the tests assemble the output files from them and compare
+ * with the numpy restatement (oracle_np.py), which was written independently.  parents / ignore may hold -1 (a sample
+ * name that did not resolve: the reference's HashSet<Integer> then never matches). */
+/* S/commands/prefilter/FindLowCoverage.java:47-58: written[i] = !(coverage(0) >= min_coverage) */
+void orc_find_low_coverage(orc_graph *roi, int32_t min_coverage, uint8_t *written);
+/* S/commands/prefilter/FindShared.java:60-109: written[i] = ROI record i is shared.  Returns -1 when GRAPH.findRecord
+ * gives null for a ROI k-mer (NullPointerException at :67 in the reference), else 0. */
+int orc_find_shared(orc_graph *graph, orc_graph *roi, int32_t child, const int32_t *parents, int nparents,
+                    const int32_t *ignore, int nignore, uint8_t *written);
+/* S/commands/discover/recover/RecoverExcludedKmers.java:49-92: written[i] = 1 (as is) / 2 (recovered) / 0, cov0[i] =
+ * coverages[0] of the record that CortexGraphWriter.addRecord receives (after coverages[child] = dirty coverage).
+ * Returns the number of recovered records. */
+uint64_t orc_recover_excluded_kmers(orc_graph *graph, orc_graph *dirty, int32_t child, uint8_t *written, int32_t *cov0);
+/* S/commands/utils/CovStats.java:46-66: per record, key[i] = coverage(child) if the record counts (else 0) and
+ * weight[i] = numberOfParents + numberOfChildren. */
+void orc_cov_stats_pairs(orc_graph *graph, int32_t child, const int32_t *parents, int nparents, int32_t *key, int32_t *weight);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,11 @@ def lib() -> C.CDLL:
         L.orc_find_windows.argtypes = [C.POINTER(OrcGraph), u8p, C.c_uint64, i64p]; L.orc_find_windows.restype = None
         L.orc_find_batch.argtypes = [C.POINTER(OrcGraph), u8p, C.c_uint64, i64p]; L.orc_find_batch.restype = None
         L.orc_pack_windows.argtypes = [u8p, C.c_uint64, C.c_uint32, u64p, u8p]; L.orc_pack_windows.restype = None
+        G = C.POINTER(OrcGraph)
+        L.orc_find_low_coverage.argtypes = [G, C.c_int32, u8p]; L.orc_find_low_coverage.restype = None
+        L.orc_find_shared.argtypes = [G, G, C.c_int32, i32p, C.c_int, i32p, C.c_int, u8p]; L.orc_find_shared.restype = C.c_int
+        L.orc_recover_excluded_kmers.argtypes = [G, G, C.c_int32, u8p, i32p]; L.orc_recover_excluded_kmers.restype = C.c_uint64
+        L.orc_cov_stats_pairs.argtypes = [G, C.c_int32, i32p, C.c_int, i32p, i32p]; L.orc_cov_stats_pairs.restype = None
         _LIB = L
     return _LIB
 
@@ -125,6 +130,42 @@ class Graph:
         out = np.empty(n * osz, dtype=np.uint8); idx = np.empty(n, dtype=np.uint64)
         cnt = lib().orc_find_rois(C.byref(self.g), child, _p(par), len(par), _p(out), _p(idx), n, int(faithful))
         return out[:cnt * osz].tobytes(), idx[:cnt].copy()
+
+
+def _i32(a):
+    return np.ascontiguousarray(list(a) if not isinstance(a, np.ndarray) else a, dtype=np.int32)
+
+
+def find_low_coverage_mask(roi: "Graph", min_coverage: int) -> np.ndarray:
+    out = np.zeros(max(roi.h.num_records, 1), dtype=np.uint8)
+    lib().orc_find_low_coverage(C.byref(roi.g), int(min_coverage), _p(out))
+    return out[:roi.h.num_records].astype(bool)
+
+
+def find_shared_mask(graph: "Graph", roi: "Graph", child: int, parents, ignore):
+    """mask of the shared ROI records, or None when the reference would hit its NullPointerException."""
+    out = np.zeros(max(roi.h.num_records, 1), dtype=np.uint8)
+    pa, ig = _i32(parents), _i32(ignore)
+    rc = lib().orc_find_shared(C.byref(graph.g), C.byref(roi.g), int(child), _p(pa) if pa.size else None, pa.size,
+                               _p(ig) if ig.size else None, ig.size, _p(out))
+    return None if rc else out[:roi.h.num_records].astype(bool)
+
+
+def recover_excluded_kmers_decisions(graph: "Graph", dirty: "Graph", child: int):
+    n = graph.h.num_records
+    written = np.zeros(max(n, 1), dtype=np.uint8)
+    cov0 = np.zeros(max(n, 1), dtype=np.int32)
+    rec = lib().orc_recover_excluded_kmers(C.byref(graph.g), C.byref(dirty.g), int(child), _p(written), _p(cov0))
+    return written[:n], cov0[:n], int(rec)
+
+
+def cov_stats_pairs(graph: "Graph", child: int, parents):
+    n = graph.h.num_records
+    key = np.zeros(max(n, 1), dtype=np.int32)
+    weight = np.zeros(max(n, 1), dtype=np.int32)
+    pa = _i32(parents)
+    lib().orc_cov_stats_pairs(C.byref(graph.g), int(child), _p(pa) if pa.size else None, pa.size, _p(key), _p(weight))
+    return key[:n], weight[:n]
 
 
 def find_rois_body(body: np.ndarray, n: int, k: int, s: int, c: int, child: int, parents, faithful=False, cap=None):

@@ -388,3 +388,56 @@ def test_prefilter_oracles_hand_checked():
     # CovStats: only ACGTA counts (child 9 > 0, one parent, one other): weight 2
     assert onp.cov_stats(g, 0, [1, 2]) == [(9, 2)]
     assert onp.cov_stats(g, 1, [0]) == [(1, 2)]              # child = mom, parent = kid: only ACGTA (kid + ref); GATTA's kid coverage is negative
+
+
+@pytest.mark.parametrize("k,c,n", [(31, 3, 3000), (47, 4, 4000), (63, 6, 1500), (95, 2, 800)])
+def test_prefilter_oracles_c_and_numpy_agree(k, c, n):
+    """The two independent restatements of FindLowCoverage / FindShared / RecoverExcludedKmers / CovStats -- the record-by-record C
+    loops (through the oracle's own getRecord / findRecord) and the vectorised numpy ones -- give the same files and tables on
+    synthetic graphs with adversarial coverages (>= 2^31, i.e. negative Java ints)."""
+    ctx = synth.make_ctx_file(500 + k, n, k, c, novel_permille=60, adv_period=37)
+    hg = onp.parse_header(ctx)
+    g = onp.records_view(ctx, hg)
+    G = orc.Graph(ctx)
+    rng = np.random.default_rng(k)
+    # a one-colour ROI graph: a subset of the records with their colour-0 coverage
+    pick = np.sort(rng.choice(n, n // 4, replace=False))
+    roi_rec = np.zeros(len(pick), dtype=onp.record_dtype(hg["kmer_bits"], 1))
+    roi_rec["kmer"], roi_rec["cov"][:, 0], roi_rec["edges"][:, 0] = g["kmer"][pick], g["cov"][pick, 0], g["edges"][pick, 0]
+    roi = onp.write_header(k, hg["kmer_bits"], [hg["colors"][0]]) + roi_rec.tobytes()
+    R = orc.Graph(roi)
+    hr = onp.parse_header(roi)
+    for m in (1, 7, 40, -3):
+        want = onp.find_low_coverage(roi, m)
+        mask = orc.find_low_coverage_mask(R, m)
+        assert onp._rewritten_header(hr, hr["colors"]) + roi_rec[mask].tobytes() == want
+    for parents, ignore in (([1], []), ([1, 2], [c - 1]), ([-1], [-1]), ([], list(range(1, c)))):
+        want = onp.find_shared(ctx, roi, 0, parents, ignore)
+        mask = orc.find_shared_mask(G, R, 0, parents, ignore)
+        assert mask is not None and onp._rewritten_header(hr, hr["colors"]) + roi_rec[mask].tobytes() == want
+    stray = np.zeros(1, dtype=onp.record_dtype(hg["kmer_bits"], 1)); stray["kmer"][0, -1] = 2
+    stray_file = onp.write_header(k, hg["kmer_bits"], [hg["colors"][0]]) + stray.tobytes()
+    if orc.Graph(ctx).find_record(onp.decode_kmers(stray["kmer"], k)[0].tobytes()) < 0:
+        assert orc.find_shared_mask(G, orc.Graph(stray_file), 0, [1], []) is None
+        with pytest.raises(KeyError):
+            onp.find_shared(ctx, stray_file, 0, [1], [])
+    # dirty graph: every third record plus coverage 0 / small / negative
+    dpick = np.arange(0, n, 3)
+    drec = np.zeros(len(dpick), dtype=onp.record_dtype(hg["kmer_bits"], 1))
+    drec["kmer"] = g["kmer"][dpick]
+    drec["cov"][:, 0] = rng.integers(0, 4, len(dpick)); drec["cov"][::11, 0] = 0x80000001
+    for child in (0, 1):
+        dirty = onp.write_header(k, hg["kmer_bits"], [hg["colors"][child]]) + drec.tobytes()
+        want, nrec = onp.recover_excluded_kmers(ctx, dirty, child)
+        written, cov0, crec = orc.recover_excluded_kmers_decisions(G, orc.Graph(dirty), child)
+        out = np.zeros(int((written > 0).sum()), dtype=onp.record_dtype(hg["kmer_bits"], 1))
+        out["kmer"], out["cov"][:, 0], out["edges"][:, 0] = g["kmer"][written > 0], cov0[written > 0].view(np.uint32), g["edges"][written > 0, 0]
+        assert crec == nrec == int((written == 2).sum()) and nrec > 0
+        assert onp._rewritten_header(hg, [hg["colors"][child]]) + out.tobytes() == want
+    for child, parents in ((0, [1, 2] if c > 2 else [1]), (1, [0]), (0, [-1]), (c - 1, [0, 1])):
+        key, weight = orc.cov_stats_pairs(G, child, parents)
+        hist = {}
+        for kk, ww in zip(key.tolist(), weight.tolist()):
+            if kk:
+                hist[kk] = hist.get(kk, 0) + ww
+        assert sorted(hist.items()) == onp.cov_stats(ctx, child, [p for p in parents])
