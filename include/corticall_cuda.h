@@ -255,7 +255,13 @@ CC_API uint64_t cc_launch_count(void);
 /* Device pointer / size of the resident body and key column (benchmarks, tests). */
 CC_API int cc_device_body(const cc_graph *g, const void **dev_body, uint64_t *bytes);
 CC_API int cc_device_keys(cc_graph *g, const uint64_t **dev_keys, uint64_t *n);
-/* Tuning knobs: "scan_stages", "scan_tile_bytes", "scan_ctas_per_sm", "index_bits", "lookup_block". */
+/* Process-wide tuning knobs (benchmarks and sweeps; the defaults are the measured optima):
+ *   scan:    "scan_stages", "scan_tile_bytes", "scan_ctas_per_sm", "scan_chunk_tiles", "scan_stage_buf_bytes", "scan_fast", "host_chunk_mb"
+ *   index:   "index_bits" (log2 of the bucket count, 0 = auto), "index_buckets" (exact count, overrides index_bits)
+ *   lookups: "lookup_queries_per_thread", "mlp_grid_per_sm", "lookup_l2_hints" (bit0 keys evict-first, bit1 table evict-last),
+ *            "rows_fused" (ASCII lists: 1 = pack + search in one kernel), "rows_rpt2_max_k"
+ *   routed:  "route_blocks_per_sm", "routed_search_blocks_per_sm", "gather_blocks_per_sm"
+ * Unknown names fail with CC_ERR_ARG. */
 CC_API int cc_set_option(const char *name, int64_t value);
 
 #ifdef __cplusplus
