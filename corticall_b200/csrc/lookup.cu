@@ -1,5 +1,4 @@
-// lookup.cu -- K3 (canonicalise + 2-bit pack) and K4 (batched sorted-array lookups), plus the
-// multi-GPU bucket / scatter helpers around the all-to-all.
+// lookup.cu -- K3 (canonicalise + 2-bit pack), K4 (batched sorted-array lookups) and the multi-GPU legs around K4.
 //
 // Reference semantics reproduced (S/ = public/java/src/uk/ac/ox/well/cortexjdk/):
 //   canonical orientation   S/utils/sequence/SequenceUtils.java:206-225  (ASCII, signed bytes, tie -> forward)
@@ -10,13 +9,21 @@
 //                           duplicate-free graph with N >= 3 that is "index of the exact match, else null",
 //                           and any query holding a byte outside ACGT (N, lower case) is a miss.
 //
-// B200 design.  K3: a CTA stages a tile of the sequence in shared memory, converts it once into a 2-bit
-// big-endian bit stream plus "not ACGTacgt" and "lower case" bit masks, and every thread cuts its window
-// out of the streams with funnel shifts (5 LDS for k=47), reverse-complements in registers (brev + pair
-// swap + multiword shift) and keeps the smaller.  K4: the key column (records stripped of coverage and
-// edges, 8s bytes per key) is searched through a prefix table over the top `bits` bits of the k-mer
-// (lower bounds per prefix, sized to stay L2-resident), so a lookup costs one table read plus one short
-// bucket scan issued as independent loads instead of ~27 dependent probes.
+// Sections (in file order):
+//   tile staging + window_canonical      sliding windows of a sequence (seq_kernel): 2-bit stream + masks in shared memory
+//   key column access + prefix table     IndexView, key_bucket (equal slices of the array's OWN key range), L2 policies, lookup_mlp
+//   seq_kernel / find_packed kernels     K3 on windows (optionally fused with K4), K4 on packed queries
+//   rows_kernel                          K3 (+K4) on independent k-byte rows: TMA-staged tiles, byte-parallel conversion,
+//                                        warp-cooperative exact path for rows with N / lower case
+//   routed lookups over peer memory      route_kernel (owner + P2P stores), find_routed_kernel, gather_routed_kernel (P2P pull)
+//   index construction, sorted-merge support, NCCL-formulation helpers (bucket / scatter), launchers
+//
+// B200 design in one paragraph.  K3: the sequence is converted once per tile into a 2-bit big-endian bit stream in shared
+// memory and every thread cuts its k-mer out with funnel shifts, reverse-complements in registers (brev + pair swap +
+// multiword shift) and keeps the smaller.  K4: the key column (records stripped of coverage and edges, 8s bytes per key) is
+// searched through a prefix table with about one key per bucket, so a lookup costs one table sector plus one key sector,
+// issued as independent loads with several queries in flight per thread, instead of ~27 dependent probes; it is bound by
+// DRAM random access.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
