@@ -231,7 +231,8 @@ void destroy(cc_graph *g) {
     if (g->stream) cudaStreamSynchronize(g->stream);
     g->scan_ws.release();
     if (g->index.keys) cudaFree(g->index.keys);
-    if (g->index.table) cudaFree(g->index.table);
+    if (g->index.lines) cudaFree(g->index.lines);
+    if (g->index.bins) cudaFree(g->index.bins);
     if (g->novel_buf) cudaFree(g->novel_buf);
     if (g->novel_idx) cudaFree(g->novel_idx);
     if (g->dev_alloc) {
@@ -356,9 +357,8 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "scan_tile_bytes")) o.scan_tile_bytes = (int)value;
     else if (!strcmp(name, "scan_ctas_per_sm")) o.scan_ctas_per_sm = (int)value;
     else if (!strcmp(name, "index_bits")) o.index_bits = (int)value;
-    else if (!strcmp(name, "index_buckets")) o.index_buckets = (int)value;
-    else if (!strcmp(name, "lookup_block")) o.lookup_block = (int)value;
-    else if (!strcmp(name, "lookup_queries_per_thread")) o.lookup_queries_per_thread = (int)value;
+    else if (!strcmp(name, "index_fill_pct")) o.index_fill_pct = (int)value;
+    else if (!strcmp(name, "find_bins_smem")) o.find_bins_smem = (int)value;
     else if (!strcmp(name, "rows_fused")) o.rows_fused = (int)value;
     else if (!strcmp(name, "rows_rpt2_max_k")) o.rows_rpt2_max_k = (int)value;
     else if (!strcmp(name, "route_blocks_per_sm")) o.route_blocks_per_sm = (int)value;
@@ -369,7 +369,6 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;
     else if (!strcmp(name, "scan_stage_buf_bytes")) o.scan_stage_buf_bytes = (int)value;
     else if (!strcmp(name, "scan_chunk_tiles")) o.scan_chunk_tiles = (int)value;
-    else if (!strcmp(name, "mlp_grid_per_sm")) o.mlp_grid_per_sm = (int)value;
     else if (!strcmp(name, "lookup_l2_hints")) o.lookup_l2_hints = (int)value;
     else return fail(CC_ERR_ARG, "unknown option '%s'", name);
     return CC_OK;

@@ -31,16 +31,14 @@ struct Options {
     int scan_stages = 3;
     int scan_tile_bytes = 32768;
     int scan_ctas_per_sm = 2;
-    int index_bits = 0;          // 0 = auto
-    int index_buckets = 0;       // exact bucket count of the prefix table (overrides index_bits; 0 = 2^bits)
-    int lookup_block = 256;
-    int lookup_queries_per_thread = 2;
+    int index_bits = 0;          // log2 of the number of bins of the lookup index (0 = auto: ~256 keys per bin, at most 2^13)
+    int index_fill_pct = 50;     // average fill of a bucket line, in percent of its capacity
     int rows_rpt2_max_k = 32;    // cc_pack_kmers: two rows per thread (512-row tiles) up to this k, else one
-    int lookup_l2_hints = 3;     // bit0: key loads evict-first in L2, bit1: prefix-table loads evict-last
-    int mlp_grid_per_sm = 8;     // find_packed_mlp_kernel: CTAs per SM (0 = resident CTAs only; measured 10 % slower)
+    int lookup_l2_hints = 1;     // bit0: line loads evict-first in L2
+    int find_bins_smem = 1;      // packed / routed search: stage the bin table in shared memory
     int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1
-    int routed_search_blocks_per_sm = 3;  // grid of find_routed_kernel per SM (3 = the resident CTAs; measured best of 3/4/8/16)
+    int routed_search_blocks_per_sm = 0;  // cap on the CTAs of find_routed_kernel per SM (0 = all resident CTAs)
     int gather_blocks_per_sm = 16;  // cap on resident gather CTAs per SM
     int host_chunk_mb = 64;      // cc_find_novel_host chunk size
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
@@ -88,11 +86,14 @@ struct ScanWorkspace {
 // ------------------------------------------------------------------ lookup index
 struct LookupIndex {
     uint64_t *keys = nullptr;     // [n*s] native words, word 0 first
-    uint32_t *table = nullptr;    // [nbuckets + 2] lower bounds over the array's own key range
-    int bits = 0;                 // requested log2 of the bucket count
+    void *lines = nullptr;        // [nlines] 64-byte bucket lines (lookup.cu: "the lookup index")
+    void *bins = nullptr;         // [nbins] {first line, lines} per equal slice of the array's own key range
+    uint64_t nlines = 0;
     uint64_t base = 0;            // top 64 bits of the first key
-    uint64_t scale = 0;           // see key_bucket
-    uint32_t norm = 0, nbuckets = 1;
+    uint64_t span = 0;            // top 64 bits of the last key - base
+    uint64_t scale = 0;           // see key_bin
+    uint32_t norm = 0, nbins = 1;
+    uint32_t pad[8] = {};         // wire form of the largest key (fills unused slots)
     bool built = false;
     bool sorted = true;
     uint64_t unsorted_at = 0;

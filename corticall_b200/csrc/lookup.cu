@@ -156,7 +156,7 @@ __device__ __forceinline__ uint32_t window_canonical(const SeqTile &t, uint32_t 
     return flags | (flip ? 1u : 0u);
 }
 
-// ------------------------------------------------------------------ key column access + prefix table
+// ------------------------------------------------------------------ key column access
 template <int S>
 __device__ __forceinline__ void load_key(const uint64_t *__restrict__ keys, uint64_t i, uint64_t (&out)[S]) {
     if (S == 2) {
@@ -168,46 +168,68 @@ __device__ __forceinline__ void load_key(const uint64_t *__restrict__ keys, uint
     }
 }
 
+// ------------------------------------------------------------------ the lookup index: 64-byte bucket lines
+// A lookup must cost ONE random DRAM access.  The sorted keys are laid out a second time as an order-preserving hash
+// table of 64-byte lines (one DRAM atom / two L2 sectors): line = f(key) with f monotone, so a line holds a contiguous run
+// of the sorted array and "base index + slot" is the record index.
+//   f: the array's OWN key range [first key, last key] is cut into `nbins` equal slices (a k-mer-range shard covers only
+//      1/world of the key space); bin b owns bins[b].y consecutive lines starting at bins[b].x, sized from the number of
+//      keys that fall into it (lines = ceil(keys / fill)), and a key's line inside its bin is the equal slice of the bin
+//      it falls into.  The bin table is what adapts the table to the key density (canonical k-mers are twice as dense at
+//      the low end of the key space as on average and vanish at the high end); it is a few KB to 64 KB and lives in shared
+//      memory in the search kernels.
+//   line: 16 32-bit words = the base index (position of the line's first key in the sorted array) + CAP keys in the wire
+//      format (KW = ceil(2k/32) words, most significant first: 12 bytes at k = 47), ascending; unused slots hold the
+//      LARGEST key of the array (it sorts after every real key of the line, can only equal a query that maps to the last
+//      line, where it is real, and makes "last slot < query" the exact test for "the bucket may continue").
+//   overflow: a bucket with more than CAP keys continues in the key column at base + CAP (rare by construction: fill = 50 %
+//      of CAP on average); the search reads on from there.
+// The word layout inside a line is chosen so that four lanes, each holding 16 bytes of the line, can compare without
+// moving key words between lanes (LineLayout).
+constexpr uint32_t kLineWords = 16;
+constexpr uint32_t kMaxBinsLog2 = 13;          // 8192 bins x 8 bytes = 64 KB of shared memory
+constexpr uint32_t kMiss32 = 0xffffffffu;
+
+template <int KW>
+struct LineLayout {
+    static constexpr int CAP = (KW == 3) ? 5 : (KW == 2) ? 7 : (KW == 4) ? 3 : 15 / KW;
+    static constexpr int kBaseWord = (KW == 3) ? 3 : 0;
+    // word index of word p (0 = most significant) of slot t
+    __host__ __device__ static constexpr int word(int t, int p) {
+        return KW == 3 ? (t < 4 ? 4 * t + p : 4 * (p + 1) + 3)       // lane j: key j in x,y,z; w = base (lane 0) or word j-1 of key 4
+             : KW == 2 ? 2 + 2 * t + p                                // lane 0: base, -, key 0; lane j: keys 2j-1, 2j
+             : KW == 4 ? 4 * (t + 1) + p                              // lane 0: base; lane j: key j-1
+                       : 1 + t * KW + p;
+    }
+};
+
 struct IndexView {
-    const uint64_t *keys;
-    const uint32_t *table;      // nbuckets + 2 lower bounds; bucket `nbuckets` is the empty "outside the range" bucket
+    const uint64_t *keys;       // key column [n * s] (binary search, bucket overflow)
+    const uint4 *lines;         // [nlines] 64-byte lines
+    const uint2 *bins;          // [nbins] {first line, lines} (global copy; kernels may stage it in shared memory)
     uint64_t n;
     uint64_t first_index;
     uint64_t base;              // top 64 bits (left-aligned) of the first key of THIS array
-    uint64_t scale;             // bucket = mulhi((top64(q) - base) << norm, scale): exactly nbuckets equal slices of the span
-    uint32_t nbuckets;
+    uint64_t span;              // top64(last key) - base
+    uint64_t scale;             // bin.frac = ((top64(q) - base) << norm) * scale as a 64.64 fixed-point number
+    uint32_t nbins;
     uint32_t norm;
     uint32_t k;
-    uint32_t hints;             // bit0: key loads evict-first in L2, bit1: table loads evict-last (keep the table resident)
+    uint32_t hints;             // bit0: line loads evict-first in L2 (touched at random, never again)
+    uint32_t pad[8];            // wire form of the largest key
 };
 
-// L2 cache policies for the search: the key column is touched at random and never again (evict first), the prefix table
-// is the only structure with reuse (evict last).
-struct LookupPolicies {
-    uint64_t keys, table;
-};
-__device__ __forceinline__ LookupPolicies make_lookup_policies(uint32_t hints) {
-    LookupPolicies p;
-    if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.keys));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.keys));
-    if (hints & 2u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.table));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.table));
+__device__ __forceinline__ uint64_t make_line_policy(uint32_t hints) {
+    uint64_t p;
+    if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t policy) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+__device__ __forceinline__ uint4 ld_line16(const uint4 *p, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
     return v;
-}
-template <int S>
-__device__ __forceinline__ void load_key_hint(const uint64_t *__restrict__ keys, uint64_t i, uint64_t (&out)[S], uint64_t policy) {
-    if (S == 2) {
-        asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(out[0]), "=l"(out[1 % S]) : "l"(keys + 2 * i), "l"(policy));
-    } else {
-#pragma unroll
-        for (int w = 0; w < S; ++w)
-            asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(out[w]) : "l"(keys + i * S + w), "l"(policy));
-    }
 }
 
 // The 64 most significant bits of the 2k-bit key, left-aligned.
@@ -218,21 +240,32 @@ __host__ __device__ __forceinline__ uint64_t key_top64(const uint64_t *q, uint32
     return (q[0] << (64u - top_bits)) | (q[S > 1 ? 1 : 0] >> top_bits);
 }
 
-// Bucket of a key in the prefix table.  The table spans only [first key, last key] of the array it indexes (a k-mer-range
-// shard covers 1/world of the key space; a table over the global top bits would leave most of its buckets empty and the
-// rest world times too long).  Keys outside the span land in the empty bucket `nbuckets`.
+// Bin of a key and its position inside the bin as a 64-bit fraction.  False: the key lies outside [first key, last key]
+// of this array (as far as its top 64 bits tell) and cannot match.
 template <int S>
-__device__ __forceinline__ uint32_t key_bucket(const IndexView &ix, const uint64_t (&q)[S]) {
+__device__ __forceinline__ bool key_bin(const IndexView &ix, const uint64_t (&q)[S], uint32_t &bin, uint64_t &frac) {
     const uint64_t t = key_top64<S>(q, ix.k);
-    if (t < ix.base) return ix.nbuckets;
+    if (t < ix.base) return false;
     const uint64_t d = t - ix.base;
-    if ((d >> (63u - ix.norm)) > 1u) return ix.nbuckets;        // d << norm would overflow: beyond the last key
-    const uint64_t b = __umul64hi(d << ix.norm, ix.scale);
-    return b < ix.nbuckets ? (uint32_t)b : ix.nbuckets;
+    if (d > ix.span) return false;
+    const uint64_t x = d << ix.norm;                           // span << norm does not overflow, so neither does this
+    bin = (uint32_t)__umul64hi(x, ix.scale);
+    frac = x * ix.scale;
+    return true;
+}
+// `bins` may point to shared or global memory.
+template <int S>
+__device__ __forceinline__ bool key_line(const IndexView &ix, const uint2 *bins, const uint64_t (&q)[S], uint32_t &line) {
+    uint32_t bin;
+    uint64_t frac;
+    if (!key_bin<S>(ix, q, bin, frac)) return false;
+    const uint2 b = bins[bin];
+    line = b.x + (uint32_t)__umul64hi(frac, (uint64_t)b.y);
+    return true;
 }
 
 constexpr int kMaxShards = 64;
-constexpr uint32_t kLinear = 8;     // bucket remainder scanned with independent loads
+constexpr uint32_t kLinear = 8;     // range remainder scanned with independent loads
 
 // Index of the exact match of q in keys[lo, hi) (lowest on duplicates), or -1.
 template <int S>
@@ -260,17 +293,158 @@ __device__ __forceinline__ int64_t search_range(const uint64_t *__restrict__ key
     return res;
 }
 
+// Continuation of a bucket in the key column: every key before `lo` is < q; the first key >= q decides.
 template <int S>
-__device__ __forceinline__ int64_t lookup_bucketed(const IndexView &ix, const uint64_t (&q)[S]) {
-    const uint32_t p = key_bucket<S>(ix, q);
-    const uint64_t lo = __ldg(ix.table + p), hi = __ldg(ix.table + p + 1);
-    const int64_t r = search_range<S>(ix.keys, lo, hi, q);
-    return r < 0 ? r : r + (int64_t)ix.first_index;
+__device__ __noinline__ int64_t search_overflow(const uint64_t *__restrict__ keys, uint64_t lo, uint64_t n, const uint64_t (&q)[S]) {
+#pragma unroll 1
+    for (int step = 0; step < 8 && lo < n; ++step, ++lo) {
+        uint64_t kk[S];
+        load_key<S>(keys, lo, kk);
+        if (!words_less<S>(kk, q)) return words_equal<S>(kk, q) ? (int64_t)lo : -1;
+    }
+    if (lo >= n) return -1;
+    return search_range<S>(keys, lo, n, q);      // a pathologically long bucket: bounded by log2(n) probes
 }
+
 template <int S>
 __device__ __forceinline__ int64_t lookup_bsearch(const IndexView &ix, const uint64_t (&q)[S]) {
     const int64_t r = search_range<S>(ix.keys, 0, ix.n, q);
     return r < 0 ? r : r + (int64_t)ix.first_index;
+}
+
+template <int S, int KW>
+__device__ __forceinline__ void key_to_wire(const uint64_t (&q)[S], uint32_t *dst) {
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const int idx = KW - 1 - j;                       // 32-bit word index counted from the least significant end
+        const uint64_t w = q[S - 1 - idx / 2];
+        dst[j] = (idx & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+    }
+}
+
+// One query per thread, the whole line in one thread (any KW): the plain form of the line search, used where the
+// threads of a warp do not walk in step (sorted pass) and for key widths without a cooperative layout.
+template <int S, int KW>
+__device__ __forceinline__ int64_t lookup_lines_thread(const IndexView &ix, const uint2 *bins, uint64_t pol, const uint64_t (&q)[S]) {
+    using LL = LineLayout<KW>;
+    uint32_t line;
+    if (ix.n == 0 || !key_line<S>(ix, bins, q, line)) return -1;
+    uint32_t w[kLineWords];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint4 v = ld_line16(ix.lines + (size_t)line * 4 + c, pol);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    uint32_t qw[KW];
+    key_to_wire<S, KW>(q, qw);
+    int slot = -1;
+#pragma unroll
+    for (int t = LL::CAP - 1; t >= 0; --t) {
+        bool eq = true;
+#pragma unroll
+        for (int p = 0; p < KW; ++p) eq &= (w[LL::word(t, p)] == qw[p]);
+        if (eq) slot = t;
+    }
+    const uint64_t base = w[LL::kBaseWord];
+    if (slot >= 0) return (int64_t)(base + (uint64_t)slot + ix.first_index);
+    bool less = false, decided = false;                    // last slot < q ?
+#pragma unroll
+    for (int p = 0; p < KW; ++p) {
+        const uint32_t a = w[LL::word(LL::CAP - 1, p)];
+        if (!decided && a != qw[p]) { decided = true; less = a < qw[p]; }
+    }
+    if (!less) return -1;
+    const int64_t r = search_overflow<S>(ix.keys, base + LL::CAP, ix.n, q);
+    return r < 0 ? r : r + (int64_t)ix.first_index;
+}
+
+// The line search by a whole warp, one query per lane (all 32 lanes must call it; `live` = this lane has a query).
+// Four lanes share a line: lane j of a quad loads bytes [16j, 16j + 16) -- one LDG.128 per warp fetches 8 whole lines (8
+// wavefronts instead of the 32 a thread-per-line load costs, which would bound the kernel on the L1 wavefront rate before
+// DRAM) -- and the quad works through its own four queries in four rounds.  All four loads are issued before the first
+// compare.  Layouts exist for KW = 2, 3, 4 (k = 17..64); other widths take the per-thread form.
+template <int S, int KW>
+__device__ __forceinline__ int64_t lookup_lines_warp(const IndexView &ix, const uint2 *bins, uint64_t pol, const uint64_t (&q)[S], bool live) {
+    if constexpr (KW < 2 || KW > 4) {
+        return live ? lookup_lines_thread<S, KW>(ix, bins, pol, q) : -1;
+    } else {
+    using LL = LineLayout<KW>;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, j = lane & 3u, g4 = lane & ~3u;
+    uint32_t line = 0;
+    bool in = live && ix.n != 0;
+    if (in) in = key_line<S>(ix, bins, q, line);
+    uint32_t qw[KW];
+    key_to_wire<S, KW>(q, qw);
+    uint4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t l = __shfl_sync(FULL, line, r, 4);
+        const int ok = __shfl_sync(FULL, (int)in, r, 4);
+        v[r] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) v[r] = ld_line16(ix.lines + (size_t)l * 4 + j, pol);
+    }
+    int slot_mine = -1;
+    bool less_mine = false;
+    uint32_t base_mine = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t qs[KW];
+#pragma unroll
+        for (int p = 0; p < KW; ++p) qs[p] = __shfl_sync(FULL, qw[p], r, 4);
+        int slot = -1;
+        bool less = false;
+        uint32_t base = 0;
+        if constexpr (KW == 3) {
+            const bool own = (v[r].x == qs[0]) & (v[r].y == qs[1]) & (v[r].z == qs[2]);
+            const uint32_t xw = j == 1 ? qs[0] : (j == 2 ? qs[1] : qs[2]);
+            const uint32_t bo = (__ballot_sync(FULL, own) >> g4) & 0xfu;
+            const uint32_t be = (__ballot_sync(FULL, (j != 0) & (v[r].w == xw)) >> g4) & 0xeu;
+            const uint32_t bl = (__ballot_sync(FULL, (j != 0) & (v[r].w < xw)) >> g4) & 0xeu;
+            base = __shfl_sync(FULL, v[r].w, 0, 4);
+            if (bo) slot = __ffs(bo) - 1;
+            else if (be == 0xeu) slot = 4;
+            const uint32_t diff = ~be & 0xeu;
+            less = (diff & (0u - diff) & bl) != 0u;        // first differing word of key 4 is below the query's
+        } else if constexpr (KW == 2) {
+            const bool a = (j != 0) & (v[r].x == qs[0]) & (v[r].y == qs[1]);
+            const bool b = (v[r].z == qs[0]) & (v[r].w == qs[1]);
+            const uint32_t ba = (__ballot_sync(FULL, a) >> g4) & 0xeu, bb = (__ballot_sync(FULL, b) >> g4) & 0xfu;
+            const bool lt = (v[r].z < qs[0]) | ((v[r].z == qs[0]) & (v[r].w < qs[1]));
+            less = (__ballot_sync(FULL, lt) >> (g4 + 3u)) & 1u;
+            base = __shfl_sync(FULL, v[r].x, 0, 4);
+            const int sa = ba ? 2 * (__ffs(ba) - 1) - 1 : 99, sb = bb ? 2 * (__ffs(bb) - 1) : 99;
+            slot = min(sa, sb) == 99 ? -1 : min(sa, sb);
+        } else if constexpr (KW == 4) {
+            const bool own = (j != 0) & (v[r].x == qs[0]) & (v[r].y == qs[1]) & (v[r].z == qs[2]) & (v[r].w == qs[3]);
+            const uint32_t bo = (__ballot_sync(FULL, own) >> g4) & 0xeu;
+            bool lt = false, dec = false;
+            const uint32_t a[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                if (!dec && a[p] != qs[p]) { dec = true; lt = a[p] < qs[p]; }
+            }
+            less = (__ballot_sync(FULL, lt) >> (g4 + 3u)) & 1u;
+            base = __shfl_sync(FULL, v[r].x, 0, 4);
+            if (bo) slot = __ffs(bo) - 2;
+        }
+        if (j == (uint32_t)r) { slot_mine = slot; less_mine = less; base_mine = base; }
+    }
+    if (!in) return -1;
+    if (slot_mine >= 0) return (int64_t)((uint64_t)base_mine + (uint64_t)slot_mine + ix.first_index);
+    if (!less_mine) return -1;
+    const int64_t res = search_overflow<S>(ix.keys, (uint64_t)base_mine + LL::CAP, ix.n, q);
+    return res < 0 ? res : res + (int64_t)ix.first_index;
+    }
+}
+
+// Stages the bin table in shared memory when the kernel was given room for it (smem_bins != nullptr), else uses the global
+// copy.  Must be called by every thread of the CTA (barrier inside).
+__device__ __forceinline__ const uint2 *stage_bins(const IndexView &ix, uint2 *smem_bins) {
+    if (!smem_bins) return ix.bins;
+    for (uint32_t i = threadIdx.x; i < ix.nbins; i += blockDim.x) smem_bins[i] = ix.bins[i];
+    __syncthreads();
+    return smem_bins;
 }
 
 // ------------------------------------------------------------------ kernels: pack, find (fused with pack), find packed
@@ -282,25 +456,38 @@ struct SeqJob {
     uint32_t per_tile;    // windows per tile
 };
 
-template <int S, bool FIND, bool BUCKETED>
+// MODE: 0 = pack only, 1 = pack + line search, 2 = pack + binary search over the key column.
+enum { SEQ_PACK = 0, SEQ_FIND = 1, SEQ_BSEARCH = 2 };
+
+template <int S, int KW, int MODE>
 __global__ void __launch_bounds__(kBlock) seq_kernel(SeqJob job, uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags,
                                                      IndexView ix, int64_t *__restrict__ out_index) {
     __shared__ SeqTile tile;
     const uint64_t ntiles = (job.nq + job.per_tile - 1) / job.per_tile;
+    const uint64_t pol = make_line_policy(ix.hints);
     for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
         const uint64_t w0 = tix * job.per_tile;
         const uint32_t nw = (uint32_t)min((uint64_t)job.per_tile, job.nq - w0);
         const uint32_t nb = (uint32_t)((nw - 1) * job.stride + job.k);
         __syncthreads();                                    // previous tile fully consumed
         const uint32_t ascii_off = stage_tile(tile, job.seq, w0 * job.stride, nb);
-        for (uint32_t j = threadIdx.x; j < nw; j += kBlock) {
+        // whole warps stay in the loop (the line search is warp-collective); lanes past the end carry no query
+        for (uint32_t j0 = 0; j0 < nw; j0 += kBlock) {
+            const uint32_t j = j0 + threadIdx.x;
+            const bool have = j < nw;
             uint64_t q[S];
-            const uint32_t flags = window_canonical<S>(tile, ascii_off, (uint32_t)(j * job.stride), job.k, q);
-            if (FIND) {
-                int64_t r = -1;
-                if ((flags & 6u) == 0) r = BUCKETED ? lookup_bucketed<S>(ix, q) : lookup_bsearch<S>(ix, q);
-                out_index[w0 + j] = r;
-            } else {
+            uint32_t flags = 2u;
+            if (have) flags = window_canonical<S>(tile, ascii_off, (uint32_t)(j * job.stride), job.k, q);
+            else {
+#pragma unroll
+                for (int w = 0; w < S; ++w) q[w] = 0;
+            }
+            if (MODE == SEQ_FIND) {
+                const int64_t r = lookup_lines_warp<S, KW>(ix, ix.bins, pol, q, have && (flags & 6u) == 0);
+                if (have) out_index[w0 + j] = r;
+            } else if (MODE == SEQ_BSEARCH) {
+                if (have) out_index[w0 + j] = (flags & 6u) == 0 ? lookup_bsearch<S>(ix, q) : -1;
+            } else if (have) {
                 if (S == 2) {
                     reinterpret_cast<ulonglong2 *>(out_words)[w0 + j] = make_ulonglong2(q[0], q[1 % S]);
                 } else {
@@ -313,84 +500,51 @@ __global__ void __launch_bounds__(kBlock) seq_kernel(SeqJob job, uint64_t *__res
     }
 }
 
-template <int S, bool BUCKETED>
-__global__ void __launch_bounds__(kBlock) find_packed_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
-                                                             uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
+template <int S>
+__global__ void __launch_bounds__(kBlock) find_bsearch_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
+                                                              uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
     for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < nq; i += (uint64_t)gridDim.x * kBlock) {
         uint64_t q[S];
         load_key<S>(words, i, q);
-        int64_t r = -1;
         const bool skip = flags && (flags[i] & 6u);
-        if (!skip) r = BUCKETED ? lookup_bucketed<S>(ix, q) : lookup_bsearch<S>(ix, q);
-        out_index[i] = r;
+        out_index[i] = skip ? -1 : lookup_bsearch<S>(ix, q);
     }
 }
 
-// The bucketed search with Q queries in flight per thread: all table reads are issued, then the first kProbe keys of
-// every bucket (independent loads), and only buckets longer than kProbe (rare at ~1 key per bucket) take the general
-// search on their remainder.  Lookups are latency-bound (two dependent random sectors each), so throughput follows the
-// number of independent loads in flight.
-constexpr uint32_t kProbe = 4;
+// K4 on packed queries: a persistent grid, the bin table in shared memory, one query per lane and four line loads in
+// flight per lane (lookup_lines_warp); the next iteration's query is fetched before this one's lines are awaited.
+// Per lookup the kernel moves the query (8s + 1 bytes), one 64-byte line and the 8-byte result.
+constexpr int kFindBlock = 512;
 
-// Q queries per thread: table reads for all, then the first kProbe keys of every bucket, then compare.
-template <int S, int Q>
-__device__ __forceinline__ void lookup_mlp(const IndexView &ix, const LookupPolicies &pol, const uint64_t (&q)[Q][S], const bool (&live)[Q], int64_t (&r)[Q]) {
-    uint32_t lo[Q], hi[Q];
+template <int S, int KW>
+__global__ void __launch_bounds__(kFindBlock, 2) find_packed_lines_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
+                                                                          uint64_t nq, IndexView ix, int64_t *__restrict__ out_index, int bins_in_smem) {
+    extern __shared__ __align__(16) uint2 find_bins_smem[];
+    const uint2 *bins = stage_bins(ix, bins_in_smem ? find_bins_smem : nullptr);
+    const uint64_t pol = make_line_policy(ix.hints);
+    const uint64_t span = (uint64_t)gridDim.x * kFindBlock;
+    uint64_t i = (uint64_t)blockIdx.x * kFindBlock + threadIdx.x;
+    uint64_t q[S];
+    bool live = false;
+    auto fetch = [&](uint64_t at) {
+        live = at < nq;
 #pragma unroll
-    for (int j = 0; j < Q; ++j) {
-        lo[j] = hi[j] = 0;
-        if (live[j]) {
-            const uint32_t p = key_bucket<S>(ix, q[j]);
-            lo[j] = ldg_u32_hint(ix.table + p, pol.table);
-            hi[j] = ldg_u32_hint(ix.table + p + 1, pol.table);
+        for (int w = 0; w < S; ++w) q[w] = 0;
+        if (live) {
+            load_key<S>(words, at, q);
+            if (flags && (__ldg(flags + at) & 6u)) live = false;
         }
-    }
-    uint64_t kk[Q][kProbe][S];
+    };
+    fetch(i);
+    // warp-uniform trip count: the first lane of the warp decides
+    for (uint64_t w0 = i - (threadIdx.x & 31u); w0 < nq; w0 += span, i += span) {
+        uint64_t qc[S];
 #pragma unroll
-    for (int j = 0; j < Q; ++j) {
-#pragma unroll
-        for (uint32_t t = 0; t < kProbe; ++t) {
-            if (live[j] && lo[j] + t < hi[j]) load_key_hint<S>(ix.keys, (uint64_t)lo[j] + t, kk[j][t], pol.keys);
-            else {
-#pragma unroll
-                for (int w = 0; w < S; ++w) kk[j][t][w] = ~0ull;
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < Q; ++j) {
-        r[j] = -1;
-        if (!live[j]) continue;
-#pragma unroll
-        for (int t = (int)kProbe - 1; t >= 0; --t)
-            if (lo[j] + (uint32_t)t < hi[j] && words_equal<S>(kk[j][t], q[j])) r[j] = (int64_t)lo[j] + t;
-        if (r[j] < 0 && hi[j] - lo[j] > kProbe) r[j] = search_range<S>(ix.keys, (uint64_t)lo[j] + kProbe, hi[j], q[j]);
-        if (r[j] >= 0) r[j] += (int64_t)ix.first_index;
-    }
-}
-
-template <int S, int Q>
-__global__ void __launch_bounds__(kBlock) find_packed_mlp_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
-                                                                 uint64_t nq, IndexView ix, int64_t *__restrict__ out_index) {
-    const uint64_t span = (uint64_t)gridDim.x * kBlock;
-    const LookupPolicies pol = make_lookup_policies(ix.hints);
-    for (uint64_t base = (uint64_t)blockIdx.x * kBlock + threadIdx.x; base < nq; base += span * Q) {
-        uint64_t q[Q][S];
-        bool live[Q];
-        int64_t r[Q];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const uint64_t i = base + (uint64_t)j * span;
-            live[j] = i < nq;
-            if (live[j]) {
-                load_key<S>(words, i, q[j]);
-                if (flags && (flags[i] & 6u)) live[j] = false, out_index[i] = -1;
-            }
-        }
-        lookup_mlp<S, Q>(ix, pol, q, live, r);
-#pragma unroll
-        for (int j = 0; j < Q; ++j)
-            if (live[j]) out_index[base + (uint64_t)j * span] = r[j];
+        for (int w = 0; w < S; ++w) qc[w] = q[w];
+        const bool lc = live;
+        fetch(i + span);
+        const int64_t r = lookup_lines_warp<S, KW>(ix, bins, pol, qc, lc);
+        if (i < nq) out_index[i] = lc ? r : -1;
     }
 }
 
@@ -493,7 +647,7 @@ inline size_t rows_smem_bytes(uint32_t rows_per_tile, uint32_t k, bool find) {
     return (find ? 2u : 3u) * (size_t)rows_tile_bytes(rows_per_tile, k) + 2u * (size_t)rows_stream_words(rows_per_tile, k) * 4u;
 }
 
-template <int S, bool FIND, int RPT>
+template <int S, int KW, bool FIND, int RPT>
 __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
                                                                                 uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags,
                                                                                 IndexView ix, int64_t *__restrict__ out_index) {
@@ -510,7 +664,7 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
     const uint64_t ntiles = (nq + kRows - 1) / kRows;
     const uint32_t top_bits = 2u * k - 64u * (S - 1);
     const uint64_t policy = make_evict_first_policy();
-    const LookupPolicies pol = make_lookup_policies(FIND ? ix.hints : 0u);
+    const uint64_t pol = make_line_policy(FIND ? ix.hints : 0u);
 
     // tile t of this CTA: rows [row0, row0 + rows); the copy fetches the 16-byte-aligned superset of its bytes
     auto issue = [&](uint64_t tile, uint32_t buf) {
@@ -618,14 +772,12 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
             }
         }
         if (FIND) {
-            bool live[RPT];
-            int64_t res[RPT];
+            // the line search is warp-collective: every thread of the CTA gets here for every h
 #pragma unroll
-            for (int h = 0; h < RPT; ++h) live[h] = have[h] && (flags[h] & 6u) == 0;
-            lookup_mlp<S, RPT>(ix, pol, q, live, res);
-#pragma unroll
-            for (int h = 0; h < RPT; ++h)
-                if (have[h]) out_index[row0 + threadIdx.x + h * kBlock] = live[h] ? res[h] : -1;
+            for (int h = 0; h < RPT; ++h) {
+                const int64_t res = lookup_lines_warp<S, KW>(ix, ix.bins, pol, q[h], have[h] && (flags[h] & 6u) == 0);
+                if (have[h]) out_index[row0 + threadIdx.x + h * kBlock] = res;
+            }
         } else {
 #pragma unroll
             for (int h = 0; h < RPT; ++h) {
@@ -680,15 +832,6 @@ struct PeerPtrs {
     void *p[kMaxShards];
 };
 
-template <int S, int KW>
-__device__ __forceinline__ void key_to_wire(const uint64_t (&q)[S], uint32_t *dst) {
-#pragma unroll
-    for (int j = 0; j < KW; ++j) {
-        const int idx = KW - 1 - j;                       // 32-bit word index counted from the least significant end
-        const uint64_t w = q[S - 1 - idx / 2];
-        dst[j] = (idx & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
-    }
-}
 template <int S, int KW>
 __device__ __forceinline__ void wire_to_key(const uint32_t *__restrict__ src, uint64_t (&q)[S]) {
 #pragma unroll
@@ -941,11 +1084,13 @@ __global__ void publish_counts_kernel(const unsigned long long *cursors, int nsh
 // kernel simply sees world * vsub owners) and the sub-ranges are searched one after another, so the slice of the key
 // column and of the prefix table in use at any time fits L2 -- the partitioned (sort-merge-like) form of the lookup for
 // large batches.  inbox: [vsub][world][cap][KW], counts_in: [vsub][world]; ret on the origin: [world * vsub][cap].
-template <int S, int KW, int Q>
-__global__ void __launch_bounds__(kBlock, S <= 2 ? 3 : 1) find_routed_kernel(const uint32_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
-                                                                             int world, int vsub, uint64_t cap, IndexView ix, uint32_t *__restrict__ res) {
+template <int S, int KW>
+__global__ void __launch_bounds__(kFindBlock, 2) find_routed_kernel(const uint32_t *__restrict__ inbox, const unsigned long long *__restrict__ counts_in,
+                                                                    int world, int vsub, uint64_t cap, IndexView ix, uint32_t *__restrict__ res,
+                                                                    int bins_in_smem) {
     // all segments in (sub-range, source) order form one flat sequence of keys; the grid sweeps it front to back, so the
     // CTAs work on the same sub-range at the same time
+    extern __shared__ __align__(16) uint2 find_bins_smem[];
     __shared__ unsigned long long pre[kMaxShards + 1];
     const uint32_t nseg = (uint32_t)(world * vsub);
     if (threadIdx.x == 0) {
@@ -953,36 +1098,41 @@ __global__ void __launch_bounds__(kBlock, S <= 2 ? 3 : 1) find_routed_kernel(con
         for (uint32_t i = 0; i < nseg; ++i) { pre[i] = acc; acc += counts_in[i] < cap ? counts_in[i] : cap; }
         pre[nseg] = acc;
     }
+    const uint2 *bins = stage_bins(ix, bins_in_smem ? find_bins_smem : nullptr);
     __syncthreads();
     const uint64_t total = pre[nseg];
-    const uint64_t span = (uint64_t)gridDim.x * kBlock;
-    const LookupPolicies pol = make_lookup_policies(ix.hints);
-    for (uint64_t basei = (uint64_t)blockIdx.x * kBlock + threadIdx.x; basei < total; basei += span * Q) {
-        uint64_t q[Q][S];
-        bool live[Q];
-        int64_t r[Q];
-        uint64_t slot[Q];                                    // segment * cap + position: same index in the inbox and in res
+    const uint64_t span = (uint64_t)gridDim.x * kFindBlock;
+    const uint64_t pol = make_line_policy(ix.hints);
+    uint64_t f = (uint64_t)blockIdx.x * kFindBlock + threadIdx.x;
+    uint64_t q[S];
+    uint64_t slot = 0;                                       // segment * cap + position: same index in the inbox and in res
+    bool live = false;
+    auto fetch = [&](uint64_t at) {
+        live = at < total;
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const uint64_t f = basei + (uint64_t)j * span;
-            live[j] = f < total;
-            slot[j] = 0;
-            if (live[j]) {
-                uint32_t lo = 0, hi = nseg - 1;              // segment e with pre[e] <= f < pre[e + 1]
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi + 1) >> 1;
-                    if (pre[mid] <= f) lo = mid; else hi = mid - 1;
-                }
-                slot[j] = (uint64_t)lo * cap + (f - pre[lo]);
-                wire_to_key<S, KW>(inbox + slot[j] * KW, q[j]);
+        for (int w = 0; w < S; ++w) q[w] = 0;
+        if (live) {
+            uint32_t lo = 0, hi = nseg - 1;                  // segment e with pre[e] <= at < pre[e + 1]
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (pre[mid] <= at) lo = mid; else hi = mid - 1;
             }
+            slot = (uint64_t)lo * cap + (at - pre[lo]);
+            wire_to_key<S, KW>(inbox + slot * KW, q);
         }
-        lookup_mlp<S, Q>(ix, pol, q, live, r);     // ix.first_index is 0 here: results are local to the shard
+    };
+    fetch(f);
+    for (uint64_t w0 = f - (threadIdx.x & 31u); w0 < total; w0 += span, f += span) {
+        uint64_t qc[S];
+#pragma unroll
+        for (int w = 0; w < S; ++w) qc[w] = q[w];
+        const bool lc = live;
+        const uint64_t sc = slot;
+        fetch(f + span);
+        const int64_t r = lookup_lines_warp<S, KW>(ix, bins, pol, qc, lc);     // ix.first_index is 0 here: results are local to the shard
         // results stay on the owner, in the inbox's own layout; the origin pulls its runs in the gather leg.  (Storing them
         // straight into the origins' buffers cost up to 1.4 ms per batch on most ranks at 8 GPUs: see DESIGN.md section 5.)
-#pragma unroll
-        for (int j = 0; j < Q; ++j)
-            if (live[j]) res[slot[j]] = r[j] < 0 ? kWireMiss : (uint32_t)r[j];
+        if (lc) res[sc] = r < 0 ? kWireMiss : (uint32_t)r;
     }
     __threadfence_system();
 }
@@ -1041,15 +1191,92 @@ __global__ void check_sorted_kernel(const uint64_t *__restrict__ keys, uint64_t 
     }
 }
 
-// table[b] = number of keys whose bucket is < b  (b in [0, nbuckets + 1]).
+// key_start[b] = number of keys whose bin is < b  (b in [0, nbins]).
 template <int S>
-__global__ void build_table_kernel(IndexView ix, uint32_t *table) {
+__global__ void bin_bounds_kernel(IndexView ix, uint32_t *key_start) {
     const uint64_t n = ix.n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
-        int64_t prev = -1, cur = (int64_t)ix.nbuckets + 1;
-        if (i > 0) { uint64_t a[S]; load_key<S>(ix.keys, i - 1, a); prev = (int64_t)key_bucket<S>(ix, a); }
-        if (i < n) { uint64_t b[S]; load_key<S>(ix.keys, i, b); cur = (int64_t)key_bucket<S>(ix, b); }
-        for (int64_t b = prev + 1; b <= cur; ++b) table[b] = (uint32_t)i;
+        int64_t prev = -1, cur = (int64_t)ix.nbins;
+        uint32_t bin; uint64_t frac;
+        if (i > 0) { uint64_t a[S]; load_key<S>(ix.keys, i - 1, a); prev = key_bin<S>(ix, a, bin, frac) ? (int64_t)bin : (int64_t)ix.nbins - 1; }
+        if (i < n) { uint64_t b[S]; load_key<S>(ix.keys, i, b); cur = key_bin<S>(ix, b, bin, frac) ? (int64_t)bin : (int64_t)ix.nbins - 1; }
+        for (int64_t b = prev + 1; b <= cur; ++b) key_start[b] = (uint32_t)i;
+    }
+}
+
+// bins[b] = {first line, lines} with lines = max(1, ceil(keys in bin * 16 / fill_x16)); *total = all lines.  One CTA.
+__global__ void __launch_bounds__(1024) bins_scan_kernel(const uint32_t *__restrict__ key_start, uint32_t nbins, uint32_t fill_x16,
+                                                         uint2 *__restrict__ bins, unsigned long long *total) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (nbins + 1023u) / 1024u;
+    const uint32_t b0 = min(nbins, threadIdx.x * per), b1 = min(nbins, b0 + per);
+    auto lines_of = [&](uint32_t b) -> unsigned long long {
+        const unsigned long long cnt = key_start[b + 1] - key_start[b];
+        const unsigned long long nl = (cnt * 16ull + fill_x16 - 1ull) / fill_x16;
+        return nl ? nl : 1ull;
+    };
+    unsigned long long acc = 0;
+    for (uint32_t b = b0; b < b1; ++b) acc += lines_of(b);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const unsigned long long v = part[t]; part[t] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    unsigned long long at = part[threadIdx.x];
+    for (uint32_t b = b0; b < b1; ++b) {
+        const unsigned long long nl = lines_of(b);
+        bins[b] = make_uint2((uint32_t)at, (uint32_t)nl);
+        at += nl;
+    }
+}
+
+// Writes every line: thread i owns the lines in (line of key i-1, line of key i] -- the empty ones in between and, when
+// key i is the first of its line, that line with up to CAP keys.
+template <int S, int KW>
+__global__ void fill_lines_kernel(IndexView ix, uint32_t *__restrict__ lines, uint64_t nlines) {
+    using LL = LineLayout<KW>;
+    const uint64_t n = ix.n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t prev = -1, cur = (int64_t)nlines;
+        uint32_t l;
+        uint64_t kq[S];
+        if (i > 0) { load_key<S>(ix.keys, i - 1, kq); prev = key_line<S>(ix, ix.bins, kq, l) ? (int64_t)l : (int64_t)nlines - 1; }
+        if (i < n) { load_key<S>(ix.keys, i, kq); cur = key_line<S>(ix, ix.bins, kq, l) ? (int64_t)l : (int64_t)nlines - 1; }
+        uint32_t w[kLineWords];
+        for (int64_t e = prev + 1; e < cur + (i < n && cur != prev ? 1 : 0); ++e) {
+#pragma unroll
+            for (uint32_t x = 0; x < kLineWords; ++x) w[x] = 0;
+            w[LL::kBaseWord] = (uint32_t)i;
+#pragma unroll
+            for (int t = 0; t < LL::CAP; ++t) {
+#pragma unroll
+                for (int p = 0; p < KW; ++p) w[LL::word(t, p)] = ix.pad[p];
+            }
+            if (e == cur) {                         // key i opens this line: it and its followers that map to the same line
+                bool more = true;
+#pragma unroll
+                for (int t = 0; t < LL::CAP; ++t) {
+                    if (more && i + t < n) {
+                        uint64_t kk[S];
+                        uint32_t lt;
+                        load_key<S>(ix.keys, i + t, kk);
+                        more = t == 0 || ((key_line<S>(ix, ix.bins, kk, lt) ? (int64_t)lt : (int64_t)nlines - 1) == cur);
+                        if (more) {
+                            uint32_t kw[KW];
+                            key_to_wire<S, KW>(kk, kw);
+#pragma unroll
+                            for (int p = 0; p < KW; ++p) w[LL::word(t, p)] = kw[p];
+                        }
+                    } else more = false;
+                }
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(lines + (uint64_t)e * kLineWords);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        }
     }
 }
 
@@ -1066,16 +1293,17 @@ __global__ void iota_kernel(uint32_t *p, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
 // Sorted pass: thread i resolves query perm[i]; neighbouring threads probe neighbouring keys.
-template <int S>
+template <int S, int KW>
 __global__ void __launch_bounds__(kBlock) find_sorted_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
                                                              const uint32_t *__restrict__ perm, uint64_t nq, IndexView ix,
                                                              int64_t *__restrict__ out_index) {
+    const uint64_t pol = make_line_policy(0u);
     for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < nq; i += (uint64_t)gridDim.x * kBlock) {
         const uint64_t src = perm[i];
         uint64_t q[S];
         load_key<S>(words, src, q);
         int64_t r = -1;
-        if (!(flags && (flags[src] & 6u))) r = lookup_bucketed<S>(ix, q);
+        if (!(flags && (flags[src] & 6u))) r = lookup_lines_thread<S, KW>(ix, ix.bins, pol, q);
         out_index[src] = r;
     }
 }
@@ -1171,15 +1399,18 @@ int sm_count_now() {
 IndexView view_of(const cc_graph *g) {
     IndexView v{};
     v.keys = g->index.keys;
-    v.table = g->index.table;
+    v.lines = static_cast<const uint4 *>(g->index.lines);
+    v.bins = static_cast<const uint2 *>(g->index.bins);
     v.n = g->h.num_records;
     v.first_index = g->first_index;
     v.base = g->index.base;
+    v.span = g->index.span;
     v.scale = g->index.scale;
-    v.nbuckets = g->index.nbuckets;
+    v.nbins = g->index.nbins;
     v.norm = g->index.norm;
     v.hints = (uint32_t)options().lookup_l2_hints;
     v.k = g->h.k;
+    for (int i = 0; i < 8; ++i) v.pad[i] = g->index.pad[i];
     return v;
 }
 
@@ -1191,6 +1422,15 @@ IndexView view_of(const cc_graph *g) {
         case 4: { constexpr int S_ = 4; __VA_ARGS__; break; }                             \
         default: return fail(CC_ERR_UNSUPPORTED, "k-mers wider than 4 words (k > 128) are not supported by pack/lookup"); \
     }
+
+#define CC_DISPATCH_SKW(s, kw, ...)                                                        \
+    switch ((s) * 2 - (kw)) {                                                              \
+        case 0: CC_DISPATCH_S(s, { constexpr int KW_ = 2 * S_; __VA_ARGS__; }) break;      \
+        case 1: CC_DISPATCH_S(s, { constexpr int KW_ = 2 * S_ - 1; __VA_ARGS__; }) break;  \
+        default: return fail(CC_ERR_ARG, "inconsistent k-mer size for the wire format");   \
+    }
+
+inline uint32_t wire_words(uint32_t k) { return (2 * k + 31) / 32; }
 
 int check_k(uint32_t k) {
     if (k == 0) return fail(CC_ERR_ARG, "k must be positive");
@@ -1219,9 +1459,9 @@ int launch_pack_windows(const uint8_t *dev_seq, uint64_t /*len*/, uint32_t k, ui
         // tile = RPT * 256 rows, sized to about 16 KB of sequence (two tiles in flight per CTA, several CTAs per SM)
 #define CC_ROWS_PACK(RPT_) CC_DISPATCH_S(s, {                                                                                  \
             const size_t smem = rows_smem_bytes(RPT_ * kBlock, k, false);                                                          \
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, false, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-            const int grid = resident_grid(rows_kernel<S_, false, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), sm_count_now()); \
-            rows_kernel<S_, false, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags, none, nullptr); })
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, 2 * S_, false, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+            const int grid = resident_grid(rows_kernel<S_, 2 * S_, false, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), sm_count_now()); \
+            rows_kernel<S_, 2 * S_, false, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags, none, nullptr); })
         if (k <= (uint32_t)options().rows_rpt2_max_k) { CC_ROWS_PACK(2); } else { CC_ROWS_PACK(1); }
 #undef CC_ROWS_PACK
         count_launch();
@@ -1232,8 +1472,8 @@ int launch_pack_windows(const uint8_t *dev_seq, uint64_t /*len*/, uint32_t k, ui
     const uint64_t ntiles = (nq + job.per_tile - 1) / job.per_tile;
     IndexView none{};
     CC_DISPATCH_S(s, {
-        const int grid = resident_grid(seq_kernel<S_, false, false>, kBlock, 0, ntiles, sm_count_now());
-        seq_kernel<S_, false, false><<<grid, kBlock, 0, st>>>(job, dev_words, dev_flags, none, nullptr);
+        const int grid = resident_grid(seq_kernel<S_, 2 * S_, SEQ_PACK>, kBlock, 0, ntiles, sm_count_now());
+        seq_kernel<S_, 2 * S_, SEQ_PACK><<<grid, kBlock, 0, st>>>(job, dev_words, dev_flags, none, nullptr);
     });
     count_launch();
     CC_CUDA(cudaGetLastError());
@@ -1259,11 +1499,11 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
             // independent rows: pack and search in one kernel (the stream of 2-bit codes is all that is staged)
             IndexView ix = view_of(g);
             const uint32_t k = g->h.k;
-#define CC_ROWS_FIND(RPT_) CC_DISPATCH_S(g->h.s, {                                                                             \
+#define CC_ROWS_FIND(RPT_) CC_DISPATCH_SKW(g->h.s, wire_words(k), {                                                            \
                 const size_t smem = rows_smem_bytes(RPT_ * kBlock, k, true);                                                       \
-                CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, true, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                const int grid = resident_grid(rows_kernel<S_, true, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), g->sm_count); \
-                rows_kernel<S_, true, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, nullptr, nullptr, ix, dev_index); })
+                CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, KW_, true, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                const int grid = resident_grid(rows_kernel<S_, KW_, true, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), g->sm_count); \
+                rows_kernel<S_, KW_, true, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, nullptr, nullptr, ix, dev_index); })
             if (k <= 64) { CC_ROWS_FIND(2); } else { CC_ROWS_FIND(1); }     // two lookups in flight per thread when the tile fits
 #undef CC_ROWS_FIND
             count_launch();
@@ -1283,13 +1523,13 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
     IndexView ix = view_of(g);
     if (algo == CC_ALGO_BSEARCH) {
         CC_DISPATCH_S(g->h.s, {
-            const int grid = resident_grid(seq_kernel<S_, true, false>, kBlock, 0, ntiles, g->sm_count);
-            seq_kernel<S_, true, false><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index);
+            const int grid = resident_grid(seq_kernel<S_, 2 * S_, SEQ_BSEARCH>, kBlock, 0, ntiles, g->sm_count);
+            seq_kernel<S_, 2 * S_, SEQ_BSEARCH><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index);
         });
     } else {
-        CC_DISPATCH_S(g->h.s, {
-            const int grid = resident_grid(seq_kernel<S_, true, true>, kBlock, 0, ntiles, g->sm_count);
-            seq_kernel<S_, true, true><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index);
+        CC_DISPATCH_SKW(g->h.s, wire_words(g->h.k), {
+            const int grid = resident_grid(seq_kernel<S_, KW_, SEQ_FIND>, kBlock, 0, ntiles, g->sm_count);
+            seq_kernel<S_, KW_, SEQ_FIND><<<grid, kBlock, 0, st>>>(job, nullptr, nullptr, ix, dev_index);
         });
     }
     count_launch();
@@ -1326,34 +1566,41 @@ int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t
     return CC_OK;
 }
 
+// Grid and dynamic shared memory of the persistent line-search kernels: the bin table goes to shared memory when the
+// batch is large enough to pay for staging it in every CTA.
+struct FindLaunch { int grid; size_t smem; int bins_in_smem; };
+template <typename Kernel>
+int plan_find(Kernel kernel, const cc_graph *g, uint64_t work, FindLaunch &fl) {
+    const size_t bins_bytes = (size_t)g->index.nbins * sizeof(uint2);
+    fl.bins_in_smem = options().find_bins_smem && work >= (1u << 16) ? 1 : 0;
+    fl.smem = fl.bins_in_smem ? bins_bytes : 0;
+    if (fl.smem > 48 * 1024) CC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fl.smem));
+    fl.grid = resident_grid(kernel, kFindBlock, fl.smem, (work + kFindBlock - 1) / kFindBlock, g->sm_count);
+    return CC_OK;
+}
+
 int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, int64_t *dev_index,
                        int algo, cudaStream_t st) {
     if (int rc = check_k(g->h.k)) return rc;
     if (nq == 0) return CC_OK;
     IndexView ix = view_of(g);
-    const uint32_t s = g->h.s;
+    const uint32_t s = g->h.s, kw = wire_words(g->h.k);
     const int grid = grid_for(nq, kBlock, g->sm_count, 8);
     if (algo == CC_ALGO_MERGE) {
         uint32_t *perm = nullptr;
         if (int rc = sort_permutation(dev_words, nq, s, g->h.k, st, &perm)) return rc;
-        CC_DISPATCH_S(s, find_sorted_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, perm, nq, ix, dev_index));
+        CC_DISPATCH_SKW(s, kw, find_sorted_kernel<S_, KW_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, perm, nq, ix, dev_index));
         count_launch();
         cudaFreeAsync(perm, st);
     } else if (algo == CC_ALGO_BSEARCH) {
-        CC_DISPATCH_S(s, find_packed_kernel<S_, false><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index));
+        CC_DISPATCH_S(s, find_bsearch_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index));
         count_launch();
     } else {
-        const int qpt = options().lookup_queries_per_thread;
-        const uint64_t nblk = ((nq + std::max(qpt, 1) - 1) / std::max(qpt, 1) + kBlock - 1) / kBlock;
-#define CC_MLP(Q_) CC_DISPATCH_S(s, {                                                                                   \
-            const int g2 = options().mlp_grid_per_sm > 0 ? (int)std::min<uint64_t>(nblk, (uint64_t)g->sm_count * options().mlp_grid_per_sm) \
-                                                         : resident_grid(find_packed_mlp_kernel<S_, Q_>, kBlock, 0, nblk, g->sm_count);  \
-            find_packed_mlp_kernel<S_, Q_><<<g2, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index); })
-        if (qpt >= 4) { CC_MLP(4); }
-        else if (qpt >= 2) { CC_MLP(2); }
-        else if (qpt == 1) { CC_MLP(1); }
-#undef CC_MLP
-        else { CC_DISPATCH_S(s, find_packed_kernel<S_, true><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index)); }
+        CC_DISPATCH_SKW(s, kw, {
+            FindLaunch fl;
+            if (int rc = plan_find(find_packed_lines_kernel<S_, KW_>, g, nq, fl)) return rc;
+            find_packed_lines_kernel<S_, KW_><<<fl.grid, kFindBlock, fl.smem, st>>>(dev_words, dev_flags, nq, ix, dev_index, fl.bins_in_smem);
+        });
         count_launch();
     }
     CC_CUDA(cudaGetLastError());
@@ -1363,30 +1610,21 @@ int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *de
 int build_index(cc_graph *g, int bits_req) {
     if (int rc = check_k(g->h.k)) return rc;
     const uint64_t n = g->h.num_records;
-    const uint32_t s = g->h.s, k = g->h.k;
+    const uint32_t s = g->h.s, k = g->h.k, kw = wire_words(k);
     if (n >= 0xffffffffull) return fail(CC_ERR_UNSUPPORTED, "more than 2^32-2 records per device shard");
     LookupIndex &ix = g->index;
     if (ix.keys) { cudaFree(ix.keys); ix.keys = nullptr; }
-    if (ix.table) { cudaFree(ix.table); ix.table = nullptr; }
+    if (ix.lines) { cudaFree(ix.lines); ix.lines = nullptr; }
+    if (ix.bins) { cudaFree(ix.bins); ix.bins = nullptr; }
     ix.built = false;
+    ix.nlines = 0;
     cudaStream_t st = g->stream;
-
-    int bits = bits_req > 0 ? bits_req : options().index_bits;
-    if (bits <= 0) {
-        // about one key per bucket: a lookup is then one table sector plus one key sector (measured on B200 at
-        // n = 1e8: 2^24 buckets 1.2e10 lookups/s, 2^26 1.9e10; the table costs 4 bytes per bucket next to 8s per key)
-        int lg = 0;
-        while ((1ull << lg) < std::max<uint64_t>(n, 1)) ++lg;
-        bits = std::max(1, lg);
-    }
-    bits = std::min<int>(bits, (int)std::min<uint32_t>(2u * k, 30u));
-    ix.bits = bits;
 
     if (int rc = g->scan_ws.ensure(0, 0)) return rc;
     CC_CUDA(cudaMalloc(&ix.keys, std::max<uint64_t>(n * s, 2) * sizeof(uint64_t) + 64));
     if (int rc = launch_decode_columns(g->dev_body, n, s, g->h.c, ix.keys, nullptr, nullptr, g->scan_ws, g->sm_count, st)) return rc;
 
-    // The table spans [first key, last key] of this array, not the whole 2k-bit key space (see key_bucket).
+    // The bins span [first key, last key] of this array, not the whole 2k-bit key space (see key_bin).
     uint64_t first[4] = {0, 0, 0, 0}, last[4] = {0, 0, 0, 0};
     if (n) {
         CC_CUDA(cudaMemcpyAsync(first, ix.keys, s * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -1395,35 +1633,67 @@ int build_index(cc_graph *g, int bits_req) {
     }
     uint64_t t0 = 0, t1 = 0;
     CC_DISPATCH_S(s, { t0 = key_top64<S_>(first, k); t1 = key_top64<S_>(last, k); });
-    const uint64_t span = t1 >= t0 ? t1 - t0 : 0;      // unsorted arrays are rejected below; buckets are clamped anyway
-    // nbuckets equal slices of [0, span]: bucket(d) = floor(d * nbuckets / (span + 1)), evaluated as a 64x64 high multiply
-    // of the normalised distance (top bit of span at bit 63) with scale = floor(2^64 * nbuckets / (span' + 1)).
-    uint64_t nb = options().index_buckets > 0 ? (uint64_t)options().index_buckets : (1ull << bits);
-    nb = std::max<uint64_t>(1, std::min<uint64_t>(nb, 1ull << 30));
+    const uint64_t span = t1 >= t0 ? t1 - t0 : 0;      // unsorted arrays are rejected below
+    // bins: about 256 keys each, a power of two, at most 2^13 (64 KB of shared memory in the search kernels)
+    int bits = bits_req > 0 ? bits_req : options().index_bits;
+    if (bits <= 0) {
+        bits = 0;
+        while (bits < (int)kMaxBinsLog2 && (256ull << (bits + 1)) <= n) ++bits;
+    }
+    bits = std::min<int>(bits, (int)kMaxBinsLog2);
+    uint64_t nb = 1ull << bits;
     if (span + 1 != 0 && nb > span + 1) nb = span + 1;  // no finer than the key resolution
+    // bin(d) = floor(d * nbins / (span + 1)), evaluated as a 64x64 multiply of the normalised distance (top bit of span at
+    // bit 63) with scale = floor(2^64 * nbins / (span' + 1)); the low half of the product is the position inside the bin.
     uint32_t norm = 0;
     while (norm < 63 && !((span << norm) >> 63)) ++norm;
     if (span == 0) norm = 0;
     const unsigned __int128 spanp1 = (unsigned __int128)(span << norm) + 1;
     const unsigned __int128 sc = (((unsigned __int128)nb) << 64) / spanp1;
     ix.base = t0;
+    ix.span = span;
     ix.norm = norm;
     ix.scale = sc > (unsigned __int128)~0ull ? ~0ull : (uint64_t)sc;
-    ix.nbuckets = (uint32_t)nb;
-    CC_CUDA(cudaMalloc(&ix.table, ((uint64_t)ix.nbuckets + 2) * sizeof(uint32_t)));
+    ix.nbins = (uint32_t)nb;
+    for (int i = 0; i < 8; ++i) ix.pad[i] = 0;
+    for (uint32_t j = 0; j < kw; ++j) {                 // wire form of the largest key: the 32-bit words, most significant first
+        const uint32_t idx = kw - 1 - j;
+        const uint64_t w = last[s - 1 - idx / 2];
+        ix.pad[j] = (idx & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+    }
 
     unsigned long long *d_unsorted = reinterpret_cast<unsigned long long *>(g->scan_ws.totals + 8);
+    unsigned long long *d_total = reinterpret_cast<unsigned long long *>(g->scan_ws.totals + 9);
     const unsigned long long none = ~0ull;
     CC_CUDA(cudaMemcpyAsync(d_unsorted, &none, 8, cudaMemcpyHostToDevice, st));
     const int grid = grid_for(n + 1, 256, g->sm_count, 8);
     CC_DISPATCH_S(s, check_sorted_kernel<S_><<<grid, 256, 0, st>>>(ix.keys, n, d_unsorted));
     count_launch();
-    const IndexView view = view_of(g);
-    CC_DISPATCH_S(s, build_table_kernel<S_><<<grid, 256, 0, st>>>(view, ix.table));
-    count_launch();
-    CC_CUDA(cudaGetLastError());
-    unsigned long long at = none;
+    CC_CUDA(cudaMalloc(&ix.bins, ((uint64_t)ix.nbins + 1) * sizeof(uint2)));
+    uint32_t *key_start = nullptr;
+    CC_CUDA(cudaMallocAsync(&key_start, ((uint64_t)ix.nbins + 2) * sizeof(uint32_t), st));
+    IndexView view = view_of(g);
+    CC_DISPATCH_S(s, bin_bounds_kernel<S_><<<grid, 256, 0, st>>>(view, key_start));
+    const int fill_pct = std::min(100, std::max(5, options().index_fill_pct));
+    uint32_t cap_keys = 0;
+    CC_DISPATCH_SKW(s, kw, cap_keys = LineLayout<KW_>::CAP);
+    const uint32_t fill_x16 = std::max<uint32_t>(1, cap_keys * 16u * (uint32_t)fill_pct / 100u);
+    bins_scan_kernel<<<1, 1024, 0, st>>>(key_start, ix.nbins, fill_x16, static_cast<uint2 *>(ix.bins), d_total);
+    count_launch(2);
+    unsigned long long at = none, nlines = 0;
     CC_CUDA(cudaMemcpyAsync(&at, d_unsorted, 8, cudaMemcpyDeviceToHost, st));
+    CC_CUDA(cudaMemcpyAsync(&nlines, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CC_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(key_start, st);
+    if (nlines >= 0xffffffffull) return fail(CC_ERR_UNSUPPORTED, "lookup index of %llu lines exceeds 2^32-2", nlines);
+    ix.nlines = nlines;
+    CC_CUDA(cudaMalloc(&ix.lines, std::max<uint64_t>(nlines, 1) * kLineWords * sizeof(uint32_t)));
+    view = view_of(g);
+    if (at == none) {                                   // an unsorted array has no order-preserving table; lookups are refused
+        CC_DISPATCH_SKW(s, kw, fill_lines_kernel<S_, KW_><<<grid, 256, 0, st>>>(view, static_cast<uint32_t *>(ix.lines), nlines));
+        count_launch();
+    }
+    CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaStreamSynchronize(st));
     ix.sorted = (at == none);
     ix.unsorted_at = at;
@@ -1463,12 +1733,6 @@ int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots,
 }
 
 // ------------------------------------------------------------------ routed lookups (peer memory) launchers
-#define CC_DISPATCH_SKW(s, kw, ...)                                                        \
-    switch ((s) * 2 - (kw)) {                                                              \
-        case 0: CC_DISPATCH_S(s, { constexpr int KW_ = 2 * S_; __VA_ARGS__; }) break;      \
-        case 1: CC_DISPATCH_S(s, { constexpr int KW_ = 2 * S_ - 1; __VA_ARGS__; }) break;  \
-        default: return fail(CC_ERR_ARG, "inconsistent k-mer size for the wire format");   \
-    }
 
 uint64_t route_state_size(uint64_t max_q, int nshards) { return route_state_bytes(max_q, nshards); }
 
@@ -1479,7 +1743,7 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
     if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
     if (my_rank < 0 || my_rank >= nshards) return fail(CC_ERR_ARG, "rank %d out of range", my_rank);
     if (nq >= (1ull << 32) || cap >= (1ull << 32)) return fail(CC_ERR_UNSUPPORTED, "routed batches are limited to 2^32-1 queries per rank");
-    const uint32_t s = (k + 31) / 32, kw = (2 * k + 31) / 32;
+    const uint32_t s = (k + 31) / 32, kw = wire_words(k);
     PeerPtrs inbox{}, counts{};
     for (int i = 0; i < nshards; ++i) {
         inbox.p[i] = peer_inbox[i]; counts.p[i] = peer_counts[i];
@@ -1516,15 +1780,17 @@ int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_c
     if (world < 1 || vsub < 1 || world * vsub > kMaxShards) return fail(CC_ERR_ARG, "world * vsub must be in 1..%d", kMaxShards);
     IndexView ix = view_of(g);
     ix.first_index = 0;                 // the wire carries indices local to the shard; the origin rebases them
-    // a sub-range that fits L2 must stay there: no evict-first on its keys
-    const uint64_t slice_bytes = g->h.num_records / (uint64_t)vsub * (8ull * g->h.s + 4ull);
+    // a sub-range that fits L2 must stay there: no evict-first on its lines
+    const uint64_t slice_bytes = g->index.nlines * 64ull / (uint64_t)vsub;
     if (vsub > 1 && slice_bytes <= (48ull << 20)) ix.hints = 0;
-    const uint32_t kw = (2 * g->h.k + 31) / 32;
-    const int grid = g->sm_count * std::max(1, options().routed_search_blocks_per_sm);
+    const uint32_t kw = wire_words(g->h.k);
     CC_DISPATCH_SKW(g->h.s, kw, {
-        find_routed_kernel<S_, KW_, 2><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t *>(dev_inbox),
-                                                                 reinterpret_cast<const unsigned long long *>(dev_counts_in), world, vsub, cap, ix,
-                                                                 static_cast<uint32_t *>(dev_res));
+        FindLaunch fl;
+        if (int rc = plan_find(find_routed_kernel<S_, KW_>, g, 1ull << 20, fl)) return rc;
+        if (options().routed_search_blocks_per_sm > 0) fl.grid = std::min(fl.grid, g->sm_count * options().routed_search_blocks_per_sm);
+        find_routed_kernel<S_, KW_><<<fl.grid, kFindBlock, fl.smem, st>>>(static_cast<const uint32_t *>(dev_inbox),
+                                                                          reinterpret_cast<const unsigned long long *>(dev_counts_in), world, vsub,
+                                                                          cap, ix, static_cast<uint32_t *>(dev_res), fl.bins_in_smem);
     });
     count_launch();
     CC_CUDA(cudaGetLastError());

@@ -155,11 +155,12 @@ CC_API int cc_pack_kmers_dev(int device, const uint8_t *dev_kmers, uint64_t nq, 
                              uint64_t *dev_words, uint8_t *dev_flags, void *stream);
 
 /* ---------------------------------------------------------------- K4: batched lookups (findRecord) */
-/* algo: 0 = auto (prefix-bucketed search), 1 = plain binary search over the key column,
- *       2 = sorted-merge (radix-sort the batch, one monotone pass over the key column). */
+/* algo: 0 = auto (the line index: one 64-byte bucket line per lookup), 1 = plain binary search over the key column,
+ *       2 = sort the batch first, then probe the line index in key order (comparison mode). */
 enum { CC_ALGO_AUTO = 0, CC_ALGO_BSEARCH = 1, CC_ALGO_MERGE = 2 };
-/* Build (or rebuild) the lookup index: key column + prefix table; validates ascending order
- * (CC_ERR_UNSORTED).  Called lazily by the first lookup.  index_bits = 0 picks a default. */
+/* Build (or rebuild) the lookup index: key column + bucket lines (an order-preserving table of 64-byte lines over the
+ * array's own key range); validates ascending order (CC_ERR_UNSORTED).  Called lazily by the first
+ * lookup.  index_bits = log2 of the number of key-range bins (0 picks a default, at most 13). */
 CC_API int cc_build_index(cc_graph *g, int index_bits);
 /* nq k-byte ASCII queries, row-major: canonicalise, search; out_index[i] = record index or -1. */
 CC_API int cc_find_ascii(cc_graph *g, const uint8_t *kmers, uint64_t nq, int64_t *out_index, int algo);
@@ -257,8 +258,8 @@ CC_API int cc_device_body(const cc_graph *g, const void **dev_body, uint64_t *by
 CC_API int cc_device_keys(cc_graph *g, const uint64_t **dev_keys, uint64_t *n);
 /* Process-wide tuning knobs (benchmarks and sweeps; the defaults are the measured optima):
  *   scan:    "scan_stages", "scan_tile_bytes", "scan_ctas_per_sm", "scan_chunk_tiles", "scan_stage_buf_bytes", "scan_fast", "host_chunk_mb"
- *   index:   "index_bits" (log2 of the bucket count, 0 = auto), "index_buckets" (exact count, overrides index_bits)
- *   lookups: "lookup_queries_per_thread", "mlp_grid_per_sm", "lookup_l2_hints" (bit0 keys evict-first, bit1 table evict-last),
+ *   index:   "index_bits" (log2 of the number of bins, 0 = auto), "index_fill_pct" (average fill of a bucket line, default 50)
+ *   lookups: "lookup_l2_hints" (bit0: line loads evict-first in L2), "find_bins_smem" (1 = bin table staged in shared memory),
  *            "rows_fused" (ASCII lists: 1 = pack + search in one kernel), "rows_rpt2_max_k"
  *   routed:  "route_blocks_per_sm", "routed_search_blocks_per_sm", "gather_blocks_per_sm"
  * Unknown names fail with CC_ERR_ARG. */
