@@ -38,6 +38,11 @@ class Stats(C.Structure):
                 ("launches", C.c_uint32)]
 
 
+class ShardedStats(C.Structure):
+    _fields_ = [("route_ms", C.c_float), ("search_ms", C.c_float), ("gather_ms", C.c_float), ("chunk_ms", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32), ("overflow_retries", C.c_uint32)]
+
+
 _P = C.c_void_p
 _U32P = C.POINTER(C.c_uint32)
 _U64P = C.POINTER(C.c_uint64)
@@ -81,6 +86,19 @@ SIGNATURES = {
     "cc_route_queries_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint32, _P, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, C.c_uint64, _P, _P]),
     "cc_find_routed_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "cc_gather_routed_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint64, _P, C.c_int, C.c_uint64, _P, _P]),
+    "cc_open_sharded": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "cc_open_sharded_memory": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "cc_open_sharded_device": (C.c_int, [C.POINTER(_P), _U64P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "cc_dispose_sharded": (None, [_P]),
+    "cc_sharded_info": (C.c_int, [_P, C.POINTER(C.c_int), _U64P, _U32P, _U32P]),
+    "cc_sharded_shard": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), _U64P]),
+    "cc_sharded_last_stats": (C.c_int, [_P, C.POINTER(ShardedStats)]),
+    "cc_find_packed_sharded": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
+    "cc_find_ascii_sharded": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "cc_find_windows_sharded": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "cc_find_packed_sharded_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _U64P, C.POINTER(_P)]),
+    "cc_find_novel_sharded": (C.c_int, [_P, C.c_int32, _P, C.c_int, _P, _P, C.c_uint64, _U64P]),
+    "cc_write_roi_file_sharded": (C.c_int, [_P, C.c_int32, _P, C.c_int, C.c_char_p, _U64P]),
     "cc_join": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "cc_sort": (C.c_int, [_P, C.POINTER(_P)]),
     "cc_write_graph": (C.c_int, [_P, C.c_char_p]),

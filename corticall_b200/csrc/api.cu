@@ -286,9 +286,16 @@ int prepare_scan(cc_graph *g, uint64_t n_per_launch, const int32_t *parents, int
     return CC_OK;
 }
 
-int sync_stream(cc_graph *, cudaStream_t st) {
+int sync_stream(cc_graph *g, cudaStream_t st) {
     cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    if (e != cudaSuccess) {
+        const int code = (g && g->scan_ws.host_error) ? *static_cast<volatile int *>(g->scan_ws.host_error) : 0;
+        if (g) g->scan_ws.poisoned = true;
+        cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+        if (code) set_error("%s (device watchdog code %d: %s)", t_error.c_str(), code,
+                            code == 1 ? "tile never arrived" : code == 2 ? "stage never released" : "look-back never resolved");
+        return CC_ERR_CUDA;
+    }
     return CC_OK;
 }
 
@@ -366,6 +373,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "gather_blocks_per_sm")) o.gather_blocks_per_sm = (int)value;
     else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;
     else if (!strcmp(name, "scan_debug")) o.scan_debug = (int)value;
+    else if (!strcmp(name, "scan_pdl")) o.scan_pdl = (int)value;
     else if (!strcmp(name, "scan_fast")) o.scan_fast = (int)value;
     else if (!strcmp(name, "scan_stage_buf_bytes")) o.scan_stage_buf_bytes = (int)value;
     else if (!strcmp(name, "scan_chunk_tiles")) o.scan_chunk_tiles = (int)value;

@@ -44,6 +44,7 @@ struct Options {
     int scan_fast = 1;           // 1 = chunked deferred-look-back kernel first, general kernel only on overflow
     int scan_chunk_tiles = 16;   // tiles per chunk of the fast kernel (power of two, <= 16)
     int scan_stage_buf_bytes = 4096;   // fast kernel: staging bytes (global scratch) per consumer warp per chunk parity
+    int scan_pdl = 1;            // launch the rewrite kernel with programmatic stream serialisation (overlaps its launch with the scan's tail)
     int scan_debug = 0;          // diagnosis only: bit0 = skip the look-back (WRONG output positions)
 };
 Options &options();
@@ -75,7 +76,9 @@ struct ScanWorkspace {
     uint64_t *totals = nullptr;       // [0] in, [1] out (ping-pong for chunked scans)
     int32_t *parents = nullptr;       // device copy of the parent colour list
     uint32_t parents_cap = 0;
-    int *dev_error = nullptr;         // watchdog code
+    int *dev_error = nullptr;         // watchdog code (device view)
+    int *host_error = nullptr;        // the same word in mapped host memory (null: plain device memory)
+    bool poisoned = false;            // a launch failed after touching the counters: reset everything on the next ensure()
     uint32_t epoch = 0;
     uint32_t ticket_base = 0;         // tickets drawn so far from tile_counter (host mirror)
     int ensure(uint64_t ntiles, uint32_t nparents);

@@ -15,6 +15,8 @@
 // already running; novel records are compacted in input order with warp ballots, an intra-tile scan and
 // a decoupled look-back over per-tile descriptors (single pass: the array is read exactly once and only
 // novel records are written).  Algorithmic bytes per record: S + f*(8s+5), f = novel fraction.
+#include <string.h>
+
 #include <algorithm>
 
 #include "cc_internal.hpp"
@@ -771,6 +773,9 @@ __global__ void __launch_bounds__(kThreads, 2) redo_chunks_kernel(const __grid_c
     uint8_t *image = smem + kCtrlBytes + parents_bytes;                              // tile_records*O + 32 bytes
     const uint32_t image_bytes = (g.tile_records * p.O + 32u + 127u) & ~127u;
     uint8_t *stage0 = image + image_bytes;
+    // Launched with programmatic stream serialisation right behind the fast scan: the CTAs of this (almost always empty)
+    // kernel are scheduled while the scan drains and wait here for its memory to be visible.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t ndirty = *reinterpret_cast<const volatile uint32_t *>(&p.dirty_ctl[0]);
 
     if (ndirty != 0) {
@@ -1050,8 +1055,28 @@ int ScanWorkspace::ensure(uint64_t ntiles, uint32_t nparents) {
         CC_CUDA(cudaMemset(tile_counter, 0, 256));
         CC_CUDA(cudaMalloc(&totals, 256));
         CC_CUDA(cudaMemset(totals, 0, 256));
-        CC_CUDA(cudaMalloc(&dev_error, 256));
-        CC_CUDA(cudaMemset(dev_error, 0, 256));
+        // the watchdog word lives in mapped host memory: the host can still read it after a kernel trapped
+        if (cudaHostAlloc(reinterpret_cast<void **>(&host_error), 256, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(reinterpret_cast<void **>(&dev_error), host_error, 0) == cudaSuccess) {
+            memset(host_error, 0, 256);
+        } else {
+            cudaGetLastError();
+            if (host_error) { cudaFreeHost(host_error); host_error = nullptr; }
+            CC_CUDA(cudaMalloc(&dev_error, 256));
+            CC_CUDA(cudaMemset(dev_error, 0, 256));
+        }
+        fresh = true;
+    }
+    if (poisoned) {
+        // an earlier launch failed half-way: the device-side ticket counter, the queue of dense chunks and the host
+        // mirrors may disagree.  Start over from zero (legacy stream + synchronise: this is the error path).
+        CC_CUDA(cudaDeviceSynchronize());
+        CC_CUDA(cudaMemset(tile_counter, 0, 256));
+        CC_CUDA(cudaMemset(totals, 0, 256));
+        if (tile_state) CC_CUDA(cudaMemset(tile_state, 0, tile_state_cap * sizeof(uint64_t)));
+        ticket_base = 0;
+        epoch = 0;
+        poisoned = false;
         fresh = true;
     }
     if (ntiles > tile_state_cap) {
@@ -1093,7 +1118,8 @@ void ScanWorkspace::release() {
     if (tile_counter) cudaFree(tile_counter);
     if (totals) cudaFree(totals);
     if (parents) cudaFree(parents);
-    if (dev_error) cudaFree(dev_error);
+    if (host_error) cudaFreeHost(host_error);
+    else if (dev_error) cudaFree(dev_error);
     *this = ScanWorkspace();
 }
 
@@ -1183,58 +1209,67 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
     using Kern = void (*)(const ScanKParams);
 
     // ---- fast kernel (chunked, deferred look-back)
+    // Every step that can fail without having touched the workspace state (allocation, attribute calls, the "does the
+    // rewrite kernel fit" test) comes first; the host mirrors of the device counters (ticket_base, epoch) advance only
+    // with a successful launch, and a failure after that point poisons the workspace so that the next call resets it.
     const FastGeom f = pick_fast_geometry(a.n, S, p.O, parents_bytes, lim.smem_optin, ctas);
     if (f.ok && f.num_chunks <= ws.tile_state_cap) {
-        if (int rc = next_epoch(ws, st)) return rc;
-        ScanKParams q = p;
-        q.g = f.g; q.epoch = ws.epoch;
-        q.chunk_log2 = f.chunk_log2; q.num_chunks = f.num_chunks; q.stg_stride = f.stg_stride; q.stg_cap = f.stg_cap; q.Ow = f.Ow;
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, f.num_chunks);
-        q.ticket_base = ws.ticket_base;
-        ws.ticket_base += f.num_chunks + grid;      // every CTA draws its chunks plus one terminal ticket
         const size_t smem = kFastCtrlBytes + parents_bytes + (size_t)f.g.stages * f.g.stage_bytes;
-        if (int rc = ws.ensure_scratch((size_t)grid * f.stg_bytes)) return rc;
-        q.stg_scratch = ws.scratch;
-        static const Kern ftable[2][kFastParents + 2] = {
-            {scan_novel_fast_kernel<false, 0>, scan_novel_fast_kernel<false, 1>, scan_novel_fast_kernel<false, 2>,
-             scan_novel_fast_kernel<false, 3>, scan_novel_fast_kernel<false, 4>, scan_novel_fast_kernel<false, -1>},
-            {scan_novel_fast_kernel<true, 0>, scan_novel_fast_kernel<true, 1>, scan_novel_fast_kernel<true, 2>,
-             scan_novel_fast_kernel<true, 3>, scan_novel_fast_kernel<true, 4>, scan_novel_fast_kernel<true, -1>}};
-        Kern kern = ftable[aligned4 ? 1 : 0][np_slot];
-        CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, st>>>(q);
-        count_launch();
-        CC_CUDA(cudaGetLastError());
-        // ---- rewrite of the chunks whose staging overflowed (dense novelty); a no-op launch on sparse graphs
-        ScanKParams r = q;
         const uint32_t image_bytes = (f.g.tile_records * p.O + 32u + 127u) & ~127u;
         int rstages = (int)f.g.stages;
         const int64_t rbudget = (int64_t)lim.smem_optin / ctas - 1024 - kCtrlBytes - parents_bytes - image_bytes;
         while (rstages > 2 && (int64_t)rstages * f.g.stage_bytes > rbudget) --rstages;
         if ((int64_t)rstages * f.g.stage_bytes > rbudget) return fail(CC_ERR_UNSUPPORTED, "record size %u bytes does not fit the rewrite kernel", S);
-        r.g.stages = (uint32_t)rstages;
         const size_t rsmem = kCtrlBytes + parents_bytes + image_bytes + (size_t)rstages * f.g.stage_bytes;
+        static const Kern ftable[2][kFastParents + 2] = {
+            {scan_novel_fast_kernel<false, 0>, scan_novel_fast_kernel<false, 1>, scan_novel_fast_kernel<false, 2>,
+             scan_novel_fast_kernel<false, 3>, scan_novel_fast_kernel<false, 4>, scan_novel_fast_kernel<false, -1>},
+            {scan_novel_fast_kernel<true, 0>, scan_novel_fast_kernel<true, 1>, scan_novel_fast_kernel<true, 2>,
+             scan_novel_fast_kernel<true, 3>, scan_novel_fast_kernel<true, 4>, scan_novel_fast_kernel<true, -1>}};
         static const Kern rtable[2][kFastParents + 2] = {
             {redo_chunks_kernel<false, 0>, redo_chunks_kernel<false, 1>, redo_chunks_kernel<false, 2>, redo_chunks_kernel<false, 3>,
              redo_chunks_kernel<false, 4>, redo_chunks_kernel<false, -1>},
             {redo_chunks_kernel<true, 0>, redo_chunks_kernel<true, 1>, redo_chunks_kernel<true, 2>, redo_chunks_kernel<true, 3>,
              redo_chunks_kernel<true, 4>, redo_chunks_kernel<true, -1>}};
+        Kern kern = ftable[aligned4 ? 1 : 0][np_slot];
         Kern rkern = rtable[aligned4 ? 1 : 0][np_slot];
+        if (int rc = ws.ensure_scratch((size_t)grid * f.stg_bytes)) return rc;
+        CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CC_CUDA(cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-        rkern<<<grid, kThreads, rsmem, st>>>(r);
+        if (int rc = next_epoch(ws, st)) { ws.poisoned = true; return rc; }
+        ScanKParams q = p;
+        q.g = f.g; q.epoch = ws.epoch;
+        q.chunk_log2 = f.chunk_log2; q.num_chunks = f.num_chunks; q.stg_stride = f.stg_stride; q.stg_cap = f.stg_cap; q.Ow = f.Ow;
+        q.ticket_base = ws.ticket_base;
+        q.stg_scratch = ws.scratch;
+        kern<<<grid, kThreads, smem, st>>>(q);
+        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return cuda_fail(e, "scan_novel_fast_kernel launch", __FILE__, __LINE__);   // nothing ran: state unchanged
         count_launch();
-        CC_CUDA(cudaGetLastError());
+        ws.ticket_base += f.num_chunks + grid;      // every CTA draws its chunks plus one terminal ticket
+        // ---- rewrite of the chunks whose staging overflowed (dense novelty); a no-op launch on sparse graphs
+        ScanKParams r = q;
+        r.g.stages = (uint32_t)rstages;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = rsmem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = options().scan_pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaError_t e = cudaLaunchKernelEx(&cfg, rkern, r); e != cudaSuccess) {
+            cudaGetLastError();
+            ws.poisoned = true;                     // the fast kernel may have queued chunks nobody will drain
+            return cuda_fail(e, "redo_chunks_kernel launch", __FILE__, __LINE__);
+        }
+        count_launch();
         return CC_OK;
     }
 
     // ---- general kernel (per-tile look-back, any density): alone, or behind the fast kernel and run only on overflow
     if (int rc = pick_geometry(a.n, S, parents_bytes, lim.smem_optin, ctas, p.g)) return rc;
     if (p.g.num_tiles > ws.tile_state_cap) return fail(CC_ERR_ARG, "scan workspace too small");
-    if (int rc = next_epoch(ws, st)) return rc;
-    p.epoch = ws.epoch;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * ctas, p.g.num_tiles);
     p.ticket_base = ws.ticket_base;
-    ws.ticket_base += p.g.num_tiles + grid;         // drawn by the CTAs, or added by block 0 when the launch is skipped
     p.run_if = nullptr;
     p.run_expect = 0;
     p.skip_tickets = p.g.num_tiles + grid;
@@ -1246,9 +1281,12 @@ int launch_scan_novel(const ScanArgs &a, ScanWorkspace &ws, int sm_count, cudaSt
          scan_novel_kernel<true, 4>, scan_novel_kernel<true, -1>}};
     Kern kern = table[aligned4 ? 1 : 0][np_slot];
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = next_epoch(ws, st)) { ws.poisoned = true; return rc; }
+    p.epoch = ws.epoch;
     kern<<<grid, kThreads, smem, st>>>(p);
+    CC_CUDA(cudaGetLastError());                    // a failed launch ran nothing: the mirror stays where it was
     count_launch();
-    CC_CUDA(cudaGetLastError());
+    ws.ticket_base += p.g.num_tiles + grid;         // drawn by the CTAs, or added by block 0 when the launch is skipped
     return CC_OK;
 }
 
@@ -1267,14 +1305,14 @@ int launch_decode_columns(const uint8_t *dev_body, uint64_t n, uint32_t s, uint3
     p.tile_counter = ws.tile_counter; p.err = ws.dev_error;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * 2, p.g.num_tiles);
     p.ticket_base = ws.ticket_base;
-    ws.ticket_base += p.g.num_tiles + grid;
     const size_t smem = kCtrlBytes + (size_t)p.g.stages * p.g.stage_bytes;
     const bool aligned4 = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(dev_body) & 3u) == 0);
     auto kern = aligned4 ? decode_columns_kernel<true> : decode_columns_kernel<false>;
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(p);
-    count_launch();
     CC_CUDA(cudaGetLastError());
+    count_launch();
+    ws.ticket_base += p.g.num_tiles + grid;
     return CC_OK;
 }
 

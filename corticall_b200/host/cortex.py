@@ -549,6 +549,133 @@ class CortexGraph:
     __str__ = toString
 
 
+class ShardedCortexGraph:
+    """One graph over several GPUs of this process (cc_open_sharded): the record array is cut into k-mer-range shards, one
+    per entry of `devices`; lookups are routed to the owning shard over peer memory and the novelty scan returns one
+    globally ordered list.  The batch surface is CortexGraph's (findRecordIndices / findWindows / findPacked / findNovel /
+    writeRois) and so are the answers; per-record access goes through `shard(r)`."""
+
+    def __init__(self, source, devices):
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = N._P()
+        if isinstance(source, (bytes, bytearray, memoryview)):
+            buf = bytes(source)
+            N.check(N.lib().cc_open_sharded_memory(buf, len(buf), devs, len(devices), C.byref(h)))
+            self.cortexFile = None
+        else:
+            self.cortexFile = os.fspath(source)
+            N.check(N.lib().cc_open_sharded(self.cortexFile.encode(), devs, len(devices), C.byref(h)))
+        self._h, self._keep = h, None
+        self._info()
+
+    @classmethod
+    def fromDevice(cls, bodies, counts, k: int, c: int, devices, keepalive=None):
+        """bodies[r]: device pointer of shard r's records on devices[r] (on-disk layout), counts[r] records each."""
+        self = cls.__new__(cls)
+        n = len(devices)
+        devs = (C.c_int * n)(*[int(d) for d in devices])
+        ptrs = (N._P * n)(*[int(b) for b in bodies])
+        cnts = (C.c_uint64 * n)(*[int(x) for x in counts])
+        h = N._P()
+        N.check(N.lib().cc_open_sharded_device(ptrs, cnts, k, getKmerBits(k), c, devs, n, C.byref(h)))
+        self._h, self._keep, self.cortexFile = h, keepalive, None
+        self._info()
+        return self
+
+    def _info(self):
+        nd, nr, k, c = C.c_int(0), C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        N.check(N.lib().cc_sharded_info(self._h, C.byref(nd), C.byref(nr), C.byref(k), C.byref(c)))
+        self.numShards, self.numRecords, self.kmerSize, self.numColors = nd.value, nr.value, k.value, c.value
+        self.kmerBits = getKmerBits(k.value)
+
+    def getNumRecords(self): return self.numRecords
+    def getKmerSize(self): return self.kmerSize
+    def getKmerBits(self): return self.kmerBits
+    def getNumColors(self): return self.numColors
+
+    def shard(self, r: int):
+        """(borrowed CortexGraph over shard r, device, first global record index)."""
+        h, dev, first = N._P(), C.c_int(0), C.c_uint64(0)
+        N.check(N.lib().cc_sharded_shard(self._h, r, C.byref(h), C.byref(dev), C.byref(first)))
+        g = CortexGraph._adopt(h, dev.value)
+        g.firstIndex = first.value
+        g.dispose = lambda: None            # owned by the sharded handle
+        g._owner = self
+        return g, dev.value, first.value
+
+    def findRecordIndices(self, kmers) -> np.ndarray:
+        q = np.ascontiguousarray(kmers, dtype=np.uint8)
+        if q.ndim != 2 or q.shape[1] != self.kmerSize:
+            raise ValueError("queries must be [nq, %d] ASCII bytes" % self.kmerSize)
+        out = np.empty(q.shape[0], dtype=np.int64)
+        N.check(N.lib().cc_find_ascii_sharded(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
+
+    def findWindows(self, seq) -> np.ndarray:
+        a = np.frombuffer(seq.encode("latin-1") if isinstance(seq, str) else bytes(seq), dtype=np.uint8) \
+            if not isinstance(seq, np.ndarray) else np.ascontiguousarray(seq, dtype=np.uint8)
+        nw = max(a.size - self.kmerSize + 1, 0)
+        out = np.empty(nw, dtype=np.int64)
+        if nw:
+            N.check(N.lib().cc_find_windows_sharded(self._h, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def findPacked(self, words, flags=None) -> np.ndarray:
+        w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, self.kmerBits)
+        f = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        out = np.empty(w.shape[0], dtype=np.int64)
+        N.check(N.lib().cc_find_packed_sharded(self._h, _ptr(w), _ptr(f), w.shape[0], _ptr(out)))
+        return out
+
+    def findPackedDevice(self, words, flags, outs):
+        """Device-resident batch: words[r] int64 [nq_r, s] / flags[r] uint8 [nq_r] or None / outs[r] int64 [nq_r] are torch
+        tensors on the shard's device."""
+        n = self.numShards
+        pw = (N._P * n)(*[w.data_ptr() for w in words])
+        pf = (N._P * n)(*[(f.data_ptr() if f is not None else None) for f in flags]) if flags is not None else None
+        po = (N._P * n)(*[o.data_ptr() for o in outs])
+        nq = (C.c_uint64 * n)(*[int(w.shape[0]) for w in words])
+        N.check(N.lib().cc_find_packed_sharded_dev(self._h, pw, pf, nq, po))
+
+    def findNovel(self, child: int, parents, cap: int | None = None, want_index: bool = True):
+        par = np.asarray(list(parents), dtype=np.int32)
+        O = 8 * self.kmerBits + 5
+        cap = self.numRecords if cap is None else cap
+        guess = min(cap, max(65536, self.numRecords // 32))
+        for _ in range(2):
+            out = np.empty((max(guess, 1), O), dtype=np.uint8)
+            idx = np.empty(max(guess, 1), dtype=np.uint64) if want_index else None
+            cnt = C.c_uint64(0)
+            N.check(N.lib().cc_find_novel_sharded(self._h, child, _ptr(par), par.size, _ptr(out), _ptr(idx), guess, C.byref(cnt)))
+            if min(cnt.value, cap) <= guess:
+                break
+            guess = min(cnt.value, cap)
+        m = min(cnt.value, guess)
+        return cnt.value, out[:m], (idx[:m] if want_index else None)
+
+    def writeRois(self, child: int, parents, out_path) -> int:
+        par = np.asarray(list(parents), dtype=np.int32)
+        cnt = C.c_uint64(0)
+        N.check(N.lib().cc_write_roi_file_sharded(self._h, child, _ptr(par), par.size, os.fspath(out_path).encode(), C.byref(cnt)))
+        return cnt.value
+
+    def lastStats(self) -> N.ShardedStats:
+        st = N.ShardedStats()
+        N.check(N.lib().cc_sharded_last_stats(self._h, C.byref(st)))
+        return st
+
+    def dispose(self):
+        if getattr(self, "_h", None):
+            N.lib().cc_dispose_sharded(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+
 def packCanonical(seq, k: int, device: int = 0):
     """K3 over a host sequence: canonical packed words [nw, s] (native order) and flags [nw]
     (bit0 flipped, bit1 not ACGTacgt, bit2 lower case)."""

@@ -29,7 +29,8 @@
  *     long[] of CortexRecord is Long.reverseBytes() of each word (CortexGraph.java:208-209);
  *   - coverage is returned as int32 (Java int: values >= 2^31 wrap negative, BinaryUtils.java:6-17);
  *   - record index results are int64, -1 = the reference's `null`;
- *   - one caller thread per cc_graph; there is NO CPU fallback: without a CUDA device every compute
+ *   - one caller thread per cc_graph, and all "_dev" calls on one handle go to ONE stream (the handle's scan workspace --
+ *     ticket counter, look-back epochs -- is not shared between streams); there is NO CPU fallback: without a CUDA device every compute
  *     entry point fails with CC_ERR_CUDA.
  */
 #ifndef CORTICALL_CUDA_H
@@ -218,6 +219,50 @@ CC_API int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t
                               uint64_t cap, void *dev_res, void *stream);
 CC_API int cc_gather_routed_dev(int device, void *const *peer_res, const void *dev_route_state, uint64_t max_queries, uint64_t nq,
                                 const uint64_t *dev_shard_first, int nshards, uint64_t cap, int64_t *dev_out, void *stream);
+
+/* ---------------------------------------------------------------- one graph over several GPUs of this process */
+/* The reference constructs ONE CortexGraph per file in one JVM (S/utils/arguments/ArgumentHandler.java:271-274); a
+ * cc_sharded is that graph with its sorted record array cut into k-mer-range shards (contiguous record slices), one per
+ * entry of `devices` (SURVEY.md Appendix C cc_open_sharded).  One host thread drives all devices: buffers are plain
+ * cudaMalloc memory opened to the other devices with cudaDeviceEnablePeerAccess, the legs of a lookup batch (route ->
+ * search -> gather, the kernels of the routed lookups above) are ordered across devices with CUDA events, and no
+ * collective library is involved.  A device id may be listed more than once (several shards on one GPU; used by the tests).
+ * Results are identical to the single-GPU entry points on the same file: global record indices / -1, and the novel
+ * records of all shards concatenated in shard order = file order (FindROIs.java:52-64). */
+typedef struct cc_sharded cc_sharded;
+typedef struct {
+    float    route_ms, search_ms, gather_ms;   /* device time of the legs of the first chunk of the last call, max over devices */
+    float    chunk_ms;                         /* route start -> gather end of that chunk, max over devices                    */
+    uint64_t h2d_bytes, d2h_bytes;             /* host-buffer entry points                                                    */
+    uint32_t launches;                         /* kernels launched by the last call                                           */
+    uint32_t overflow_retries;                 /* chunks re-run in pieces because a (source, owner) segment overflowed        */
+} cc_sharded_stats;
+CC_API int cc_open_sharded(const char *path, const int *devices, int ndev, cc_sharded **out);
+CC_API int cc_open_sharded_memory(const void *file_image, uint64_t size, const int *devices, int ndev, cc_sharded **out);
+/* Wrap slices that are already resident: dev_bodies[r] = counts[r] records (on-disk layout) on devices[r], ascending across r. */
+CC_API int cc_open_sharded_device(const void *const *dev_bodies, const uint64_t *counts, uint32_t k, uint32_t s, uint32_t c,
+                                  const int *devices, int ndev, cc_sharded **out);
+CC_API void cc_dispose_sharded(cc_sharded *sh);
+CC_API int cc_sharded_info(const cc_sharded *sh, int *ndev, uint64_t *num_records, uint32_t *kmer_size, uint32_t *num_colors);
+/* The handle of one shard (owned by sh; header / colour queries, cc_decode_records ...), its device and first record index. */
+CC_API int cc_sharded_shard(const cc_sharded *sh, int rank, cc_graph **shard, int *device, uint64_t *first_index);
+CC_API int cc_sharded_last_stats(const cc_sharded *sh, cc_sharded_stats *out);
+/* findRecord batches from HOST buffers: the batch is split evenly over the devices, copied, (packed,) routed, searched,
+ * gathered and copied back; out_index[i] = global record index or -1, exactly as cc_find_packed / cc_find_ascii /
+ * cc_find_windows answer on one device. */
+CC_API int cc_find_packed_sharded(cc_sharded *sh, const uint64_t *words, const uint8_t *flags, uint64_t nq, int64_t *out_index);
+CC_API int cc_find_ascii_sharded(cc_sharded *sh, const uint8_t *kmers, uint64_t nq, int64_t *out_index);
+CC_API int cc_find_windows_sharded(cc_sharded *sh, const uint8_t *seq, uint64_t len, int64_t *out_index);
+/* The same with the queries already on the devices: dev_words[r] / dev_flags[r] / dev_out[r] live on devices[r], nq[r] queries
+ * each (dev_flags or any of its entries may be NULL).  Synchronous; cc_sharded_last_stats has the device times. */
+CC_API int cc_find_packed_sharded_dev(cc_sharded *sh, const uint64_t *const *dev_words, const uint8_t *const *dev_flags,
+                                      const uint64_t *nq, int64_t *const *dev_out);
+/* FindROIs over all shards (arguments as cc_find_novel): every device scans its slice, the per-shard counts become
+ * exclusive offsets and the novel records land in out_records at those offsets -- one globally sorted list. */
+CC_API int cc_find_novel_sharded(cc_sharded *sh, int32_t child, const int32_t *parents, int nparents,
+                                 void *out_records, uint64_t *out_index, uint64_t cap, uint64_t *out_count);
+CC_API int cc_write_roi_file_sharded(cc_sharded *sh, int32_t child, const int32_t *parents, int nparents,
+                                     const char *out_path, uint64_t *out_count);
 
 /* ---------------------------------------------------------------- next rows: merged view of several graphs */
 /* CortexCollection / Join (S/utils/io/graph/cortex/CortexCollection.java:34-62,245-293, S/commands/utils/Join.java:23-57):
