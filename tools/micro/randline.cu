@@ -53,6 +53,15 @@ int main() {
     const uint64_t bytes = 2560ull << 20, nq = 1ull << 28;
     uint4 *buf; uint32_t *out;
     cudaMalloc(&buf, bytes); cudaMemset(buf, 1, bytes); cudaMalloc(&out, 4);
+    // does the L2 fetch-granularity hint change what a random line costs?
+    for (size_t gran : {(size_t)128, (size_t)64, (size_t)32}) {
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("cudaLimitMaxL2FetchGranularity %zu -> %s, now %zu\n", gran, cudaGetErrorString(e), got);
+        run("coop", coop_kernel<2>, 2, buf, bytes, nq, out);
+        run("coop", coop_kernel<4>, 4, buf, bytes, nq, out);
+    }
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 128);
     run("coop", coop_kernel<2>, 2, buf, bytes, nq, out);
     run("coop", coop_kernel<4>, 4, buf, bytes, nq, out);
     run("coop", coop_kernel<8>, 8, buf, bytes, nq, out);

@@ -320,3 +320,72 @@ def random_genome(seed: int, length: int, device="cpu", n_permille: int = 0) -> 
     if n_permille:
         seq = torch.where(umod(hash_idx(seed, 21, idx), 1000) < n_permille, torch.full_like(seq, ord("N")), seq)
     return seq
+
+
+# ------------------------------------------------------------------ k-mer-range partitioned graphs (BASELINE configs[3])
+
+def canonical_range_bounds(k: int, world: int) -> list[int]:
+    """Key-space boundaries that give every rank the same number of canonical k-mers: a k-mer x is canonical iff
+    x <= rc(x), and rc(x) is (for this purpose) independent of the leading bases of x, so the density of canonical
+    k-mers at relative position t of the key space is 2(1 - t) and the r-th boundary sits at 1 - sqrt(1 - r/world)."""
+    import math
+    space = 4 ** k
+    return [min(space, int(space * (1.0 - math.sqrt(max(0.0, 1.0 - r / world))))) for r in range(world + 1)]
+
+
+def range_canonical_keys(seed: int, n: int, k: int, lo: int, hi: int, device, chunk: int = 1 << 26) -> list[torch.Tensor]:
+    """Exactly n distinct canonical k-mers inside [lo, hi), ascending, one word (k <= 31).  Rejection sampling: uniform
+    draws from the range are kept when they are their own canonical form, which samples the canonical k-mers of the
+    range uniformly -- every rank builds its own shard of one global sorted graph without seeing the others."""
+    assert k <= 31 and 0 <= lo < hi <= 4 ** k
+    space = 4 ** k
+    acc = max(0.02, 1.0 - (lo + hi) / (2.0 * space))            # expected acceptance = mean canonical density / 2
+    have: torch.Tensor | None = None
+    drawn = 0
+    for _ in range(64):
+        got = 0 if have is None else int(have.numel())
+        if got >= n:
+            break
+        want = int((n - got) / acc * 1.02) + 65536
+        parts = [] if have is None else [have]
+        for o in range(0, want, chunk):
+            m = min(chunk, want - o)
+            idx = torch.arange(drawn + o, drawn + o + m, dtype=torch.int64, device=device)
+            x = umod(hash_idx(seed, 31, idx), hi - lo) + lo
+            rc = revcomp_words([x], k)[0]
+            parts.append(x[x <= rc])
+            del idx, x, rc
+        drawn += want
+        allk = torch.cat(parts)
+        del parts
+        srt, _ = torch.sort(allk)
+        del allk
+        keep = torch.ones(srt.numel(), dtype=torch.bool, device=device)
+        keep[1:] = srt[1:] != srt[:-1]
+        have = srt[keep]
+        del srt, keep
+    u = int(have.numel())
+    if u < n:
+        raise RuntimeError("could not draw enough distinct k-mers in the range")
+    if u > n:                                                    # drop u-n evenly spread elements, order kept
+        pick = (torch.arange(n, dtype=torch.int64, device=device) * u) // n
+        have = have[pick]
+    return [have]
+
+
+def owner_of_keys(words: list[torch.Tensor], splitters: torch.Tensor | None) -> torch.Tensor:
+    """Number of splitters <= key (unsigned, lexicographic over the words): the shard that owns the key.  An independent
+    torch formulation of the owner rule of the routed lookup, used to check it."""
+    n = words[0].numel()
+    owner = torch.zeros(n, dtype=torch.int64, device=words[0].device)
+    if splitters is None:
+        return owner
+    for j in range(splitters.shape[0]):
+        sp = [splitters[j, w] for w in range(len(words))]
+        lt = torch.zeros(n, dtype=torch.bool, device=words[0].device)
+        eq = torch.ones(n, dtype=torch.bool, device=words[0].device)
+        for w, s in zip(words, sp):                               # key < splitter ?
+            lt |= eq & (_ukey(w) < _ukey(s))
+            eq &= w == s
+        owner += (~lt).to(torch.int64)
+    return owner
