@@ -7,10 +7,10 @@ FindROIs, the Call helpers) on top of the C ABI.  There is no CPU fallback.
 from ._native import (CC_ALGO_AUTO, CC_ALGO_BSEARCH, CC_ALGO_MERGE, CortexJDKException, device_count, launch_count, lib,
                       set_option)
 from .host.commands import (CallHelpers, CortexCollection, CortexVertex, CovStats, FindLowCoverage, FindROIs, FindShared, Join,
-                            RecoverExcludedKmers, Sort)
+                            RecoverExcludedKmers, Remove, Sort)
 from .host.cortex import CortexColor, CortexGraph, CortexHeader, CortexRecord, ShardedCortexGraph, packCanonical
 from .host.kmer import CanonicalKmer, CortexBinaryKmer, CortexByteKmer, SequenceUtils
 
 __all__ = ["CortexGraph", "ShardedCortexGraph", "CortexRecord", "CortexHeader", "CortexColor", "CanonicalKmer", "CortexByteKmer",
-           "CortexBinaryKmer", "SequenceUtils", "FindROIs", "Join", "Sort", "FindLowCoverage", "FindShared", "RecoverExcludedKmers", "CovStats", "CortexCollection", "CallHelpers", "CortexVertex", "CortexJDKException", "packCanonical", "lib", "launch_count",
+           "CortexBinaryKmer", "SequenceUtils", "FindROIs", "Join", "Remove", "Sort", "FindLowCoverage", "FindShared", "RecoverExcludedKmers", "CovStats", "CortexCollection", "CallHelpers", "CortexVertex", "CortexJDKException", "packCanonical", "lib", "launch_count",
            "set_option", "device_count", "CC_ALGO_AUTO", "CC_ALGO_BSEARCH", "CC_ALGO_MERGE"]

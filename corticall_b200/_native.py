@@ -79,6 +79,7 @@ SIGNATURES = {
     "cc_find_windows_dev": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_int, _P]),
     "cc_find_packed": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int]),
     "cc_find_packed_dev": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, _P]),
+    "cc_find_records": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "cc_contains_windows": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "cc_bucket_by_owner_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint32, _P, C.c_int, _P, _P, _P, _P]),
     "cc_scatter_results_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, _P, _P]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "cc_find_novel_sharded": (C.c_int, [_P, C.c_int32, _P, C.c_int, _P, _P, C.c_uint64, _U64P]),
     "cc_write_roi_file_sharded": (C.c_int, [_P, C.c_int32, _P, C.c_int, C.c_char_p, _U64P]),
     "cc_join": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "cc_remove": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.POINTER(_P), _U64P]),
     "cc_sort": (C.c_int, [_P, C.POINTER(_P)]),
     "cc_write_graph": (C.c_int, [_P, C.c_char_p]),
     "cc_find_low_coverage": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),

@@ -139,6 +139,10 @@ int parse_header(const uint8_t *buf, uint64_t avail, uint64_t total_size, const 
         return fail(CC_ERR_BAD_TRAILER, "We didn't see a proper header terminator at the expected place in Cortex graph '%s'", path);
     c.pos += 6;
     h.data_offset = c.pos;
+    // kmer_bits must be the word count of kmer_size (CortexRecord.getKmerBits :309-311); a header that disagrees would make every
+    // shift of the 2-bit arithmetic undefined
+    if (h.k == 0 || h.s != (h.k + 31) / 32)
+        return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': kmer_bits %u does not match kmer_size %u", path, h.s, h.k);
     h.record_size = 8ull * h.s + 5ull * h.c;
     if (h.record_size == 0) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': zero-sized records", path);
     h.num_records = (total_size - h.data_offset) / h.record_size;       // floors: trailing partial record ignored
@@ -235,6 +239,7 @@ void destroy(cc_graph *g) {
     if (g->index.bins) cudaFree(g->index.bins);
     if (g->novel_buf) cudaFree(g->novel_buf);
     if (g->novel_idx) cudaFree(g->novel_idx);
+    if (g->small_host) cudaFreeHost(g->small_host);
     if (g->dev_alloc) {
         if (g->dev_alloc_pooled && g->stream) { cudaFreeAsync(g->dev_alloc, g->stream); cudaStreamSynchronize(g->stream); }
         else cudaFree(g->dev_alloc);
@@ -493,7 +498,11 @@ int cc_color_for_sample_name(const cc_graph *g, const char *name, int32_t *out_c
         if (*p == '+' || *p == '-') ++p;
         bool digits = *p != 0;
         for (const char *q = p; *q; ++q) digits &= (*q >= '0' && *q <= '9');
-        if (digits) { color = (int32_t)strtol(name, nullptr, 10); copies = 1; }
+        if (digits) {                     // Integer.valueOf throws NumberFormatException outside int range: then the colour stays -1
+            errno = 0;
+            const long long v = strtoll(name, nullptr, 10);
+            if (errno == 0 && v >= INT32_MIN && v <= INT32_MAX) { color = (int32_t)v; copies = 1; }
+        }
     }
     *out_color = (copies == 1) ? color : -1;
     return CC_OK;
@@ -909,6 +918,51 @@ int cc_find_packed(cc_graph *g, const uint64_t *words, const uint8_t *flags, uin
                           });
 }
 
+// The legacy per-record API in one call: TraversalEngine asks findRecord for a vertex and then for its (up to 8) neighbours
+// (S/utils/traversal/TraversalEngine.java:67-252); the reference answers each from an LRU over mmap'ed pages.  Up to 64 k-mers
+// take ONE kernel launch with no allocation and no staging copies (queries and answers travel through mapped pinned memory
+// kept in the handle); larger batches go through cc_find_ascii and a gather of the records.
+int cc_find_records(cc_graph *g, const uint8_t *kmers, uint64_t nq, int64_t *out_index, void *out_raw) {
+    if (!g || (nq && (!kmers || !out_index))) return fail(CC_ERR_ARG, "null argument");
+    if (nq == 0) return CC_OK;
+    DeviceGuard guard(g->device);
+    if (int rc = ensure_index(g)) return rc;
+    const uint64_t k = g->h.k, S = g->h.record_size;
+    const uint64_t in_bytes = (nq * k + 63) & ~63ull, idx_bytes = nq * 8, raw_bytes = out_raw ? nq * S : 0;
+    if (nq <= 64 && in_bytes + idx_bytes + raw_bytes <= (256u << 10)) {
+        if (!g->small_host) {
+            const size_t cap = (256u << 10) + 4096;
+            if (cudaHostAlloc(reinterpret_cast<void **>(&g->small_host), cap, cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer(reinterpret_cast<void **>(&g->small_dev), g->small_host, 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (g->small_host) { cudaFreeHost(g->small_host); g->small_host = nullptr; }
+                return fail(CC_ERR_CUDA, "cannot allocate mapped pinned staging for cc_find_records");
+            }
+            g->small_bytes = cap;
+        }
+        memcpy(g->small_host, kmers, nq * k);
+        int64_t *d_idx = reinterpret_cast<int64_t *>(g->small_dev + in_bytes);
+        uint8_t *d_raw = out_raw ? g->small_dev + in_bytes + idx_bytes : nullptr;
+        if (int rc = launch_find_small(g, g->small_dev, (uint32_t)nq, d_idx, d_raw, g->stream)) return rc;
+        if (int rc = sync_stream(g, g->stream)) return rc;
+        memcpy(out_index, g->small_host + in_bytes, idx_bytes);
+        if (out_raw) memcpy(out_raw, g->small_host + in_bytes + idx_bytes, raw_bytes);
+        return CC_OK;
+    }
+    if (int rc = cc_find_ascii(g, kmers, nq, out_index, CC_ALGO_AUTO)) return rc;
+    if (out_raw) {
+        // records of the hits, one copy each (this path is for convenience, not speed)
+        uint8_t *dst = static_cast<uint8_t *>(out_raw);
+        for (uint64_t i = 0; i < nq; ++i) {
+            if (out_index[i] < 0) { memset(dst + i * S, 0, S); continue; }
+            const uint64_t local = (uint64_t)out_index[i] - g->first_index;
+            if (g->host_image) memcpy(dst + i * S, g->host_image + g->h.data_offset + local * S, S);
+            else CC_CUDA(cudaMemcpy(dst + i * S, g->dev_body + local * S, S, cudaMemcpyDeviceToHost));
+        }
+    }
+    return CC_OK;
+}
+
 int cc_contains_windows(cc_graph *g, const uint8_t *seq, uint64_t len, uint8_t *out_present) {
     if (!g) return fail(CC_ERR_ARG, "null graph");
     const uint32_t k = g->h.k;
@@ -978,9 +1032,10 @@ int cc_gather_routed_dev(int device, void *const *peer_res, const void *dev_rout
 int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out) {
     if (!graphs || !out || ngraphs < 1) return fail(CC_ERR_ARG, "null argument");
     *out = nullptr;
+    for (int i = 0; i < ngraphs; ++i)
+        if (!graphs[i]) return fail(CC_ERR_ARG, "null graph");
     const int device = graphs[0]->device;
     for (int i = 0; i < ngraphs; ++i) {
-        if (!graphs[i]) return fail(CC_ERR_ARG, "null graph");
         if (graphs[i]->device != device) return fail(CC_ERR_ARG, "graphs to join must live on one device");
         if (graphs[i]->h.k != graphs[0]->h.k)      // CortexCollection.java:43-45
             return fail(CC_ERR_ARG, "Graph kmer sizes are not equal.  Expected k=%u, but found k=%u in graph %s", graphs[0]->h.k,
@@ -1152,6 +1207,36 @@ int cc_find_low_coverage(cc_graph *roi, int32_t min_coverage, cc_graph **out) {
     return make_selected_graph(roi, roi->h, roi->h.c, sel, m, nullptr, nullptr, 0, st, out);
 }
 
+// Remove (S/commands/utils/Remove.java:30-88): the merged view of the primary and the secondary graphs (CortexCollection) is
+// walked; a record with coverage > 0 in any secondary colour is dropped, the others are written with the primary's colours
+// under the primary's header.  K-mers that only a secondary graph holds, with coverage <= 0 there, come out as records with
+// all-zero primary colours -- the reference writes them, so they are written here.
+int cc_remove(cc_graph *primary, cc_graph *const *secondaries, int nsecondaries, cc_graph **out, uint64_t *out_removed) {
+    if (!primary || !out || nsecondaries < 0 || (nsecondaries > 0 && !secondaries)) return fail(CC_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::vector<cc_graph *> all;
+    all.push_back(primary);
+    for (int i = 0; i < nsecondaries; ++i) all.push_back(secondaries[i]);
+    cc_graph *merged = nullptr;
+    if (int rc = cc_join(all.data(), (int)all.size(), &merged)) return rc;
+    std::unique_ptr<cc_graph, void (*)(cc_graph *)> mg(merged, destroy);
+    DeviceGuard guard(merged->device);
+    cudaStream_t st = merged->stream;
+    const uint64_t n = merged->h.num_records;
+    StreamBuf sb(st);
+    int32_t *cov = nullptr; uint8_t *flags = nullptr;
+    if (int rc = CC_SB_ALLOC(sb, cov, n * merged->h.c)) return rc;
+    if (int rc = CC_SB_ALLOC(sb, flags, n)) return rc;
+    if (int rc = merged->scan_ws.ensure(0, 0)) return rc;
+    if (int rc = launch_decode_columns(merged->dev_body, n, merged->h.s, merged->h.c, nullptr, cov, nullptr, merged->scan_ws, merged->sm_count, st)) return rc;
+    if (int rc = launch_remove_flags(cov, n, merged->h.c, primary->h.c, flags, merged->sm_count, st)) return rc;
+    uint32_t *sel = nullptr; uint64_t m = 0;
+    if (int rc = select_flagged(flags, n, &sel, &m, st)) return rc;
+    sb.p.push_back(sel);
+    if (out_removed) *out_removed = n - m;
+    return make_selected_graph(merged, primary->h, primary->h.c, sel, m, nullptr, nullptr, 0, st, out);
+}
+
 // FindShared (S/commands/prefilter/FindShared.java:40-118): the ROI records whose k-mer, looked up in the pedigree graph, has
 // coverage in a colour that is neither the child, a parent nor ignored.
 int cc_find_shared(cc_graph *graph, cc_graph *roi, int32_t child, const int32_t *parents, int nparents, const int32_t *ignore, int nignore,
@@ -1174,6 +1259,10 @@ int cc_find_shared(cc_graph *graph, cc_graph *roi, int32_t child, const int32_t 
     for (int i = 0; i < nignore; ++i)
         if (ignore[i] >= 0 && (uint32_t)ignore[i] < graph->h.c) mask[ignore[i] >> 5] |= 1u << (ignore[i] & 31);
     if (child >= 0 && (uint32_t)child < graph->h.c) mask[child >> 5] |= 1u << (child & 31);
+    // FindShared.java:64-70 dereferences the found record only inside `c != child && !parents.contains(c) && !ignore.contains(c)`:
+    // with every colour excluded a ROI k-mer that is absent from the graph is not an error there, it is simply not shared
+    bool any_free = false;
+    for (uint32_t cc = 0; cc < graph->h.c; ++cc) any_free |= !((mask[cc >> 5] >> (cc & 31)) & 1u);
     if (int rc = CC_SB_ALLOC(sb, dmask, mask.size())) return rc;
     if (int rc = CC_SB_ALLOC(sb, missing, 1)) return rc;
     const unsigned long long none = ~0ull;
@@ -1187,7 +1276,7 @@ int cc_find_shared(cc_graph *graph, cc_graph *roi, int32_t child, const int32_t 
     unsigned long long at = none;
     CC_CUDA(cudaMemcpyAsync(&at, missing, 8, cudaMemcpyDeviceToHost, st));
     CC_CUDA(cudaStreamSynchronize(st));
-    if (at != none)
+    if (at != none && any_free)
         return fail(CC_ERR_ARG, "ROI record %llu is not in the graph (java.lang.NullPointerException at FindShared.java:69 in the reference)", at);
     uint32_t *sel = nullptr; uint64_t m = 0;
     if (int rc = select_flagged(flags, n, &sel, &m, st)) return rc;

@@ -130,6 +130,9 @@ struct cc_graph {
     void *novel_idx = nullptr;
     uint64_t novel_cap = 0;
     std::vector<int32_t> parents_cached;   // what scan_ws.parents currently holds
+    // mapped pinned staging of cc_find_records (the low-latency findRecord path): queries | indices | record bytes
+    uint8_t *small_host = nullptr, *small_dev = nullptr;
+    size_t small_bytes = 0;
 };
 
 namespace cc {
@@ -161,6 +164,7 @@ int launch_pack_windows(const uint8_t *dev_seq, uint64_t len, uint32_t k, uint64
                         uint64_t row_stride /*1 for sliding windows, k for independent rows*/, uint64_t nq, cudaStream_t st);
 int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, int64_t *dev_index,
                        int algo, cudaStream_t st);
+int launch_find_small(cc_graph *g, const uint8_t *dev_kmers, uint32_t nq, int64_t *dev_index, uint8_t *dev_raw, cudaStream_t st);
 int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t len, uint64_t row_stride, uint64_t nq, int64_t *dev_index,
                     int algo, cudaStream_t st);
 int launch_bucket_by_owner(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t s,
@@ -173,6 +177,7 @@ int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t
 int launch_gather_records(const uint8_t *body, const uint32_t *perm, uint64_t n, uint32_t S, uint8_t *out, cudaStream_t st);
 // prefilter.cu
 int launch_lowcov_flags(const int32_t *cov, uint64_t n, uint32_t c, int32_t min_cov, uint8_t *flags, int sm_count, cudaStream_t st);
+int launch_remove_flags(const int32_t *cov, uint64_t n, uint32_t c, uint32_t c_primary, uint8_t *flags, int sm_count, cudaStream_t st);
 int launch_recover_classes(const int32_t *cov, uint64_t n, uint32_t c, uint32_t child, uint8_t *cls, uint8_t *find_flags, int sm_count,
                            cudaStream_t st);
 int launch_recover_finalize(const uint8_t *cls, const int64_t *idx, const uint8_t *dirty_body, uint32_t dirty_S, uint32_t s, uint64_t dirty_first,

@@ -794,6 +794,34 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
     }
 }
 
+// findRecord for a handful of k-mers in one launch (the legacy per-record API: a vertex and its neighbours): one warp per
+// query reads the ASCII k-mer straight from mapped host memory, canonicalises it exactly (row_canonical_warp), searches
+// the line index and copies the record's bytes back into mapped host memory -- no staging copies on either side.
+template <int S, int KW>
+__global__ void __launch_bounds__(256) find_small_kernel(const uint8_t *__restrict__ kmers, uint32_t nq, uint32_t k, IndexView ix,
+                                                         const uint8_t *__restrict__ body, uint32_t rec_bytes,
+                                                         int64_t *__restrict__ out_index, uint8_t *__restrict__ out_raw) {
+    const uint32_t w = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    const bool have = w < nq;                                   // whole warps: the search below is warp-collective
+    uint64_t q[S];
+    uint32_t fl = 2u;
+    if (have) fl = row_canonical_warp<S>(kmers + (size_t)w * k, k, lane, q);
+    else {
+#pragma unroll
+        for (int i = 0; i < S; ++i) q[i] = 0;
+    }
+    const uint64_t pol = make_line_policy(0u);
+    int64_t r = lookup_lines_warp<S, KW>(ix, ix.bins, pol, q, have && lane == 0 && (fl & 6u) == 0);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (!have) return;
+    if (lane == 0) out_index[w] = r;
+    if (out_raw) {
+        uint8_t *dst = out_raw + (size_t)w * rec_bytes;
+        const uint8_t *src = r >= 0 ? body + (uint64_t)(r - (int64_t)ix.first_index) * rec_bytes : nullptr;
+        for (uint32_t b = lane; b < rec_bytes; b += 32u) dst[b] = src ? src[b] : (uint8_t)0;
+    }
+}
+
 template <int S>
 __device__ __forceinline__ uint32_t owner_of(const uint64_t (&q)[S], const uint64_t *__restrict__ splitters, int nshards) {
     // number of splitters <= q  (splitter j = first key of shard j+1)
@@ -1576,6 +1604,18 @@ int plan_find(Kernel kernel, const cc_graph *g, uint64_t work, FindLaunch &fl) {
     fl.smem = fl.bins_in_smem ? bins_bytes : 0;
     if (fl.smem > 48 * 1024) CC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fl.smem));
     fl.grid = resident_grid(kernel, kFindBlock, fl.smem, (work + kFindBlock - 1) / kFindBlock, g->sm_count);
+    return CC_OK;
+}
+
+int launch_find_small(cc_graph *g, const uint8_t *dev_kmers, uint32_t nq, int64_t *dev_index, uint8_t *dev_raw, cudaStream_t st) {
+    if (int rc = check_k(g->h.k)) return rc;
+    if (nq == 0) return CC_OK;
+    IndexView ix = view_of(g);
+    CC_DISPATCH_SKW(g->h.s, wire_words(g->h.k), {
+        find_small_kernel<S_, KW_><<<(nq + 7) / 8, 256, 0, st>>>(dev_kmers, nq, g->h.k, ix, g->dev_body, (uint32_t)g->h.record_size, dev_index, dev_raw);
+    });
+    count_launch();
+    CC_CUDA(cudaGetLastError());
     return CC_OK;
 }
 

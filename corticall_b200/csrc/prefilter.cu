@@ -39,6 +39,17 @@ __global__ void lowcov_flags_kernel(const int32_t *__restrict__ cov, uint64_t n,
         flags[i] = cov[i * c] < min_cov ? 1 : 0;
 }
 
+// Remove.java:47-55: a merged record is dropped when a colour of a secondary graph (colours c_primary .. c-1 of the
+// collection) has coverage > 0 (signed); flags = 1 for the records that are KEPT.
+__global__ void remove_flags_kernel(const int32_t *__restrict__ cov, uint64_t n, uint32_t c, uint32_t c_primary, uint8_t *__restrict__ flags) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t *row = cov + i * c;
+        bool found = false;
+        for (uint32_t cc = c_primary; cc < c; ++cc) found |= row[cc] > 0;
+        flags[i] = found ? 0 : 1;
+    }
+}
+
 // RecoverExcludedKmers.java:50-62: class 1 = child coverage > 0 (written as is); class 2 = candidate (child <= 0 and
 // another colour > 0: looked up in the dirty graph); 0 = dropped.  find_flags: 0 for candidates, 2 (skip) otherwise.
 __global__ void recover_classes_kernel(const int32_t *__restrict__ cov, uint64_t n, uint32_t c, uint32_t child, uint8_t *__restrict__ cls,
@@ -151,6 +162,14 @@ int grid_of(uint64_t n, int sm_count) {
 int launch_lowcov_flags(const int32_t *cov, uint64_t n, uint32_t c, int32_t min_cov, uint8_t *flags, int sm_count, cudaStream_t st) {
     if (n == 0) return CC_OK;
     lowcov_flags_kernel<<<grid_of(n, sm_count), kPBlock, 0, st>>>(cov, n, c, min_cov, flags);
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_remove_flags(const int32_t *cov, uint64_t n, uint32_t c, uint32_t c_primary, uint8_t *flags, int sm_count, cudaStream_t st) {
+    if (n == 0) return CC_OK;
+    remove_flags_kernel<<<grid_of(n, sm_count), kPBlock, 0, st>>>(cov, n, c, c_primary, flags);
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;

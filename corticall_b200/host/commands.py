@@ -74,6 +74,22 @@ class Join:
         return n
 
 
+class Remove:
+    """`Remove -g primary.ctx -s secondary.ctx ... -o out.ctx` (S/commands/utils/Remove.java:19-88): the primary graph minus
+    the k-mers with coverage in a secondary graph."""
+
+    def __init__(self, PGRAPH: CortexGraph, SGRAPH, out):
+        self.PGRAPH, self.SGRAPH, self.out = PGRAPH, list(SGRAPH), out
+
+    def execute(self) -> tuple[int, int]:
+        """-> (numKept, numRemoved), the two counters the reference logs."""
+        kept, removed = self.PGRAPH.remove(self.SGRAPH)
+        kept.writeGraph(self.out)
+        n = kept.getNumRecords()
+        kept.dispose()
+        return n, removed
+
+
 class Sort:
     """`Sort -cg raw.ctx -o sorted.ctx` (S/commands/utils/Sort.java:12-51)."""
 

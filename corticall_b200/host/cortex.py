@@ -373,14 +373,26 @@ class CortexGraph:
             if len(b) > self.header.kmerSize:
                 raise IndexError("ArrayIndexOutOfBoundsException: query longer than the graph's k-mer size")
             return None
-        idx = self.findRecordIndices(np.frombuffer(b, dtype=np.uint8).reshape(1, -1))
-        i = int(idx[0])
-        if i < 0:
-            return None
-        saved = self._block
-        w, c, e = self.decodeRecords(i - self.firstIndex, 1)
-        self._block = saved
-        return self._make_record(w[0], c[0], e[0])
+        idx, raw = self.findRecords(np.frombuffer(b, dtype=np.uint8).reshape(1, -1))
+        return self._record_from_raw(raw[0]) if idx[0] >= 0 else None
+
+    def findRecords(self, kmers):
+        """cc_find_records: a handful of k-mers (a vertex and its neighbours) in one call and one kernel launch ->
+        (int64 indices, uint8 [nq, recordSize] raw records, zeros for misses)."""
+        q = np.ascontiguousarray(kmers, dtype=np.uint8)
+        if q.ndim != 2 or q.shape[1] != self.header.kmerSize:
+            raise ValueError("queries must be [nq, %d] ASCII bytes" % self.header.kmerSize)
+        idx = np.empty(q.shape[0], dtype=np.int64)
+        raw = np.empty((q.shape[0], self.recordSize), dtype=np.uint8)
+        N.check(N.lib().cc_find_records(self._h, _ptr(q), q.shape[0], _ptr(idx), _ptr(raw)))
+        return idx, raw
+
+    def _record_from_raw(self, raw: np.ndarray) -> CortexRecord:
+        s, c = self.header.kmerBits, self.header.numColors
+        words = raw[:8 * s].copy().view("<u8")
+        cov = raw[8 * s:8 * s + 4 * c].copy().view("<i4")
+        edges = raw[8 * s + 4 * c:8 * s + 5 * c].copy()
+        return self._make_record(words, cov, edges)
 
     def findRecordIndices(self, kmers, algo: int = N.CC_ALGO_AUTO) -> np.ndarray:
         """kmers: uint8 [nq, k] ASCII (any orientation) -> int64 record index per query, -1 = the reference's null."""
@@ -461,6 +473,15 @@ class CortexGraph:
         self._block = None
         self._nextRecord = self._record_at(0)
         return self
+
+    def remove(self, secondaries):
+        """Remove.java:30-88 with this = the primary graph -> (new graph of the kept records, number removed)."""
+        sec = list(secondaries)
+        arr = (N._P * max(len(sec), 1))(*[g._h for g in sec])
+        h = N._P()
+        removed = C.c_uint64(0)
+        N.check(N.lib().cc_remove(self._h, arr, len(sec), C.byref(h), C.byref(removed)))
+        return CortexGraph._adopt(h, self._device), int(removed.value)
 
     def sorted(self) -> "CortexGraph":
         """Sort (S/commands/utils/Sort.java:19-50): the same records in ascending k-mer order, as a new graph."""

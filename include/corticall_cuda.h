@@ -174,6 +174,11 @@ CC_API int cc_find_windows_dev(cc_graph *g, const uint8_t *dev_seq, uint64_t len
 CC_API int cc_find_packed(cc_graph *g, const uint64_t *words, const uint8_t *flags, uint64_t nq, int64_t *out_index, int algo);
 CC_API int cc_find_packed_dev(cc_graph *g, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq,
                               int64_t *dev_index, int algo, void *stream);
+/* The legacy per-record findRecord for a handful of k-mers in one call -- a vertex and its neighbours, as TraversalEngine asks
+ * for them (S/utils/traversal/TraversalEngine.java:67-252): out_index[i] = record index or -1; out_raw (optional) receives the
+ * record_size bytes of every hit's record (zeros for a miss), so the caller needs no second call to decode it.  Up to 64
+ * k-mers cost one kernel launch, no allocation and no staging copies. */
+CC_API int cc_find_records(cc_graph *g, const uint8_t *kmers, uint64_t nq, int64_t *out_index, void *out_raw);
 /* ROI membership (`rois.contains(new CanonicalKmer(window))`, Call.java:191-197,2425-2451): 1/0 per window. */
 CC_API int cc_contains_windows(cc_graph *g, const uint8_t *seq, uint64_t len, uint8_t *out_present);
 
@@ -270,6 +275,10 @@ CC_API int cc_write_roi_file_sharded(cc_sharded *sh, int32_t child, const int32_
  * coverage 0 and no edges in that graph's colours.  All graphs on one device, same k.  Returns a new device-resident
  * graph (dispose with cc_dispose). */
 CC_API int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out);
+/* Remove (S/commands/utils/Remove.java:30-88): the records of the merged view of `primary` and the secondary graphs that
+ * have no coverage > 0 in any secondary colour, written with the primary's colours under the primary's header (a new
+ * device-resident graph).  *out_removed (optional) = merged records dropped. */
+CC_API int cc_remove(cc_graph *primary, cc_graph *const *secondaries, int nsecondaries, cc_graph **out, uint64_t *out_removed);
 /* Sort (S/commands/utils/Sort.java:19-50): a new graph with the records in ascending k-mer order (stable), same header. */
 CC_API int cc_sort(cc_graph *g, cc_graph **out);
 /* CortexGraphWriter (S/utils/io/graph/cortex/CortexGraphWriter.java:31-138): header from the colours, then every record. */

@@ -65,6 +65,12 @@ public final class NativeCortex {
     static native long findNovel(long handle, int child, int[] parents, byte[] outRecords, long[] outIndex);
     static native long writeRoiFile(long handle, int child, int[] parents, String outPath);
 
+    // legacy findRecord, batched ------------------------------------------------------------- cc_find_records
+    /** nq k-byte ASCII k-mers (a vertex and its neighbours) in ONE native call and one kernel launch: outIndex[i] = record index
+     *  or -1; for every hit the decoded record lands in binaryKmers (kmerBits longs, Java convention), coverages and edges
+     *  (numColors each) at slot i. */
+    static native void findRecords(long handle, byte[] kmers, int nq, long[] outIndex, long[] binaryKmers, int[] coverages, byte[] edges);
+
     // K3+K4 ------------------------------------------------------------------------------------ cc_find_ascii / cc_find_windows / cc_contains_windows
     /** nq k-byte ASCII k-mers, row-major -> record index per query, -1 = null. */
     static native void findAscii(long handle, byte[] kmers, int nq, long[] outIndex);
@@ -79,6 +85,8 @@ public final class NativeCortex {
     /** Each returns the handle of a NEW device-resident graph (dispose it). */
     static native long join(long[] handles);
     static native long sort(long handle);
+    /** cc_remove: {handle of the new graph, merged records removed}. */
+    static native long[] remove(long primaryHandle, long[] secondaryHandles);
     static native void writeGraph(long handle, String outPath);
 
     // pre-filters / recovery ------------------------------------------------------------------- cc_find_low_coverage / cc_find_shared / ...
@@ -87,4 +95,17 @@ public final class NativeCortex {
     static native long recoverExcludedKmers(long graphHandle, long dirtyHandle, int child);
     /** {coverage0, count0, coverage1, count1, ...} in ascending coverage (cc_cov_stats). */
     static native int[] covStats(long handle, int child, int[] parents);
+
+    // one graph over several GPUs ---------------------------------------------------------------- cc_open_sharded / cc_*_sharded
+    /** The record array cut into k-mer-range shards, one per device id (ArgumentHandler.java:271-274 constructs ONE graph per file). */
+    static native long openSharded(String path, int[] devices);
+    static native void disposeSharded(long shardedHandle);
+    /** {numShards, numRecords, kmerSize, numColors} */
+    static native long[] shardedInfo(long shardedHandle);
+    /** {borrowed cc_graph handle of the shard (header, colours, decodeRecords), device, first record index} */
+    static native long[] shardedShard(long shardedHandle, int rank);
+    static native void findAsciiSharded(long shardedHandle, byte[] kmers, int nq, long[] outIndex);
+    static native void findWindowsSharded(long shardedHandle, byte[] seq, long[] outIndex);
+    static native long findNovelSharded(long shardedHandle, int child, int[] parents, byte[] outRecords, long[] outIndex);
+    static native long writeRoiFileSharded(long shardedHandle, int child, int[] parents, String outPath);
 }

@@ -452,15 +452,18 @@ int orc_find_shared(orc_graph *graph, orc_graph *roi, int32_t child, const int32
         orc_get_record(roi, i, bk, rcov, red);
         orc_decode_binary_kmer(bk, roi->h.kmer_size, roi->h.kmer_bits, kmer);           /* rr.getCanonicalKmer() */
         const int64_t at = orc_find_record(graph, kmer);                                /* GRAPH.findRecord(...) :65 */
-        if (at < 0) { rc = -1; break; }                                                 /* cr == null -> NPE at :67 */
-        orc_get_record(graph, (uint64_t)at, gk, gcov, ged);
+        if (at >= 0) orc_get_record(graph, (uint64_t)at, gk, gcov, ged);
         int shared = 0;
         for (uint32_t c = 0; c < graph->h.num_colors; ++c) {                            /* :67-73 */
-            if ((int32_t)c != child && !in_list(parents, nparents, (int32_t)c) && !in_list(ignore, nignore, (int32_t)c) && gcov[c] > 0) {
-                shared = 1;
-                break;
+            if ((int32_t)c != child && !in_list(parents, nparents, (int32_t)c) && !in_list(ignore, nignore, (int32_t)c)) {
+                if (at < 0) { rc = -1; break; }                                         /* cr == null: cr.getCoverage(c) is the NPE at :67; */
+                if (gcov[c] > 0) {                                                      /* the && short-circuits, so only a free colour gets here */
+                    shared = 1;
+                    break;
+                }
             }
         }
+        if (rc) break;
         written[i] = (uint8_t)shared;                                                   /* second loop :95-104 writes the shared ones */
     }
     free(rcov); free(gcov); free(red); free(ged); free(kmer);
@@ -519,4 +522,71 @@ void orc_cov_stats_pairs(orc_graph *graph, int32_t child, const int32_t *parents
         weight[i] = counts ? np + nc : 0;
     }
     free(cov); free(ed);
+}
+
+/* ---------------------------------------------------------------- Remove over a CortexCollection
+ * S/commands/utils/Remove.java:30-88 driving S/utils/io/graph/cortex/CortexCollection.java:245-293: next() picks the graph whose
+ * pending record has the smallest k-mer STRING, merges every graph whose pending record has that same string into one record
+ * (colours concatenated in graph order, absent graphs zero), and advances those graphs.  Remove drops the merged record when a
+ * colour >= PGRAPH.getNumColors() has coverage > 0 and otherwise writes the primary's colours.  graphs[0] is the primary.
+ * out: kept records in the primary's on-disk layout (s LE words, cp LE uint32, cp edge bytes), at most cap of them.
+ * Returns the number kept; *removed gets the number dropped. */
+uint64_t orc_remove(orc_graph **graphs, int ngraphs, uint8_t *out, uint64_t cap, uint64_t *removed) {
+    const uint32_t k = graphs[0]->h.kmer_size, s = graphs[0]->h.kmer_bits, cp = graphs[0]->h.num_colors;
+    uint32_t ctot = 0;
+    for (int i = 0; i < ngraphs; ++i) ctot += graphs[i]->h.num_colors;
+    uint64_t *pos = calloc((size_t)ngraphs, sizeof(uint64_t));                      /* nextRecs[i] = graph i's pending record */
+    uint8_t *kstr = malloc((size_t)ngraphs * (k + 1));
+    int64_t bk[ORC_MAX_WORDS], merged_bk[ORC_MAX_WORDS];
+    int32_t *cov = malloc(4 * (size_t)(ctot + 1)), *gcov = malloc(4 * (size_t)(ctot + 1));
+    uint8_t *edges = malloc(ctot + 1), *ged = malloc(ctot + 1);
+    for (int i = 0; i < ngraphs; ++i)
+        if (pos[i] < graphs[i]->h.num_records) record_kmer_bytes(graphs[i], pos[i], kstr + (size_t)i * (k + 1));
+    uint64_t kept = 0, dropped = 0;
+    const size_t out_size = 8 * (size_t)s + 5 * (size_t)cp;
+    for (;;) {
+        int lowc = -1;                                                              /* CortexCollection.next :245-254 */
+        for (int i = 0; i < ngraphs; ++i) {
+            if (pos[i] >= graphs[i]->h.num_records) continue;                       /* nextRecs[i] == null */
+            if (lowc == -1 || memcmp(kstr + (size_t)i * (k + 1), kstr + (size_t)lowc * (k + 1), k) < 0) lowc = i;   /* String.compareTo on ACGT */
+        }
+        if (lowc < 0) break;                                                        /* hasNext() == false */
+        uint8_t comp[ORC_MAX_WORDS * 32 + 1];
+        memcpy(comp, kstr + (size_t)lowc * (k + 1), k);
+        memset(cov, 0, 4 * (size_t)ctot);
+        memset(edges, 0, ctot);
+        uint32_t c0 = 0;
+        for (int i = 0; i < ngraphs; ++i) {                                         /* :262-283 */
+            const uint32_t ci = graphs[i]->h.num_colors;
+            if (pos[i] < graphs[i]->h.num_records && memcmp(kstr + (size_t)i * (k + 1), comp, k) == 0) {
+                orc_get_record(graphs[i], pos[i], bk, gcov, ged);
+                memcpy(merged_bk, bk, 8 * (size_t)s);                               /* binaryKmer = cr.getBinaryKmer() */
+                for (uint32_t c = 0; c < ci; ++c) { cov[c0 + c] = gcov[c]; edges[c0 + c] = ged[c]; }
+                pos[i]++;                                                           /* nextRecs[i] = graphList.get(i).next() */
+                if (pos[i] < graphs[i]->h.num_records) record_kmer_bytes(graphs[i], pos[i], kstr + (size_t)i * (k + 1));
+            }
+            c0 += ci;
+        }
+        int found = 0;                                                              /* Remove.java:47-55 */
+        for (uint32_t c = cp; c < ctot; ++c) if (cov[c] > 0) { found = 1; break; }
+        if (!found) {                                                               /* :57-73 + CortexGraphWriter.addRecord */
+            if (kept < cap) {
+                uint8_t *p = out + kept * out_size;
+                for (uint32_t w = 0; w < s; ++w) {                                  /* the writer emits each long big-endian: the on-disk word */
+                    const uint64_t v = (uint64_t)merged_bk[w];
+                    for (int b = 0; b < 8; ++b) p[8 * w + b] = (uint8_t)(v >> (56 - 8 * b));
+                }
+                for (uint32_t c = 0; c < cp; ++c) {
+                    const uint32_t v = (uint32_t)cov[c];
+                    p[8 * s + 4 * c] = (uint8_t)v; p[8 * s + 4 * c + 1] = (uint8_t)(v >> 8);
+                    p[8 * s + 4 * c + 2] = (uint8_t)(v >> 16); p[8 * s + 4 * c + 3] = (uint8_t)(v >> 24);
+                }
+                memcpy(p + 8 * s + 4 * cp, edges, cp);
+            }
+            kept++;
+        } else dropped++;
+    }
+    free(pos); free(kstr); free(cov); free(gcov); free(edges); free(ged);
+    if (removed) *removed = dropped;
+    return kept;
 }

@@ -127,6 +127,10 @@ uint64_t orc_recover_excluded_kmers(orc_graph *graph, orc_graph *dirty, int32_t 
  * weight[i] = numberOfParents + numberOfChildren. */
 void orc_cov_stats_pairs(orc_graph *graph, int32_t child, const int32_t *parents, int nparents, int32_t *key, int32_t *weight);
 
+/* S/commands/utils/Remove.java:30-88 over CortexCollection.next (:245-293), record by record: graphs[0] is the primary; kept records
+ * (primary colours, on-disk layout) go to out (at most cap); returns the number kept, *removed the number dropped. */
+uint64_t orc_remove(orc_graph **graphs, int ngraphs, uint8_t *out, uint64_t cap, uint64_t *removed);
+
 #ifdef __cplusplus
 }
 #endif

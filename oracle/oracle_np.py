@@ -407,6 +407,23 @@ def join(bufs: list[bytes]) -> bytes:
     return write_header(k, s, colors) + out.tobytes()
 
 
+def remove(primary_buf: bytes, secondary_bufs: list[bytes]) -> tuple[bytes, int]:
+    """S/commands/utils/Remove.java:30-88: walk the merged collection (join() above); `found` = coverage > 0 (Java int) in a
+    colour >= PGRAPH.getNumColors(); the records that are not found are written with the primary's colours under the primary's
+    header (re-emitted by CortexGraphWriter).  Returns (file bytes, records removed)."""
+    merged = join([primary_buf] + list(secondary_bufs))
+    hm, hp = parse_header(merged), parse_header(primary_buf)
+    rec = records_view(merged, hm)
+    cp = hp["num_colors"]
+    found = (java_coverage(rec["cov"][:, cp:]) > 0).any(axis=1) if hm["num_colors"] > cp else np.zeros(len(rec), dtype=bool)
+    keep = rec[~found]
+    out = np.zeros(len(keep), dtype=record_dtype(hp["kmer_bits"], cp))
+    out["kmer"] = keep["kmer"]
+    out["cov"] = keep["cov"][:, :cp]
+    out["edges"] = keep["edges"][:, :cp]
+    return _rewritten_header(hp, hp["colors"]) + out.tobytes(), int(found.sum())
+
+
 def sort_graph(buf: bytes) -> bytes:
     """S/commands/utils/Sort.java:19-50: Arrays.sort of the records by k-mer string (stable), same header re-emitted by
     CortexGraphWriter (total_sequence byte-reversed, see join())."""
@@ -450,10 +467,11 @@ def find_shared(graph_buf: bytes, roi_buf: bytes, child: int, parents: list[int]
     hg, hr = parse_header(graph_buf), parse_header(roi_buf)
     g, r = records_view(graph_buf, hg), records_view(roi_buf, hr)
     idx = find_packed(np.ascontiguousarray(g["kmer"]), np.ascontiguousarray(r["kmer"]))
-    if (idx < 0).any():
-        raise KeyError("ROI record %d is not in the graph" % int(np.nonzero(idx < 0)[0][0]))
-    cov = java_coverage(g["cov"][idx])
     free = np.array([c != child and c not in set(parents) and c not in set(ignore) for c in range(hg["num_colors"])], dtype=bool)
+    # the null record is dereferenced only for a colour that passes the three exclusions (short-circuit && at :67)
+    if (idx < 0).any() and free.any():
+        raise KeyError("ROI record %d is not in the graph" % int(np.nonzero(idx < 0)[0][0]))
+    cov = java_coverage(g["cov"][np.maximum(idx, 0)]) if len(g) else np.zeros((len(r), hg["num_colors"]), dtype=np.int64)
     shared = (cov[:, free] > 0).any(axis=1) if free.any() else np.zeros(len(r), dtype=bool)
     return _rewritten_header(hr, hr["colors"]) + r[shared].tobytes()
 

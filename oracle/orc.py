@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         L.orc_find_shared.argtypes = [G, G, C.c_int32, i32p, C.c_int, i32p, C.c_int, u8p]; L.orc_find_shared.restype = C.c_int
         L.orc_recover_excluded_kmers.argtypes = [G, G, C.c_int32, u8p, i32p]; L.orc_recover_excluded_kmers.restype = C.c_uint64
         L.orc_cov_stats_pairs.argtypes = [G, C.c_int32, i32p, C.c_int, i32p, i32p]; L.orc_cov_stats_pairs.restype = None
+        L.orc_remove.argtypes = [C.POINTER(G), C.c_int, u8p, C.c_uint64, u64p]; L.orc_remove.restype = C.c_uint64
         _LIB = L
     return _LIB
 
@@ -166,6 +167,18 @@ def cov_stats_pairs(graph: "Graph", child: int, parents):
     pa = _i32(parents)
     lib().orc_cov_stats_pairs(C.byref(graph.g), int(child), _p(pa) if pa.size else None, pa.size, _p(key), _p(weight))
     return key[:n], weight[:n]
+
+
+def remove_records(primary: "Graph", secondaries: list["Graph"]):
+    """Remove.java over the merged collection, record by record -> (kept records as bytes in the primary's layout, removed)."""
+    gs = [primary] + list(secondaries)
+    arr = (C.POINTER(OrcGraph) * len(gs))(*[C.pointer(g.g) for g in gs])
+    cap = sum(g.h.num_records for g in gs)
+    osz = 8 * primary.h.kmer_bits + 5 * primary.h.num_colors
+    out = np.empty(max(cap, 1) * osz, dtype=np.uint8)
+    removed = C.c_uint64(0)
+    kept = int(lib().orc_remove(arr, len(gs), _p(out), cap, C.byref(removed)))
+    return out[:kept * osz].tobytes(), int(removed.value)
 
 
 def find_rois_body(body: np.ndarray, n: int, k: int, s: int, c: int, child: int, parents, faithful=False, cap=None):

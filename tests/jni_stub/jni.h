@@ -16,6 +16,7 @@ struct JNIEnv {
   jsize GetArrayLength(jarray);
   jlong* GetLongArrayElements(jlongArray, jboolean*); void ReleaseLongArrayElements(jlongArray, jlong*, jint);
   jint* GetIntArrayElements(jintArray, jboolean*); void ReleaseIntArrayElements(jintArray, jint*, jint);
+  void SetByteArrayRegion(jbyteArray, jsize, jsize, const jbyte*);
   jbyte* GetByteArrayElements(jbyteArray, jboolean*); void ReleaseByteArrayElements(jbyteArray, jbyte*, jint);
   jboolean* GetBooleanArrayElements(jbooleanArray, jboolean*); void ReleaseBooleanArrayElements(jbooleanArray, jboolean*, jint);
 };

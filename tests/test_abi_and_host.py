@@ -68,6 +68,9 @@ def test_header_errors_mirror_the_reference(fixture_ctx, tmp_path):
     assert rc == N.CC_ERR_BAD_TRAILER and "proper header terminator" in msg
     rc, msg = open_status(fixture_ctx[:60])
     assert rc == N.CC_ERR_IO
+    # kmer_bits that is not ceil(kmer_size / 32) (k = 31 claiming 2 words): every shift of the 2-bit arithmetic would be undefined
+    rc, msg = open_status(fixture_ctx[:14] + b"\x02\0\0\0" + fixture_ctx[18:])
+    assert rc == N.CC_ERR_IO and "kmer_bits 2 does not match kmer_size 31" in msg
     rc, _ = open_status(b"cortex" + fixture_ctx[6:])           # equalsIgnoreCase: header accepted, fails only for lack of a device
     assert rc == (0 if HAS_GPU else N.CC_ERR_CUDA)
     h = N._P()
@@ -216,3 +219,57 @@ def test_c_abi_from_plain_c_on_the_fixture(tmp_path):
         assert p.returncode == 0, p.stderr
         assert "version 6 k 31 words 1 colours 2 records 66" in p.stdout
         assert "novel %d\n" % novel in p.stdout and "found %d of %d at the reported index" % (novel, novel) in p.stdout
+
+
+@pytest.mark.gpu
+def test_c_abi_sharded_from_plain_c(tmp_path):
+    """The multi-GPU entry points driven from plain C (tools/abi_example.c with CC_DEVICES): one cc_sharded handle over several
+    shards -- on every GPU of the box, or three shards on device 0 -- gives the single-GPU novel records and lookup indices."""
+    import subprocess
+    import torch
+    from tools import synth
+    exe, fixture = _build_abi_example(tmp_path)
+    big = tmp_path / "big.ctx"
+    big.write_bytes(synth.make_ctx_file(21, 300000, 47, 4, novel_permille=30))
+    ndev = torch.cuda.device_count()
+    lists = ["0,0,0"] + ([",".join(str(i) for i in range(ndev))] if ndev >= 2 else [])
+    for path in (fixture, str(big)):
+        for devs in lists:
+            p = subprocess.run([exe, path, "0", "1"], capture_output=True, text=True, env=dict(os.environ, CC_DEVICES=devs))
+            assert p.returncode == 0, p.stdout + p.stderr
+            assert "sharded over %d devices" % len(devs.split(",")) in p.stdout and "equal the single-GPU answers" in p.stdout
+
+
+@pytest.mark.gpu
+def test_find_records_one_call_per_vertex():
+    """cc_find_records: the legacy per-record findRecord for a vertex and its neighbours in one call (indices + record bytes),
+    on the fast path (<= 64 k-mers, one launch, mapped pinned staging) and beyond it; equal to findRecordIndices + getRawRecords."""
+    import numpy as np
+    import torch
+    import corticall_b200 as cb
+    from oracle import orc
+    from tools import synth
+    for k, c, n in ((47, 4, 50000), (31, 2, 3000), (95, 3, 2000), (31, 1000, 300)):
+        ctx = synth.make_ctx_file(3 + k, n, k, c, adv_period=0)
+        g = cb.CortexGraph(ctx)
+        og = orc.Graph(ctx)
+        words, _, _ = g.decodeRecords(0, n)
+        tw = [torch.from_numpy(words[:, w].copy().view(np.int64)) for w in range(g.getKmerBits())]
+        a, _, _ = synth.make_queries(8, tw, k, 400, corrupt_permille=50)
+        qa = a.numpy()
+        want = og.find_batch(qa)
+        launches0 = cb.launch_count()
+        for nq in (1, 9, 64, 65, 400):
+            idx, raw = g.findRecords(qa[:nq])
+            assert idx.tolist() == want[:nq].tolist(), (k, nq)
+            for i in range(nq):
+                if idx[i] >= 0:
+                    assert (raw[i] == g.getRawRecords(int(idx[i]), 1)[0]).all()
+                else:
+                    assert not raw[i].any()
+        assert g.findRecord(qa[0].tobytes()) == (g.getRecord(int(want[0])) if want[0] >= 0 else None)
+        if c < 100:
+            lc = cb.launch_count()
+            g.findRecords(qa[:9])
+            assert cb.launch_count() - lc == 1          # one kernel for the vertex and its eight neighbours
+        g.dispose()

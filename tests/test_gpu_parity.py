@@ -810,8 +810,13 @@ def test_prefilters_vs_oracle(tmp_path, k, c, n):
         assert onp.parse_header(onp.find_shared(ctx, roi_bytes, 0, pcols, []))["num_records"] > 0
     # a ROI k-mer that is not in the graph: NullPointerException in the reference, an error here
     stray = cb.CortexGraph(_one_colour_graph(np.full((1, graph.getKmerBits()), 3, dtype=np.uint64), [1], [0], k, names[0]))
-    with pytest.raises(cb.CortexJDKException):
-        graph.findShared(stray, 0, pcols, [])
+    if len(set(pcols) | {0}) < c:
+        with pytest.raises(cb.CortexJDKException):
+            graph.findShared(stray, 0, pcols, [])
+    # ... unless every colour is excluded: then the reference never dereferences the null record (FindShared.java:67 short-circuits)
+    none_shared = graph.findShared(stray, 0, pcols, list(range(c)))
+    assert none_shared.getNumRecords() == 0
+    none_shared.dispose()
     stray.dispose()
 
     # RecoverExcludedKmers: the dirty graph holds every third k-mer of the pedigree graph plus strangers, coverage 0 / small / >= 2^31
@@ -857,3 +862,30 @@ def test_prefilters_empty_graph(tmp_path):
     rec, nrec = g.recoverExcludedKmers(g, 0)
     assert rec.getNumRecords() == 0 and nrec == 0
     rec.dispose(); g.dispose()
+
+
+@pytest.mark.parametrize("k,shapes", [(31, [(2, 15000), (1, 12000), (3, 8000)]), (47, [(4, 30000), (1, 25000)]), (47, [(1, 20000)]),
+                                      (63, [(21, 3000), (2, 2500), (1, 1)]), (95, [(1, 700), (2, 0), (1, 900)]), (31, [(1, 0), (1, 500)])])
+def test_remove_vs_oracle(tmp_path, k, shapes):
+    """cc_remove / Remove.execute (S/commands/utils/Remove.java:30-88): the primary graph minus the k-mers covered by a secondary
+    graph, bit-exact file against the oracle (both restatements), including the reference's all-zero records for k-mers only a
+    secondary graph holds with coverage <= 0 and adversarial coverages >= 2^31."""
+    from oracle import oracle_np as onp
+    pool = synth.random_canonical_keys(5 + k, int(max(n for _, n in shapes) * 1.4) + 10, k, "cpu")
+    ctxs, graphs = [], []
+    for gi, (c, n) in enumerate(shapes):
+        g = torch.Generator().manual_seed(gi)
+        pick = torch.sort(torch.randperm(len(pool[0]), generator=g)[:n]).values
+        cov, edges = synth.coverage_and_edges(50 + gi, n, c, "cpu", novel_permille=100, adv_period=7)
+        body = synth.assemble_records([w[pick] for w in pool], cov, edges) if n else torch.zeros((0, 8 * len(pool) + 5 * c), dtype=torch.uint8)
+        ctxs.append(synth.header_bytes(k, c, ["g%d_%d" % (gi, j) for j in range(c)]) + body.numpy().tobytes())
+        graphs.append(cb.CortexGraph(ctxs[-1]))
+    want, removed = onp.remove(ctxs[0], ctxs[1:])
+    o_rec, o_removed = orc.remove_records(orc.Graph(ctxs[0]), [orc.Graph(x) for x in ctxs[1:]])
+    assert o_removed == removed and o_rec == want[onp.parse_header(want)["data_offset"]:]
+    out = tmp_path / "kept.ctx"
+    kept, got_removed = cb.Remove(graphs[0], graphs[1:], out).execute()
+    assert got_removed == removed and kept == onp.parse_header(want)["num_records"]
+    assert out.read_bytes() == want
+    for g in graphs:
+        g.dispose()

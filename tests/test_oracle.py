@@ -10,6 +10,7 @@ import pytest
 from oracle import oracle_np as onp
 from oracle import orc
 from tools import synth
+import torch
 
 
 # ---------------------------------------------------------------- header / numRecordsTest / getShortSampleNames
@@ -372,6 +373,11 @@ def test_prefilter_oracles_hand_checked():
     assert onp.parse_header(onp.find_shared(g, roi, 0, [1, 2], [3]))["num_records"] == 0        # ref ignored: nothing is free
     with pytest.raises(KeyError):
         onp.find_shared(g, _tiny_graph(["TTTTT"], [[1]], ["kid"]), 0, [1], [])
+    # ... but with EVERY colour excluded the null record is never dereferenced (short-circuit && at FindShared.java:67): nothing is shared
+    absent = _tiny_graph(["AAAAC"], [[1]], ["kid"])          # canonical, and not a k-mer of g
+    assert onp.parse_header(onp.find_shared(g, absent, 0, [1, 2], [3]))["num_records"] == 0
+    assert orc.find_shared_mask(orc.Graph(g), orc.Graph(absent), 0, [1, 2], [3]).tolist() == [False]
+    assert orc.find_shared_mask(orc.Graph(g), orc.Graph(absent), 0, [1, 2], []) is None
     # RecoverExcludedKmers: dirty graph holds AAACC (cov 6) and CCCAA (cov 8) and GATTA (cov 0)
     dirty = _tiny_graph(["AAACC", "CCCAA", "GATTA"], [[6], [8], [0]], ["kid"])
     rec, nrec = onp.recover_excluded_kmers(g, dirty, 0)
@@ -418,9 +424,13 @@ def test_prefilter_oracles_c_and_numpy_agree(k, c, n):
     stray = np.zeros(1, dtype=onp.record_dtype(hg["kmer_bits"], 1)); stray["kmer"][0, -1] = 2
     stray_file = onp.write_header(k, hg["kmer_bits"], [hg["colors"][0]]) + stray.tobytes()
     if orc.Graph(ctx).find_record(onp.decode_kmers(stray["kmer"], k)[0].tobytes()) < 0:
-        assert orc.find_shared_mask(G, orc.Graph(stray_file), 0, [1], []) is None
-        with pytest.raises(KeyError):
-            onp.find_shared(ctx, stray_file, 0, [1], [])
+        if c > 2:            # a colour beside child and parent exists: its coverage is read from the null record
+            assert orc.find_shared_mask(G, orc.Graph(stray_file), 0, [1], []) is None
+            with pytest.raises(KeyError):
+                onp.find_shared(ctx, stray_file, 0, [1], [])
+        else:                # every colour excluded: the null record is never touched, the k-mer is simply not shared
+            assert orc.find_shared_mask(G, orc.Graph(stray_file), 0, [1], []).tolist() == [False]
+            assert onp.parse_header(onp.find_shared(ctx, stray_file, 0, [1], []))["num_records"] == 0
     # dirty graph: every third record plus coverage 0 / small / negative
     dpick = np.arange(0, n, 3)
     drec = np.zeros(len(dpick), dtype=onp.record_dtype(hg["kmer_bits"], 1))
@@ -441,3 +451,35 @@ def test_prefilter_oracles_c_and_numpy_agree(k, c, n):
             if kk:
                 hist[kk] = hist.get(kk, 0) + ww
         assert sorted(hist.items()) == onp.cov_stats(ctx, child, [p for p in parents])
+
+
+def test_remove_oracle_hand_checked_and_c_numpy_agree():
+    """Remove.java:30-88 (parity unpinned by reference tests: none exist).  Hand-computed case first, then the record-by-record C
+    restatement (CortexCollection.next + Remove's loop) against the vectorised numpy one on overlapping synthetic graphs."""
+    # primary (2 colours): AAAAA, ACGTA, CCCAA, GATTA; secondary A (1 colour): ACGTA cov 4, GATTA cov 0, TTTAA cov 2^31; secondary B: CCCAA cov 1, GGGAA cov 0
+    p = _tiny_graph(["AAAAA", "ACGTA", "CCCAA", "GATTA"], [[3, 1], [9, 0], [2, 2], [5, 7]], ["kid", "mom"])
+    a = _tiny_graph(["ACGTA", "GATTA", "TTTAA"], [[4], [0], [2 ** 31]], ["x"])
+    b = _tiny_graph(["CCCAA", "GGGAA"], [[1], [0]], ["y"])
+    out, removed = onp.remove(p, [a, b])
+    h = onp.parse_header(out)
+    r = onp.records_view(out, h)
+    # ACGTA and CCCAA are covered by a secondary graph -> removed.  GATTA (secondary coverage 0) stays.  GGGAA and TTTAA exist only in
+    # secondaries with coverage <= 0 (TTTAA's wraps negative): the reference writes them with all-zero primary colours.
+    assert removed == 2 and h["num_colors"] == 2 and [c["sample_name"] for c in h["colors"]] == ["kid", "mom"]
+    assert onp.decode_kmers(r["kmer"], 5).tobytes().decode() == "AAAAA" + "GATTA" + "GGGAA" + "TTTAA"
+    assert r["cov"].tolist() == [[3, 1], [5, 7], [0, 0], [0, 0]] and r["edges"][2:].tolist() == [[0, 0], [0, 0]]
+    got, rem2 = orc.remove_records(orc.Graph(p), [orc.Graph(a), orc.Graph(b)])
+    assert rem2 == removed and got == out[h["data_offset"]:]
+    assert onp.remove(p, [])[0][onp.parse_header(onp.remove(p, [])[0])["data_offset"]:] == p[onp.parse_header(p)["data_offset"]:]
+    for k, shapes in ((31, [(2, 1500), (1, 1200), (3, 800)]), (47, [(4, 3000), (1, 2500)]), (95, [(1, 700), (2, 0), (1, 900)])):
+        pool = synth.random_canonical_keys(5 + k, 4000, k, "cpu")
+        ctxs = []
+        for gi, (c, n) in enumerate(shapes):
+            g = torch.Generator().manual_seed(gi)
+            pick = torch.sort(torch.randperm(len(pool[0]), generator=g)[:n]).values
+            cov, edges = synth.coverage_and_edges(50 + gi, n, c, "cpu", novel_permille=100, adv_period=7)
+            body = synth.assemble_records([w[pick] for w in pool], cov, edges) if n else torch.zeros((0, 8 * len(pool) + 5 * c), dtype=torch.uint8)
+            ctxs.append(synth.header_bytes(k, c, ["g%d_%d" % (gi, j) for j in range(c)]) + body.numpy().tobytes())
+        want, removed = onp.remove(ctxs[0], ctxs[1:])
+        got, rem2 = orc.remove_records(orc.Graph(ctxs[0]), [orc.Graph(x) for x in ctxs[1:]])
+        assert rem2 == removed and removed > 0 and got == want[onp.parse_header(want)["data_offset"]:]
