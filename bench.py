@@ -616,6 +616,21 @@ def bench_lookup(args, env):
         out["e2e"] = {"value": ne / dt, "unit": "lookups/s", "h2d_bytes_per_step": ne * K, "d2h_bytes_per_step": ne * 8, "ms_per_step": dt * 1e3,
                       "api": "cc_find_ascii (pinned host ASCII k-mers -> device in chunks on two streams -> indices back to host)",
                       "equals_device_path": bool(torch.equal(h_out.to(dev), res[:ne]))}
+        # ---- the legacy per-record API: latency of one findRecord call, and of a vertex + its 8 neighbours in one call
+        lat = {}
+        one = np.ascontiguousarray(h_in[:9].numpy())
+        idx9 = np.empty(9, dtype=np.int64)
+        raw9 = np.empty(9 * REC_BYTES, dtype=np.uint8)
+        for nqs in (1, 9):
+            for _ in range(200):
+                N.check(L.cc_find_records(g._h, one.ctypes.data, nqs, idx9.ctypes.data, raw9.ctypes.data))
+            t0 = time.perf_counter()
+            for _ in range(3000):
+                L.cc_find_records(g._h, one.ctypes.data, nqs, idx9.ctypes.data, raw9.ctypes.data)
+            lat["cc_find_records_%d_us_per_call" % nqs] = (time.perf_counter() - t0) / 3000 * 1e6
+        lat["matches_batch_path"] = bool(np.array_equal(idx9, h_out[:9].numpy()))
+        lat["note"] = "host k-mer in, index + record bytes out, measured through ctypes (about 1 us of call overhead)"
+        out["find_record_latency"] = lat
         # ---- the CPU port beside it: the oracle's findRecord on a bounded sample of the same queries
         if not args.no_cpu:
             from oracle import orc

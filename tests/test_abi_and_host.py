@@ -249,7 +249,7 @@ def test_find_records_one_call_per_vertex():
     import corticall_b200 as cb
     from oracle import orc
     from tools import synth
-    for k, c, n in ((47, 4, 50000), (31, 2, 3000), (95, 3, 2000), (31, 1000, 300)):
+    for k, c, n in ((47, 4, 50000), (31, 2, 3000), (95, 3, 2000), (31, 45, 300)):
         ctx = synth.make_ctx_file(3 + k, n, k, c, adv_period=0)
         g = cb.CortexGraph(ctx)
         og = orc.Graph(ctx)
