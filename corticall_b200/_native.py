@@ -85,6 +85,7 @@ SIGNATURES = {
     "cc_scatter_results_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, _P, _P]),
     "cc_route_state_bytes": (C.c_int, [C.c_uint64, C.c_int, _U64P]),
     "cc_route_queries_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint32, _P, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, C.c_uint64, _P, _P]),
+    "cc_publish_counts_dev": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "cc_find_routed_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "cc_gather_routed_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint64, _P, C.c_int, C.c_uint64, _P, _P]),
     "cc_open_sharded": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),

@@ -1012,6 +1012,13 @@ int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *d
                         max_queries, dev_sent, static_cast<cudaStream_t>(stream));
 }
 
+int cc_publish_counts_dev(int device, const uint64_t *dev_sent, int nshards, int my_rank, uint64_t cap, void *const *peer_counts_in, void *stream) {
+    if (int rc = check_device(device)) return rc;
+    if (!dev_sent || !peer_counts_in) return fail(CC_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    return launch_publish_counts(dev_sent, nshards, my_rank, cap, peer_counts_in, static_cast<cudaStream_t>(stream));
+}
+
 int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, uint64_t cap,
                        void *dev_res, void *stream) {
     if (!g || !dev_inbox || !dev_counts_in || !dev_res) return fail(CC_ERR_ARG, "null argument");

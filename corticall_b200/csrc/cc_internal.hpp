@@ -193,6 +193,7 @@ uint64_t route_state_size(uint64_t max_q, int nshards);
 int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k, const uint64_t *dev_splitters, int nshards,
                  int my_rank, uint64_t cap, void *const *peer_inbox, void *const *peer_counts, void *dev_route_state, uint64_t max_q,
                  uint64_t *dev_sent, cudaStream_t st);
+int launch_publish_counts(const uint64_t *dev_sent, int nshards, int my_rank, uint64_t cap, void *const *peer_counts, cudaStream_t st);
 int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub, uint64_t cap,
                        void *dev_res, cudaStream_t st);
 int launch_gather_routed(void *const *peer_res, const void *dev_route_state, uint64_t max_q, uint64_t nq, const uint64_t *dev_shard_first,

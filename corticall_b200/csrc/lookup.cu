@@ -193,12 +193,14 @@ constexpr uint32_t kMiss32 = 0xffffffffu;
 template <int KW>
 struct LineLayout {
     static constexpr int CAP = (KW == 3) ? 5 : (KW == 2) ? 7 : (KW == 4) ? 3 : 15 / KW;
-    static constexpr int kBaseWord = (KW == 3) ? 3 : 0;
-    // word index of word p (0 = most significant) of slot t
+    static constexpr int kBaseWord = 0;
+    // word index of word p (0 = most significant) of slot t.  For KW = 2, 3, 4 a key never straddles the two 32-byte halves
+    // of the line except key 4 of KW = 3 (word 0 closes the first half, words 1-2 the second): two lanes, each holding one
+    // half, compare without moving key words between them.
     __host__ __device__ static constexpr int word(int t, int p) {
-        return KW == 3 ? (t < 4 ? 4 * t + p : 4 * (p + 1) + 3)       // lane j: key j in x,y,z; w = base (lane 0) or word j-1 of key 4
-             : KW == 2 ? 2 + 2 * t + p                                // lane 0: base, -, key 0; lane j: keys 2j-1, 2j
-             : KW == 4 ? 4 * (t + 1) + p                              // lane 0: base; lane j: key j-1
+        return KW == 3 ? (t < 2 ? 1 + 3 * t + p : t < 4 ? 8 + 3 * (t - 2) + p : (p == 0 ? 7 : 13 + p))
+             : KW == 2 ? (t < 3 ? 2 + 2 * t + p : 8 + 2 * (t - 3) + p)     // first half: base, -, keys 0-2; second half: keys 3-6
+             : KW == 4 ? (t < 1 ? 4 + p : 8 + 4 * (t - 1) + p)             // first half: base, -, -, -, key 0; second half: keys 1-2
                        : 1 + t * KW + p;
     }
 };
@@ -219,16 +221,35 @@ struct IndexView {
     uint32_t pad[8];            // wire form of the largest key
 };
 
+// hints: 0 = plain loads, 1 = evict-first in L2 (+ no L1 allocation), 2 = evict-normal policy object, 3 = evict-last
 __device__ __forceinline__ uint64_t make_line_policy(uint32_t hints) {
-    uint64_t p;
-    if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    uint64_t p = 0;
+    if (hints == 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (hints == 2u) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    else if (hints == 3u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+struct Half { uint32_t w[8]; };       // one 32-byte half of a line
+__device__ __forceinline__ Half ld_line32(const uint4 *p, uint64_t policy) {
+    Half h;
+    if (policy == 0) {
+        asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(h.w[0]), "=r"(h.w[1]), "=r"(h.w[2]), "=r"(h.w[3]), "=r"(h.w[4]), "=r"(h.w[5]), "=r"(h.w[6]), "=r"(h.w[7]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                     : "=r"(h.w[0]), "=r"(h.w[1]), "=r"(h.w[2]), "=r"(h.w[3]), "=r"(h.w[4]), "=r"(h.w[5]), "=r"(h.w[6]), "=r"(h.w[7])
+                     : "l"(p), "l"(policy));
+    }
+    return h;
 }
 __device__ __forceinline__ uint4 ld_line16(const uint4 *p, uint64_t policy) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    if (policy == 0) {              // no hint at all: a table small enough for L2 to help is left to the default replacement
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    }
     return v;
 }
 
@@ -359,10 +380,11 @@ __device__ __forceinline__ int64_t lookup_lines_thread(const IndexView &ix, cons
 }
 
 // The line search by a whole warp, one query per lane (all 32 lanes must call it; `live` = this lane has a query).
-// Four lanes share a line: lane j of a quad loads bytes [16j, 16j + 16) -- one LDG.128 per warp fetches 8 whole lines (8
-// wavefronts instead of the 32 a thread-per-line load costs, which would bound the kernel on the L1 wavefront rate before
-// DRAM) -- and the quad works through its own four queries in four rounds.  All four loads are issued before the first
-// compare.  Layouts exist for KW = 2, 3, 4 (k = 17..64); other widths take the per-thread form.
+// Two lanes share a line: lane h of a pair loads bytes [32h, 32h + 32) with one 256-bit load -- a warp-wide load fetches 16
+// whole lines (16 wavefronts instead of the 64 a thread-per-line search costs) -- and the pair works through its own two
+// queries in two rounds; both loads are issued before the first compare.  What crosses the lanes per round is the query
+// (KW words), the line index, one word of match bits and the base index.  Layouts exist for KW = 2, 3, 4 (k = 17..64);
+// other widths take the per-thread form.
 template <int S, int KW>
 __device__ __forceinline__ int64_t lookup_lines_warp(const IndexView &ix, const uint2 *bins, uint64_t pol, const uint64_t (&q)[S], bool live) {
     if constexpr (KW < 2 || KW > 4) {
@@ -370,65 +392,77 @@ __device__ __forceinline__ int64_t lookup_lines_warp(const IndexView &ix, const 
     } else {
     using LL = LineLayout<KW>;
     constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u, j = lane & 3u, g4 = lane & ~3u;
-    uint32_t line = 0;
+    const uint32_t h = threadIdx.x & 1u;
+    uint32_t line = 0;                       // a lane without a query reads line 0 and ignores it: no branch around the loads
     bool in = live && ix.n != 0;
     if (in) in = key_line<S>(ix, bins, q, line);
+    if (!in) line = 0;
     uint32_t qw[KW];
     key_to_wire<S, KW>(q, qw);
-    uint4 v[4];
+    Half v[2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const uint32_t l = __shfl_sync(FULL, line, r, 4);
-        const int ok = __shfl_sync(FULL, (int)in, r, 4);
-        v[r] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) v[r] = ld_line16(ix.lines + (size_t)l * 4 + j, pol);
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t l = __shfl_sync(FULL, line, r, 2);
+        v[r] = ld_line32(ix.lines + (size_t)l * 4 + 2 * h, pol);
     }
     int slot_mine = -1;
     bool less_mine = false;
     uint32_t base_mine = 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 2; ++r) {
         uint32_t qs[KW];
 #pragma unroll
-        for (int p = 0; p < KW; ++p) qs[p] = __shfl_sync(FULL, qw[p], r, 4);
-        int slot = -1;
-        bool less = false;
-        uint32_t base = 0;
+        for (int p = 0; p < KW; ++p) qs[p] = __shfl_sync(FULL, qw[p], r, 2);
+        const uint32_t (&a)[8] = v[r].w;
+        // bits 0..6: slot t matches; bit 8: last slot < query (decided in this half); bits 9, 10: KW = 3 only, see below
+        uint32_t m = 0;
         if constexpr (KW == 3) {
-            const bool own = (v[r].x == qs[0]) & (v[r].y == qs[1]) & (v[r].z == qs[2]);
-            const uint32_t xw = j == 1 ? qs[0] : (j == 2 ? qs[1] : qs[2]);
-            const uint32_t bo = (__ballot_sync(FULL, own) >> g4) & 0xfu;
-            const uint32_t be = (__ballot_sync(FULL, (j != 0) & (v[r].w == xw)) >> g4) & 0xeu;
-            const uint32_t bl = (__ballot_sync(FULL, (j != 0) & (v[r].w < xw)) >> g4) & 0xeu;
-            base = __shfl_sync(FULL, v[r].w, 0, 4);
-            if (bo) slot = __ffs(bo) - 1;
-            else if (be == 0xeu) slot = 4;
-            const uint32_t diff = ~be & 0xeu;
-            less = (diff & (0u - diff) & bl) != 0u;        // first differing word of key 4 is below the query's
-        } else if constexpr (KW == 2) {
-            const bool a = (j != 0) & (v[r].x == qs[0]) & (v[r].y == qs[1]);
-            const bool b = (v[r].z == qs[0]) & (v[r].w == qs[1]);
-            const uint32_t ba = (__ballot_sync(FULL, a) >> g4) & 0xeu, bb = (__ballot_sync(FULL, b) >> g4) & 0xfu;
-            const bool lt = (v[r].z < qs[0]) | ((v[r].z == qs[0]) & (v[r].w < qs[1]));
-            less = (__ballot_sync(FULL, lt) >> (g4 + 3u)) & 1u;
-            base = __shfl_sync(FULL, v[r].x, 0, 4);
-            const int sa = ba ? 2 * (__ffs(ba) - 1) - 1 : 99, sb = bb ? 2 * (__ffs(bb) - 1) : 99;
-            slot = min(sa, sb) == 99 ? -1 : min(sa, sb);
-        } else if constexpr (KW == 4) {
-            const bool own = (j != 0) & (v[r].x == qs[0]) & (v[r].y == qs[1]) & (v[r].z == qs[2]) & (v[r].w == qs[3]);
-            const uint32_t bo = (__ballot_sync(FULL, own) >> g4) & 0xeu;
-            bool lt = false, dec = false;
-            const uint32_t a[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+            // half 0: base, key 0, key 1, word 0 of key 4;  half 1: key 2, key 3, words 1-2 of key 4
+            uint32_t b[6];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                if (!dec && a[p] != qs[p]) { dec = true; lt = a[p] < qs[p]; }
+            for (int i = 0; i < 6; ++i) b[i] = h ? a[i] : a[i + 1];
+            const bool ma = (b[0] == qs[0]) & (b[1] == qs[1]) & (b[2] == qs[2]);
+            const bool mb = (b[3] == qs[0]) & (b[4] == qs[1]) & (b[5] == qs[2]);
+            m = ((uint32_t)ma | ((uint32_t)mb << 1)) << (2u * h);
+            if (h == 0) m |= ((uint32_t)(a[7] == qs[0]) << 9) | ((uint32_t)(a[7] < qs[0]) << 8);               // key 4, word 0: equal / below
+            else m |= ((uint32_t)((a[6] == qs[1]) & (a[7] == qs[2])) << 10) |
+                      ((uint32_t)((a[6] < qs[1]) | ((a[6] == qs[1]) & (a[7] < qs[2]))) << 11);                  // key 4, words 1-2: equal / below
+        } else if constexpr (KW == 2) {
+            // half 0: base, -, keys 0-2;  half 1: keys 3-6
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const bool e = (a[2 * t] == qs[0]) & (a[2 * t + 1] == qs[1]);
+                if (t > 0) m |= (uint32_t)(e & (h == 0)) << (t - 1);
+                m |= (uint32_t)(e & (h == 1)) << (3 + t);
             }
-            less = (__ballot_sync(FULL, lt) >> (g4 + 3u)) & 1u;
-            base = __shfl_sync(FULL, v[r].x, 0, 4);
-            if (bo) slot = __ffs(bo) - 2;
+            if (h == 1) m |= (uint32_t)((a[6] < qs[0]) | ((a[6] == qs[0]) & (a[7] < qs[1]))) << 8;
+        } else {
+            // half 0: base, -, -, -, key 0;  half 1: keys 1-2
+            const bool e1 = (a[4] == qs[0]) & (a[5] == qs[1]) & (a[6] == qs[2]) & (a[7] == qs[3]);
+            const bool e0 = (a[0] == qs[0]) & (a[1] == qs[1]) & (a[2] == qs[2]) & (a[3] == qs[3]);
+            if (h == 0) m = (uint32_t)e1;
+            else {
+                bool lt = false, dec = false;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    if (!dec && a[4 + p] != qs[p]) { dec = true; lt = a[4 + p] < qs[p]; }
+                }
+                m = ((uint32_t)e0 << 1) | ((uint32_t)e1 << 2) | ((uint32_t)lt << 8);
+            }
         }
-        if (j == (uint32_t)r) { slot_mine = slot; less_mine = less; base_mine = base; }
+        m |= __shfl_xor_sync(FULL, m, 1);
+        const uint32_t base = __shfl_sync(FULL, a[0], 0, 2);
+        int slot = -1;
+        bool less;
+        if constexpr (KW == 3) {
+            if (m & 0xfu) slot = __ffs(m & 0xfu) - 1;
+            else if ((m & 0x600u) == 0x600u) slot = 4;
+            less = ((m >> 8) & 1u) | (((m >> 9) & 1u) & ((m >> 11) & 1u));      // word 0 below, or equal and the rest below
+        } else {
+            if (m & 0x7fu) slot = __ffs(m & 0x7fu) - 1;
+            less = (m >> 8) & 1u;
+        }
+        if (h == (uint32_t)r) { slot_mine = slot; less_mine = less; base_mine = base; }
     }
     if (!in) return -1;
     if (slot_mine >= 0) return (int64_t)((uint64_t)base_mine + (uint64_t)slot_mine + ix.first_index);
@@ -1185,16 +1219,30 @@ __global__ void __launch_bounds__(BLOCK) gather_routed_kernel(PeerPtrs res, Rout
         }
         __syncthreads();
         const uint32_t total = loc[nshards];
-        for (uint32_t p = threadIdx.x; p < total; p += BLOCK) {
-            uint32_t lo = 0, hi = (uint32_t)nshards - 1;  // owner o with loc[o] <= p < loc[o+1]
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (loc[mid] <= p) lo = mid; else hi = mid - 1;
+        // all remote loads of the tile are issued before the first result is used: the NVLink round trip (microseconds) is
+        // paid once per tile, not once per loop iteration
+        uint32_t own[kRouteQ], val[kRouteQ];
+#pragma unroll
+        for (int j = 0; j < kRouteQ; ++j) {
+            const uint32_t p = threadIdx.x + (uint32_t)j * BLOCK;
+            own[j] = 0;
+            val[j] = kWireMiss;
+            if (p < total) {
+                uint32_t lo = 0, hi = (uint32_t)nshards - 1;  // owner o with loc[o] <= p < loc[o+1]
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (loc[mid] <= p) lo = mid; else hi = mid - 1;
+                }
+                own[j] = lo;
+                const uint64_t at = (uint64_t)base[lo] + (p - loc[lo]);
+                // res.p[o] = this origin's result segment on owner o (peer memory: read over NVLink, never cached in L1)
+                if (at < cap) val[j] = __ldcv(static_cast<const uint32_t *>(res.p[lo]) + at);   // >= cap: dropped by an overflowing segment
             }
-            const uint64_t at = (uint64_t)base[lo] + (p - loc[lo]);
-            // res.p[o] = this origin's result segment on owner o (peer memory: read over NVLink, never cached in L1)
-            const uint32_t r = at < cap ? __ldcv(static_cast<const uint32_t *>(res.p[lo]) + at) : kWireMiss;   // >= cap: dropped by an overflowing segment
-            staged[p] = r == kWireMiss ? -1 : (int64_t)(first[lo] + r);
+        }
+#pragma unroll
+        for (int j = 0; j < kRouteQ; ++j) {
+            const uint32_t p = threadIdx.x + (uint32_t)j * BLOCK;
+            if (p < total) staged[p] = val[j] == kWireMiss ? -1 : (int64_t)(first[own[j]] + val[j]);
         }
         __syncthreads();
 #pragma unroll
@@ -1809,6 +1857,16 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
         count_launch();
     }
     publish_counts_kernel<<<1, kMaxShards, 0, st>>>(cursors, nshards, my_rank, cap, counts);
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_publish_counts(const uint64_t *dev_sent, int nshards, int my_rank, uint64_t cap, void *const *peer_counts, cudaStream_t st) {
+    if (nshards < 1 || nshards > kMaxShards) return fail(CC_ERR_ARG, "nshards must be in 1..%d", kMaxShards);
+    PeerPtrs counts{};
+    for (int i = 0; i < nshards; ++i) counts.p[i] = peer_counts[i];
+    publish_counts_kernel<<<1, kMaxShards, 0, st>>>(reinterpret_cast<const unsigned long long *>(dev_sent), nshards, my_rank, cap, counts);
     count_launch();
     CC_CUDA(cudaGetLastError());
     return CC_OK;

@@ -223,9 +223,11 @@ class RoutedLookup:
         """int64 elements of one rank's symmetric block."""
         return RoutedLookup._layout(world, vsub, RoutedLookup.round_cap(cap), (2 * k + 31) // 32)[3] // 8
 
-    def _barrier(self):
+    def _barrier(self, channel: int = 0):
+        """Cross-rank barrier on the current stream (symmetric-memory signal pads).  Barriers that can be in flight at the
+        same time on different streams must use different channels."""
         if self.hdl is not None:
-            self.hdl.barrier()
+            self.hdl.barrier(channel=channel)
 
     def route(self, words, flags):
         if words.shape[0] > self.max_batch:
@@ -283,22 +285,27 @@ class RoutedLookup:
 
 
 class PipelinedRoutedLookup:
-    """RoutedLookup over sub-batches with the NVLink legs overlapped with the search.
+    """RoutedLookup over sub-batches with the three legs of DIFFERENT sub-batches running at the same time: while the owners
+    search sub-batch i (bound by random DRAM access), sub-batch i+1 is routed (SM issue + NVLink stores) and the results of
+    sub-batch i-1 are pulled back (NVLink reads) -- three resources, three streams.
 
-    Two RoutedLookup buffer sets (parity = sub-batch & 1) and two streams: X carries route_i and gather_i, Y carries
-    search_i.  Order on X: R0 R1 G0 R2 G1 R3 G2 ... ; on Y: S0 S1 S2 ...  Cross-rank barriers follow R_i (on X) and S_i
-    (on Y), so every rank issues the same sequence per stream and a buffer set is never overwritten while a peer still
-    reads it.  The route / gather kernels run as one persistent CTA per SM on a high-priority
-    stream beside two persistent search CTAs per SM.
+    Two RoutedLookup buffer sets (parity = sub-batch & 1); streams R, S, G carry route_i, search_i, gather_i in order.
+    Dependencies: route_i waits for gather_(i-2) (its set's bookkeeping is free, and every owner has finished searching that
+    set: the gather waited for all of them); search_i waits for route_i of EVERY rank (barrier on channel 0 of stream R);
+    gather_i waits for search_i of every rank (barrier on channel 1 of stream S).  Every rank issues the same sequence per
+    stream.  The kernels are sized (cc_set_option route/search/gather blocks per SM) so that all three fit on an SM together.
     """
 
-    def __init__(self, graph, splitters, rank: int, world: int, device, sub_batch: int, k: int, shard_first=None, group=None):
+    def __init__(self, graph, splitters, rank: int, world: int, device, sub_batch: int, k: int, shard_first=None, group=None,
+                 per_sm=(3, 1, 2)):
         self.sub = int(sub_batch)
-        self.sets = [RoutedLookup(graph, splitters, rank, world, device, self.sub, k, shard_first=shard_first, group=group) for _ in range(2)]
-        self.sx = torch.cuda.Stream(device=device, priority=-1)     # NVLink legs first: they are short and hide behind the search
-        self.sy = torch.cuda.Stream(device=device)
+        self.sets = [RoutedLookup(graph, splitters, rank, world, device, int(self.sub / world * 1.25) + 4096 if world > 1 else self.sub, k,
+                                  shard_first=shard_first, group=group, max_batch=self.sub) for _ in range(2)]
+        self.sr = torch.cuda.Stream(device=device, priority=-1)     # the NVLink legs first: they are short and hide behind the search
+        self.sg = torch.cuda.Stream(device=device, priority=-1)
+        self.ss = torch.cuda.Stream(device=device)
         self.world = world
-        self.route_per_sm, self.gather_per_sm, self.search_per_sm = 1, 1, 2
+        self.route_per_sm, self.search_per_sm, self.gather_per_sm = per_sm
 
     def find_packed(self, words: torch.Tensor, flags: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
         nq = words.shape[0]
@@ -309,53 +316,47 @@ class PipelinedRoutedLookup:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             nsub = int(t.item())
         cur = torch.cuda.current_stream()
-        start = torch.cuda.Event()
-        start.record(cur)
-        self.sx.wait_stream(cur)
-        self.sy.wait_stream(cur)
+        for st in (self.sr, self.ss, self.sg):
+            st.wait_stream(cur)
         routed = [torch.cuda.Event() for _ in range(nsub)]
         searched = [torch.cuda.Event() for _ in range(nsub)]
-        # one route / gather CTA per SM beside two (instead of three) resident search CTAs: all three kernels are
-        # persistent, so they are co-resident by construction (registers: 2 x 78 x 256 + 72 x 256 < 64 K)
+        gathered = [torch.cuda.Event() for _ in range(nsub)]
         N.set_option("route_blocks_per_sm", self.route_per_sm)
-        N.set_option("gather_blocks_per_sm", self.gather_per_sm)
         N.set_option("routed_search_blocks_per_sm", self.search_per_sm)
+        N.set_option("gather_blocks_per_sm", self.gather_per_sm if self.gather_per_sm > 0 else 16)
 
         def part(i):
             lo, hi = min(i * self.sub, nq), min((i + 1) * self.sub, nq)
             return words[lo:hi], (flags[lo:hi] if flags is not None else None), out[lo:hi]
 
-        def route(i):
-            w, f, o = part(i)
-            with torch.cuda.stream(self.sx):
-                self.sets[i & 1].route(w, f)
-                self.sets[i & 1]._barrier()
-                routed[i].record(self.sx)
-
-        def search(i):
-            with torch.cuda.stream(self.sy):
-                self.sy.wait_event(routed[i])
-                self.sets[i & 1].search()
-                self.sets[i & 1]._barrier()
-                searched[i].record(self.sy)
-
-        def gather(i):
-            _, _, o = part(i)
-            with torch.cuda.stream(self.sx):
-                self.sx.wait_event(searched[i])
-                self.sets[i & 1].gather(o)
-
         try:
             for i in range(nsub):
-                route(i)
-                search(i)
-                if i >= 1:
-                    gather(i - 1)
-            gather(nsub - 1)
+                w, f, o = part(i)
+                rl = self.sets[i & 1]
+                with torch.cuda.stream(self.sr):
+                    if i >= 2:
+                        self.sr.wait_event(gathered[i - 2])
+                    rl.route(w, f)
+                    rl._barrier(0)
+                    routed[i].record(self.sr)
+                with torch.cuda.stream(self.ss):
+                    self.ss.wait_event(routed[i])
+                    rl.search()
+                    rl._barrier(1)
+                    searched[i].record(self.ss)
+                with torch.cuda.stream(self.sg):
+                    self.sg.wait_event(searched[i])
+                    rl.gather(o)
+                    gathered[i].record(self.sg)
         finally:
             N.set_option("route_blocks_per_sm", 0)
             N.set_option("gather_blocks_per_sm", 16)
-            N.set_option("routed_search_blocks_per_sm", 3)
-        cur.wait_stream(self.sx)
-        cur.wait_stream(self.sy)
+            N.set_option("routed_search_blocks_per_sm", 0)
+        for st in (self.sr, self.ss, self.sg):
+            cur.wait_stream(st)
         return out
+
+    def check_overflow(self):
+        for rl in self.sets:
+            rl.check_overflow()
+

@@ -220,6 +220,12 @@ CC_API int cc_route_queries_dev(int device, const uint64_t *dev_words, const uin
                                 const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap,
                                 void *const *peer_inbox, void *const *peer_counts_in,
                                 void *dev_route_state, uint64_t max_queries, uint64_t *dev_sent, void *stream);
+/* Staged form of the route leg (the copy engines move the keys instead of the SMs): cc_route_queries_dev is pointed at LOCAL
+ * staging (peer_inbox[v] = stage + (v - my_rank) * cap * kw * 4, peer_counts_in[v] = local_counts + (v - my_rank)), the caller
+ * copies stage segment v into owner v's inbox segment (cudaMemcpyAsync over NVLink) and this call publishes the counts:
+ * counts_in[my_rank] on owner v := min(dev_sent[v], cap). */
+CC_API int cc_publish_counts_dev(int device, const uint64_t *dev_sent, int nshards, int my_rank, uint64_t cap,
+                                 void *const *peer_counts_in, void *stream);
 CC_API int cc_find_routed_dev(cc_graph *g, const void *dev_inbox, const uint64_t *dev_counts_in, int world, int vsub,
                               uint64_t cap, void *dev_res, void *stream);
 CC_API int cc_gather_routed_dev(int device, void *const *peer_res, const void *dev_route_state, uint64_t max_queries, uint64_t nq,

@@ -75,7 +75,7 @@ for fill in (50, 40, 60, 75):
         N.set_option("find_bins_smem", 1)
 N.set_option("index_fill_pct", 50)
 g.buildIndex(0)
-for hints in (0, 1):
+for hints in (0, 1, 2, 3):
     N.set_option("lookup_l2_hints", hints)
     ms = timeit(lambda: N.check(L.cc_find_packed_dev(g._h, qw.data_ptr(), qf.data_ptr(), nq, res.data_ptr(), cb.CC_ALGO_AUTO, st)))
     print("packed lines hints=%d  %8.3f ms  %.3g lookups/s" % (hints, ms, nq / ms * 1e3), flush=True)

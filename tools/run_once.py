@@ -10,9 +10,13 @@ from tools import synth
 
 what = sys.argv[1] if len(sys.argv) > 1 else "scan"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+NT = 100_000_000
 for kv in sys.argv[3:]:
     name, val = kv.split("=")
-    N.set_option(name, int(val))
+    if name == "nt":
+        NT = int(float(val))
+    else:
+        N.set_option(name, int(val))
 L = N.lib()
 st = torch.cuda.current_stream().cuda_stream
 
@@ -40,7 +44,7 @@ if what in ("scan", "scan5"):
     print(what, "n", n, "novel", int(cnt[0]), "ms", ms)
 else:
     k, c = 47, 4
-    nt, nq = 100_000_000, 1 << 25
+    nt, nq = NT, 1 << 25
     table = synth.random_canonical_keys(2, nt, k, "cuda")
     cov, edges = synth.coverage_and_edges(2, nt, c, "cuda")
     body = synth.assemble_records(table, cov, edges)
