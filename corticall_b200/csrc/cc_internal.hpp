@@ -34,7 +34,7 @@ struct Options {
     int index_bits = 0;          // log2 of the number of bins of the lookup index (0 = auto: ~256 keys per bin, at most 2^13)
     int index_fill_pct = 50;     // average fill of a bucket line, in percent of its capacity
     int rows_rpt2_max_k = 32;    // cc_pack_kmers: two rows per thread (512-row tiles) up to this k, else one
-    int lookup_l2_hints = 1;     // bit0: line loads evict-first in L2
+    int lookup_l2_hints = -1;    // line loads: -1 = auto (plain up to 1 GB of lines, evict-first beyond), 0 plain, 1 evict-first, 2 evict-normal, 3 evict-last
     int find_bins_smem = 1;      // packed / routed search: stage the bin table in shared memory
     int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1

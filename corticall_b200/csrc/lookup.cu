@@ -943,12 +943,11 @@ __device__ __forceinline__ void warp_excl_scan64(uint32_t v0, uint32_t v1, uint3
 
 constexpr uint32_t kOwnerLutBits = 10;         // owner lookup: 2^10 key prefixes -> first candidate owner
 
-// Dynamic shared memory of route_kernel: staged wire keys (each owner's run padded to its destination's 16-byte phase)
-// followed by one owner id per 16-byte slot of that staging area.
+// Dynamic shared memory of route_kernel: two staging areas of wire keys (each owner's run padded to its destination's
+// 16-byte phase).
 inline uint32_t route_stage_words(uint32_t tile_q, uint32_t kw, int nshards) { return (tile_q * kw + 8u * (uint32_t)nshards + 3u) & ~3u; }
 inline size_t route_smem_bytes(uint32_t tile_q, uint32_t kw, int nshards) {
-    const uint32_t w = route_stage_words(tile_q, kw, nshards);
-    return (size_t)w * 4u + ((w / 4u + 15u) & ~15u);
+    return 2u * (size_t)route_stage_words(tile_q, kw, nshards) * 4u;       // two staging areas: a tile's runs leave while the next is built
 }
 
 // Tile of BLOCK * kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory, every owner's run
@@ -960,8 +959,7 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
                                                       PeerPtrs inbox, RouteState rs, unsigned long long *cursors, uint32_t stage_words,
                                                       uint32_t k_bases) {
     constexpr uint32_t kTile = BLOCK * kRouteQ;
-    extern __shared__ __align__(16) uint32_t stage[];     // [stage_words] wire keys, then uint8 slot_owner[stage_words / 4]
-    uint8_t *slot_owner = reinterpret_cast<uint8_t *>(stage + stage_words);
+    extern __shared__ __align__(128) uint32_t stage_all[];   // 2 x [stage_words] wire keys (double-buffered: see the copy-out)
     __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1], locw[kMaxShards], endw[kMaxShards];
     __shared__ unsigned long long base[kMaxShards];
     __shared__ uint32_t *dptr[kMaxShards];                // dptr[o] + w = destination of staged word w of owner o
@@ -992,10 +990,13 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
         owner_lut[p] = (uint8_t)o;
     }
     const uint64_t ntiles = route_tiles(nq, kTile);
-    const uint32_t nslots = stage_words >> 2;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        uint32_t *stage = stage_all + (it & 1u) * stage_words;
         for (int i = threadIdx.x; i < nshards; i += BLOCK) hist[i] = 0;
-        for (uint32_t i = threadIdx.x; i < (nslots + 3u) / 4u; i += BLOCK) reinterpret_cast<uint32_t *>(slot_owner)[i] = 0xffffffffu;
+        // this tile's staging area was last read by the bulk copies of tile it-2: their issuers wait for those reads here
+        // (at most the copies of tile it-1 stay pending); the barrier below publishes that to the whole CTA
+        if (threadIdx.x < (uint32_t)nshards) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncthreads();
         uint64_t q[kRouteQ][S];
         uint32_t own[kRouteQ], rank_in[kRouteQ];
@@ -1106,32 +1107,35 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
                 at = loc[own[j]] + rank_in[j];                       // position in the tile's regrouped order (for the gather)
                 const uint32_t w0 = locw[own[j]] + rank_in[j] * KW;
                 key_to_wire<S, KW>(q[j], stage + w0);
-                slot_owner[w0 >> 2] = (uint8_t)own[j];               // same value from every key of the run: benign
-                slot_owner[(w0 + KW - 1) >> 2] = (uint8_t)own[j];
-                if (KW > 4) {
-#pragma unroll
-                    for (uint32_t w = 4; w < (uint32_t)KW; w += 4) slot_owner[(w0 + w) >> 2] = (uint8_t)own[j];
-                }
             }
             rs.at16[i] = (uint16_t)at;
         }
+        // the staged keys are read by the async proxy (bulk copies): order the generic-proxy writes before it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        // copy-out, flat over the 16-byte slots of the staging area: a slot belongs to one owner (runs start in a fresh slot)
-        for (uint32_t sl = threadIdx.x; sl < nslots; sl += BLOCK) {
-            const uint32_t o = slot_owner[sl];
-            if (o == 0xffu) continue;
-            const uint32_t w0 = sl << 2, lo = locw[o], hi = endw[o];
-            uint32_t *d = dptr[o] + w0;
-            if (w0 >= lo && w0 + 4u <= hi) {
-                *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(stage + w0);
-            } else {
-#pragma unroll
-                for (uint32_t w = 0; w < 4; ++w)
-                    if (w0 + w >= lo && w0 + w < hi) d[w] = stage[w0 + w];
+        // copy-out: one thread per owner hands the 16-byte-aligned body of its run to the bulk-copy (TMA) engine -- shared
+        // memory -> the owner's inbox, over NVLink when the owner is a peer -- and stores the ragged head / tail words (at most
+        // three each) itself.  The copies are asynchronous: the CTA goes on to the next tile while the link drains this one,
+        // and no warp sits in a backed-up store queue (plain stores from all warps left the SMs stalled on the link: the leg
+        // took compute + transfer instead of max(compute, transfer)).
+        if (threadIdx.x < (uint32_t)nshards) {
+            const uint32_t o = threadIdx.x, lo = locw[o], hi = endw[o];
+            if (hi > lo) {
+                const uint32_t blo = (lo + 3u) & ~3u, bhi = hi & ~3u;
+                uint32_t *d = dptr[o];
+                if (bhi > blo) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(d + blo), "r"(smem_u32(stage + blo)), "r"((bhi - blo) * 4u) : "memory");
+                    for (uint32_t w = lo; w < blo; ++w) d[w] = stage[w];
+                    for (uint32_t w = bhi; w < hi; ++w) d[w] = stage[w];
+                } else {
+                    for (uint32_t w = lo; w < hi; ++w) d[w] = stage[w];
+                }
             }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // one group per tile, empty or not: wait_group counts tiles
         }
-        __syncthreads();
     }
+    if (threadIdx.x < (uint32_t)nshards) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __threadfence_system();
 }
 
@@ -1484,7 +1488,9 @@ IndexView view_of(const cc_graph *g) {
     v.scale = g->index.scale;
     v.nbins = g->index.nbins;
     v.norm = g->index.norm;
-    v.hints = (uint32_t)options().lookup_l2_hints;
+    // a table of a few hundred MB gets a little help from L2 (about 18 % hits at 320 MB: each die caches its own copy) and loses it
+    // when its lines are marked evict-first; a multi-GB table is touched at random and never again
+    v.hints = options().lookup_l2_hints >= 0 ? (uint32_t)options().lookup_l2_hints : (g->index.nlines * 64ull > (1ull << 30) ? 1u : 0u);
     v.k = g->h.k;
     for (int i = 0; i < 8; ++i) v.pad[i] = g->index.pad[i];
     return v;
@@ -1878,9 +1884,6 @@ int launch_find_routed(cc_graph *g, const void *dev_inbox, const uint64_t *dev_c
     if (world < 1 || vsub < 1 || world * vsub > kMaxShards) return fail(CC_ERR_ARG, "world * vsub must be in 1..%d", kMaxShards);
     IndexView ix = view_of(g);
     ix.first_index = 0;                 // the wire carries indices local to the shard; the origin rebases them
-    // a sub-range that fits L2 must stay there: no evict-first on its lines
-    const uint64_t slice_bytes = g->index.nlines * 64ull / (uint64_t)vsub;
-    if (vsub > 1 && slice_bytes <= (48ull << 20)) ix.hints = 0;
     const uint32_t kw = wire_words(g->h.k);
     CC_DISPATCH_SKW(g->h.s, kw, {
         FindLaunch fl;
