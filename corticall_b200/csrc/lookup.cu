@@ -116,6 +116,8 @@ __device__ __forceinline__ bool any_bits(const uint32_t *w, uint32_t P, uint32_t
     return acc != 0;
 }
 
+__device__ __forceinline__ uint64_t spread_bits(uint32_t x);
+
 // Canonical packed k-mer of the window starting at tile byte `start`.  Returns flags
 // (bit0 flipped, bit1 not ACGTacgt, bit2 has lower case); words zeroed when bit1.
 template <int S>
@@ -139,16 +141,34 @@ __device__ __forceinline__ uint32_t window_canonical(const SeqTile &t, uint32_t 
     bool flip = words_less<S>(rc, fw);
     uint32_t flags = 0;
     if (any_bits(t.lower, p0, k)) {
-        // Mixed / lower case: the reference compares ASCII bytes (signed), not 2-bit codes
-        // (SequenceUtils.java:211-219).  Rare, so take the byte loop.
+        // Mixed / lower case (soft-masked genomes are half lower case): the reference compares ASCII bytes, seq[i] against
+        // complement(seq[k-1-i]), first difference decides (SequenceUtils.java:211-219).  For bytes in ACGTacgt that is the
+        // lexicographic order of (case, code) per base -- every upper-case letter sorts before every lower-case one and the
+        // 2-bit codes follow the ASCII order within a case; complement keeps the case -- so the comparison is done on the
+        // packed words plus the case bits spread to the same 2-bit grid, without touching the bytes again.
         flags |= 4u;
+        uint64_t fc[S], nfc[S], rcc[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const uint32_t P = (uint32_t)((int32_t)p0 + (int32_t)k - 32 * (S - j));     // first base of word j in the case stream
+            const uint32_t x = __funnelshift_l(t.lower[(P >> 5) + 1], t.lower[P >> 5], P & 31u);
+            const uint64_t e = spread_bits(x);
+            fc[j] = e | (e << 1);
+        }
+        if (top_bits < 64) fc[0] &= (1ull << top_bits) - 1ull;
+#pragma unroll
+        for (int j = 0; j < S; ++j) nfc[j] = ~fc[j];
+        revcomp_words<S>(nfc, rcc, k);                      // reverse (the complement inside cancels the ~): case of the reverse strand
         flip = false;
-        const uint8_t *a = t.ascii + ascii_off + start;
-        for (uint32_t i = 0; i < k; ++i) {
-            const int8_t f = (int8_t)a[i];
-            const int8_t r = (int8_t)complement_ascii(a[k - 1 - i]);
-            if (f < r) break;
-            if (f > r) { flip = true; break; }
+        bool decided = false;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const uint64_t dc = fc[j] ^ rcc[j], d = (fw[j] ^ rc[j]) | dc;
+            if (!decided && d != 0) {
+                decided = true;
+                const uint64_t m = 3ull << ((63u - (uint32_t)__clzll((long long)d)) & ~1u);      // the first base that differs
+                flip = (dc & m) ? (fc[j] & m) != 0 : (fw[j] & m) > (rc[j] & m);                    // case first, then the letter
+            }
         }
     }
 #pragma unroll

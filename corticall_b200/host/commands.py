@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from .._native import CortexJDKException
-from .cortex import CortexGraph, CortexRecord
+from .cortex import CortexGraph, CortexRecord, packCanonical
 from .kmer import CanonicalKmer
 
 
@@ -236,3 +236,53 @@ class CallHelpers:
         k = rois.getKmerSize()
         present = rois.containsWindows(trimmedQuery)
         return sorted({CanonicalKmer(trimmedQuery[i:i + k]) for i in np.nonzero(present)[0].tolist()})
+
+    @staticmethod
+    def trimQuery(walkContig: str, targets, rois: CortexGraph):
+        """Call.trimQuery :1946-1986 on the contig of the child walk `ws` (ws[i] = window i of walkContig): the span from the first
+        to the last window that is either novel (its canonical k-mer is in the ROI set: one `containsWindows` call) or shared with
+        one of the target sequences (the canonical packed k-mers of all windows come from K3, `packCanonical`; the intersection is
+        a set operation on the packed words).  Returns (firstIndex, lastIndex + 1, contig of ws[firstIndex..lastIndex])."""
+        k = rois.getKmerSize()
+        nw = max(len(walkContig) - k + 1, 0)
+        novel = np.nonzero(rois.containsWindows(walkContig))[0]
+        firstNovel, lastNovel = (int(novel[0]), int(novel[-1])) if novel.size else (-1, -1)
+        firstIndex, lastIndex = 2 ** 31 - 1, 0                                       # Integer.MAX_VALUE, 0
+        ww, wf = packCanonical(walkContig, k, rois._device)
+        void = np.dtype((np.void, 8 * ww.shape[1]))
+        clean = (wf & 6) == 0                                # upper-case ACGT only: equality of CanonicalKmers = equality of packed words
+        wkeys = np.ascontiguousarray(ww).view(void).reshape(-1)
+        dirty_walk = {}                                      # windows with N / lower case compare as the byte strings they are (rare)
+        for i in np.nonzero(~clean)[0].tolist():
+            dirty_walk.setdefault(CanonicalKmer(walkContig[i:i + k]).getKmerAsString(), []).append(i)
+        for target in (targets.values() if hasattr(targets, "values") else targets):
+            tw, tf = packCanonical(target, k, rois._device)
+            tclean = (tf & 6) == 0
+            tkeys = np.ascontiguousarray(tw[tclean]).view(void).reshape(-1)
+            shared = np.nonzero(clean & np.isin(wkeys, tkeys))[0].tolist()
+            if dirty_walk:
+                for j in np.nonzero(~tclean)[0].tolist():
+                    shared += dirty_walk.get(CanonicalKmer(target[j:j + k]).getKmerAsString(), [])
+            if shared:
+                firstIndex, lastIndex = min(firstIndex, min(shared)), max(lastIndex, max(shared))
+        if firstNovel < firstIndex:
+            firstIndex = firstNovel
+        if lastNovel > lastIndex:
+            lastIndex = lastNovel
+        if firstIndex < 0 or nw == 0:                        # ws.subList(-1, ...) throws in the reference
+            raise IndexError("trimQuery: the walk has neither a novel k-mer nor a k-mer of a target")
+        return firstIndex, lastIndex + 1, walkContig[firstIndex:lastIndex + k]
+
+    @staticmethod
+    def noveltyMask(rois: CortexGraph, query: str) -> str:
+        """The first loop of Call.makeNoveltyTrack :2062-2070: a track one character longer than the (gap-free) query with '*' over
+        every base covered by a window whose canonical k-mer is in the ROI set; the gap insertion and expansion that follow in the
+        reference work on the alignment columns and stay in the host."""
+        k = rois.getKmerSize()
+        present = rois.containsWindows(query)
+        cover = np.zeros(len(query) + 2, dtype=np.int32)
+        hit = np.nonzero(present)[0]
+        np.add.at(cover, hit, 1)
+        np.add.at(cover, hit + k, -1)
+        starred = np.cumsum(cover)[:len(query) + 1] > 0
+        return "".join("*" if s else " " for s in starred.tolist())

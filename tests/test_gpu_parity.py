@@ -204,6 +204,39 @@ def test_pack_canonical_vs_oracle(k):
     assert (w == ow).all() and (f == of).all()
 
 
+@pytest.mark.parametrize("k", [5, 21, 31, 32, 33, 47, 63, 64, 65, 96, 127])
+def test_pack_canonical_soft_masked_genome(k):
+    """Mixed-case sequence (half the bases lower case, in runs and singly, as in a soft-masked genome) with a few N / n: the
+    orientation is the reference's ASCII byte rule (SequenceUtils.java:211-219; every upper-case letter sorts before every
+    lower-case one), evaluated on the device from packed codes + case bits.  Near-palindromes put the first difference deep
+    inside the k-mer and at a case-only position."""
+    rng = np.random.default_rng(100 + k)
+    n = 30000
+    seq = synth.random_genome(5 + k, n).numpy().copy()
+    # near-palindromic stretches: a random half followed by its reverse complement, then single-base edits
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    for at in range(500, n - 400, 1500):
+        half = seq[at:at + 150].copy()
+        seq[at + 150:at + 300] = comp[half[::-1]]
+    low = rng.random(n) < 0.5
+    for at in range(0, n, 977):                         # runs of one case
+        low[at:at + int(rng.integers(1, 200))] = rng.random() < 0.5
+    seq[low] += 32
+    seq[rng.integers(0, n, 12)] = ord("N")
+    seq[rng.integers(0, n, 5)] = ord("n")
+    w, f = cb.packCanonical(seq, k)
+    ow, of = orc.pack_windows(seq, k)
+    assert (f == of).all() and (w == ow).all()
+    assert ((f & 4) != 0).sum() > n // 4 and ((f & 1) != 0).sum() > n // 8
+    # the fused windows lookup treats every such window as a miss (findRecord compares with upper-case record k-mers)
+    ctx = synth.make_ctx_file(1, min(1000, 4 ** k // 8), k, 1, adv_period=0)
+    g = cb.CortexGraph(ctx)
+    idx = g.findWindows(seq[:5000])
+    assert (idx[(f[:len(idx)] & 6) != 0] == -1).all()
+    g.dispose()
+
+
 def test_lowest_orientation_property_gpu():
     """SequenceUtilsTest :59-72 on the GPU packer: canonical == min(fw, rc) for random k in {21,31,41,51}."""
     comp = bytes.maketrans(b"ACGT", b"TGCA")
@@ -418,6 +451,34 @@ def test_findrois_command_and_call_helpers(tmp_path):
             regions.append((start, i - 1)); start = -1
     assert cb.CallHelpers.getRegions(rois, contig) == regions and len(regions) > 0
     assert [x.getKmerAsString() for x in cb.CallHelpers.sectionRois(rois, contig)] == sorted({x for x, m in zip(canon, member) if m})
+    # Call.makeNoveltyTrack :2062-2070 (the '*' track over the gap-free query) and Call.trimQuery :1946-1986, restated literally
+    track = [" "] * (len(contig) + 1)
+    for i, m in enumerate(member):
+        if m:
+            track[i:i + k] = "*" * k
+    assert cb.CallHelpers.noveltyMask(rois, contig) == "".join(track)
+    sub = contig[700:1300]                                                    # holds the lower-case stretch
+    rc_piece = cb.SequenceUtils.reverseComplement(contig[1500:1600].encode()).decode()
+    for targets in ({"t1": sub[40:200], "t2": rc_piece}, {"t": "ACGT" * 30}, {"a": contig[905:950], "b": contig[480:540]}):
+        ws_canon = [cb.CanonicalKmer(contig[i:i + k]) for i in range(len(contig) - k + 1)]
+        pos = {}
+        first_novel = last_novel = -1
+        for i, ck in enumerate(ws_canon):
+            pos.setdefault(ck, []).append(i)
+            if ck.getKmerAsString() in roi_set:
+                first_novel = i if first_novel == -1 else first_novel
+                last_novel = i
+        fi, li = 2 ** 31 - 1, 0
+        for t in targets.values():
+            for i in range(len(t) - k + 1):
+                ck = cb.CanonicalKmer(t[i:i + k])
+                if ck in pos:
+                    fi, li = min(fi, pos[ck][0]), max(li, pos[ck][-1])
+        if first_novel < fi:
+            fi = first_novel
+        if last_novel > li:
+            li = last_novel
+        assert cb.CallHelpers.trimQuery(contig, targets, rois) == (fi, li + 1, contig[fi:li + k]), list(targets)
     graph.dispose(); rois.dispose()
 
 
