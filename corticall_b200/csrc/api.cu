@@ -628,10 +628,10 @@ int cc_find_novel_host(int device, const void *host_body, uint32_t k, uint32_t s
     DeviceGuard guard(device);
     // A handle over nothing, kept per device for the life of the process: only its workspace (look-back state, staging
     // scratch -- tens of MB, too costly to allocate per call), stream and header fields are used.
-    static std::mutex mu;
+    static std::mutex mu[64];                  // one per device: scans on different GPUs do not serialise each other
     static cc_graph *cache[64] = {};
-    std::lock_guard<std::mutex> lock(mu);
     if (device >= 64) return fail(CC_ERR_ARG, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(mu[device]);
     if (!cache[device]) {
         if (int rc = cc_open_device(nullptr, k, s, c, 0, 0, device, &cache[device])) return rc;
     }

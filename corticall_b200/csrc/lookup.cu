@@ -10,20 +10,23 @@
 //                           and any query holding a byte outside ACGT (N, lower case) is a miss.
 //
 // Sections (in file order):
-//   tile staging + window_canonical      sliding windows of a sequence (seq_kernel): 2-bit stream + masks in shared memory
-//   key column access + prefix table     IndexView, key_bucket (equal slices of the array's OWN key range), L2 policies, lookup_mlp
-//   seq_kernel / find_packed kernels     K3 on windows (optionally fused with K4), K4 on packed queries
+//   tile staging + window_canonical      sliding windows of a sequence (seq_kernel): 2-bit stream + masks in shared memory; mixed
+//                                        case decided on packed codes + case bits
+//   the lookup index                     64-byte bucket lines (LineLayout, IndexView, key_bin / key_line), search by lane pairs with
+//                                        256-bit loads (lookup_lines_warp), per-thread form, overflow into the key column
+//   seq_kernel / find kernels            K3 on windows (optionally fused with K4), K4 on packed queries (find_packed_lines_kernel)
 //   rows_kernel                          K3 (+K4) on independent k-byte rows: TMA-staged tiles, byte-parallel conversion,
-//                                        warp-cooperative exact path for rows with N / lower case
-//   routed lookups over peer memory      route_kernel (owner + P2P stores), find_routed_kernel, gather_routed_kernel (P2P pull)
-//   index construction, sorted-merge support, NCCL-formulation helpers (bucket / scatter), launchers
+//                                        warp-cooperative exact path for rows with N / lower case; find_small_kernel (findRecord)
+//   routed lookups over peer memory      route_kernel (owner + bulk copies into the owners' inboxes), find_routed_kernel,
+//                                        gather_routed_kernel (P2P pull)
+//   index construction, sort support, NCCL-formulation helpers (bucket / scatter), launchers
 //
 // B200 design in one paragraph.  K3: the sequence is converted once per tile into a 2-bit big-endian bit stream in shared
 // memory and every thread cuts its k-mer out with funnel shifts, reverse-complements in registers (brev + pair swap +
-// multiword shift) and keeps the smaller.  K4: the key column (records stripped of coverage and edges, 8s bytes per key) is
-// searched through a prefix table with about one key per bucket, so a lookup costs one table sector plus one key sector,
-// issued as independent loads with several queries in flight per thread, instead of ~27 dependent probes; it is bound by
-// DRAM random access.
+// multiword shift) and keeps the smaller.  K4: HBM serves about 3.9e10 random lines per second whatever their size up to 128
+// bytes (tools/micro/randline.cu), so a lookup must cost ONE random access: the sorted keys are laid out a second time as an
+// order-preserving table of 64-byte bucket lines addressed through a small bin table in shared memory, and two lanes share a
+// line (one 256-bit load each); the kernel runs at 86 % of that access rate.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -204,8 +207,8 @@ __device__ __forceinline__ void load_key(const uint64_t *__restrict__ keys, uint
 //      line, where it is real, and makes "last slot < query" the exact test for "the bucket may continue").
 //   overflow: a bucket with more than CAP keys continues in the key column at base + CAP (rare by construction: fill = 50 %
 //      of CAP on average); the search reads on from there.
-// The word layout inside a line is chosen so that four lanes, each holding 16 bytes of the line, can compare without
-// moving key words between lanes (LineLayout).
+// The word layout inside a line is chosen so that two lanes, each holding one 32-byte half of the line, can compare without
+// moving key words between them (LineLayout).
 constexpr uint32_t kLineWords = 16;
 constexpr uint32_t kMaxBinsLog2 = 13;          // 8192 bins x 8 bytes = 64 KB of shared memory
 constexpr uint32_t kMiss32 = 0xffffffffu;
@@ -249,14 +252,17 @@ __device__ __forceinline__ uint64_t make_line_policy(uint32_t hints) {
     else if (hints == 3u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// Line loads carry the L2::64B prefetch-size qualifier: without it every random access pulls the whole 128-byte L2 line out of
+// DRAM (147 bytes of DRAM reads per lookup measured); with it the 64-byte line is all that moves (89 bytes per lookup).  The
+// access RATE does not change -- HBM serves about 3.9e10 random lines per second at 32, 64 or 128 bytes alike.
 struct Half { uint32_t w[8]; };       // one 32-byte half of a line
 __device__ __forceinline__ Half ld_line32(const uint4 *p, uint64_t policy) {
     Half h;
     if (policy == 0) {
-        asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        asm volatile("ld.global.nc.L2::64B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(h.w[0]), "=r"(h.w[1]), "=r"(h.w[2]), "=r"(h.w[3]), "=r"(h.w[4]), "=r"(h.w[5]), "=r"(h.w[6]), "=r"(h.w[7]) : "l"(p));
     } else {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
                      : "=r"(h.w[0]), "=r"(h.w[1]), "=r"(h.w[2]), "=r"(h.w[3]), "=r"(h.w[4]), "=r"(h.w[5]), "=r"(h.w[6]), "=r"(h.w[7])
                      : "l"(p), "l"(policy));
     }
@@ -265,9 +271,9 @@ __device__ __forceinline__ Half ld_line32(const uint4 *p, uint64_t policy) {
 __device__ __forceinline__ uint4 ld_line16(const uint4 *p, uint64_t policy) {
     uint4 v;
     if (policy == 0) {              // no hint at all: a table small enough for L2 to help is left to the default replacement
-        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     } else {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
     }
     return v;

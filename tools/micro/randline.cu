@@ -25,6 +25,32 @@ __global__ void __launch_bounds__(512, 2) coop_kernel(const uint4 *lines, uint64
     }
     if (acc == 0x12345678u) out[0] = acc;
 }
+// the same with an explicit L2 prefetch-size qualifier on the loads (PF = 64, 128 or 256 bytes)
+template <int PF>
+__device__ __forceinline__ uint4 ld_pf(const uint4 *p) {
+    uint4 v;
+    if (PF == 64) asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (PF == 128) asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+template <int PF>
+__global__ void __launch_bounds__(512, 2) coop_pf_kernel(const uint4 *lines, uint64_t nlines, uint64_t nq, uint32_t *out) {
+    const uint32_t lane = threadIdx.x & 31, j = lane % 4;
+    uint32_t acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * 512 + threadIdx.x; i < nq; i += (uint64_t)gridDim.x * 512) {
+        const uint64_t l = mix(i) % nlines;
+        uint4 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint64_t lr = __shfl_sync(0xffffffffu, l, r, 4);
+            v[r] = ld_pf<PF>(lines + lr * 4 + j);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc += v[r].x ^ v[r].y ^ v[r].z ^ v[r].w;
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
 template <int LINE16>
 __global__ void __launch_bounds__(512, 2) thread_kernel(const uint4 *lines, uint64_t nlines, uint64_t nq, uint32_t *out) {
     uint32_t acc = 0;
@@ -68,6 +94,9 @@ int main() {
     run("thread", thread_kernel<2>, 2, buf, bytes, nq, out);
     run("thread", thread_kernel<4>, 4, buf, bytes, nq, out);
     run("thread", thread_kernel<8>, 8, buf, bytes, nq, out);
+    run("coop L2::64B", coop_pf_kernel<64>, 4, buf, bytes, nq, out);
+    run("coop L2::128B", coop_pf_kernel<128>, 4, buf, bytes, nq, out);
+    run("coop L2::256B", coop_pf_kernel<256>, 4, buf, bytes, nq, out);
     run("coop 320MB (8-GPU shard)", coop_kernel<4>, 4, buf, 320ull << 20, nq, out);
     run("coop 40MB (L2)", coop_kernel<4>, 4, buf, 40ull << 20, nq, out);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
