@@ -699,6 +699,66 @@ def test_shard_index_spans_its_own_key_range(k):
     whole.dispose()
 
 
+@pytest.mark.parametrize("k", [21, 31, 47, 63, 95])
+def test_line_index_on_clustered_keys(k):
+    """The bucket-line index on key sets that are nothing like uniform: dense runs of consecutive k-mers (thousands of keys in one
+    bucket: the search continues in the key column, linearly and then by bisection), keys that differ only below the top 64 bits
+    (k > 32: same bin, same line), a lone key far from the rest (almost every bin empty), all fill factors and bin counts.  Every
+    answer against a numpy searchsorted over the sorted keys (the oracle's order is the same unsigned word order)."""
+    rng = np.random.default_rng(k)
+    s = (k + 31) // 32
+    top_bits = 2 * k - 64 * (s - 1)
+    def rand_keys(n):
+        w = rng.integers(0, 2 ** 63, size=(n, s), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(n, s), dtype=np.uint64)
+        if top_bits < 64:
+            w[:, 0] &= np.uint64((1 << top_bits) - 1)
+        return w
+    parts = [rand_keys(3000)]
+    base = rand_keys(6)
+    for b in base[:3]:                                   # runs of consecutive keys: differ in the last word only
+        run = np.repeat(b[None, :], 5000, axis=0)
+        run[:, -1] = (run[:, -1] & np.uint64(0xffffffffffff0000)) + np.arange(5000, dtype=np.uint64) * np.uint64(3)
+        parts.append(run)
+    if s > 1:                                            # same top 64 bits, different low words
+        for b in base[3:]:
+            run = np.repeat(b[None, :], 2000, axis=0)
+            run[:, -1] = rng.integers(0, 2 ** 63, size=2000, dtype=np.uint64)
+            parts.append(run)
+    lone = np.zeros((1, s), dtype=np.uint64)             # the smallest possible key, far below everything else
+    parts.append(lone)
+    keys = np.concatenate(parts)
+    order = np.lexsort([keys[:, w] for w in range(s - 1, -1, -1)])
+    keys = keys[order]
+    keep = np.ones(len(keys), dtype=bool)
+    keep[1:] = (keys[1:] != keys[:-1]).any(axis=1)
+    keys = keys[keep]
+    n, c = len(keys), 1
+    tw = [torch.from_numpy(keys[:, w].copy().view(np.int64)) for w in range(s)]
+    cov, edges = synth.coverage_and_edges(1, n, c, "cpu", adv_period=0)
+    body = synth.assemble_records(tw, cov, edges).cuda()
+    g = cb.CortexGraph.fromDevice(body.data_ptr(), k, c, n, keepalive=body)
+    # queries: every key, every key +-1 in the last word (mostly misses next to hits), random keys
+    q = np.concatenate([keys, keys + np.array([0] * (s - 1) + [1], dtype=np.uint64), keys - np.array([0] * (s - 1) + [1], dtype=np.uint64), rand_keys(5000)])
+    if top_bits < 64:
+        q[:, 0] &= np.uint64((1 << top_bits) - 1)
+    be = lambda a: np.ascontiguousarray(a.astype(">u8")).view(np.dtype((np.void, 8 * s))).reshape(-1)
+    kb, qb = be(keys), be(q)
+    pos = np.searchsorted(kb, qb)
+    want = np.where((pos < n) & (kb[np.minimum(pos, n - 1)] == qb), pos, -1)
+    assert (want[:n] == np.arange(n)).all()
+    try:
+        for fill in (50, 100, 10):
+            N.set_option("index_fill_pct", fill)
+            for bits in (0, 1, 13):
+                g.buildIndex(bits)
+                assert (g.findPacked(q) == want).all(), (fill, bits)
+        assert (g.findPacked(q, algo=cb.CC_ALGO_BSEARCH) == want).all()
+        assert (g.findPacked(q, algo=cb.CC_ALGO_MERGE) == want).all()
+    finally:
+        N.set_option("index_fill_pct", 50)
+    g.dispose()
+
+
 # ------------------------------------------------------------------ next row: CortexCollection / Join
 
 @pytest.mark.parametrize("k,colors,sizes", [(31, (1, 1), (5000, 7000)), (47, (1, 1, 1, 1), (20000, 30000, 25000, 9000)),
