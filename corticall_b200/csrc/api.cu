@@ -374,6 +374,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "rows_fused")) o.rows_fused = (int)value;
     else if (!strcmp(name, "rows_rpt2_max_k")) o.rows_rpt2_max_k = (int)value;
     else if (!strcmp(name, "route_blocks_per_sm")) o.route_blocks_per_sm = (int)value;
+    else if (!strcmp(name, "route_stage_depth")) o.route_stage_depth = (int)value;
     else if (!strcmp(name, "routed_search_blocks_per_sm")) o.routed_search_blocks_per_sm = (int)value;
     else if (!strcmp(name, "gather_blocks_per_sm")) o.gather_blocks_per_sm = (int)value;
     else if (!strcmp(name, "host_chunk_mb")) o.host_chunk_mb = (int)value;

@@ -37,6 +37,7 @@ struct Options {
     int lookup_l2_hints = -1;    // line loads: -1 = auto (plain up to 1 GB of lines, evict-first beyond), 0 plain, 1 evict-first, 2 evict-normal, 3 evict-last
     int find_bins_smem = 1;      // packed / routed search: stage the bin table in shared memory
     int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
+    int route_stage_depth = 2;            // staging areas per route CTA (2..4): tiles whose bulk copies may still be reading shared memory
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1
     int routed_search_blocks_per_sm = 0;  // cap on the CTAs of find_routed_kernel per SM (0 = all resident CTAs)
     int gather_blocks_per_sm = 16;  // cap on resident gather CTAs per SM

@@ -972,8 +972,8 @@ constexpr uint32_t kOwnerLutBits = 10;         // owner lookup: 2^10 key prefixe
 // Dynamic shared memory of route_kernel: two staging areas of wire keys (each owner's run padded to its destination's
 // 16-byte phase).
 inline uint32_t route_stage_words(uint32_t tile_q, uint32_t kw, int nshards) { return (tile_q * kw + 8u * (uint32_t)nshards + 3u) & ~3u; }
-inline size_t route_smem_bytes(uint32_t tile_q, uint32_t kw, int nshards) {
-    return 2u * (size_t)route_stage_words(tile_q, kw, nshards) * 4u;       // two staging areas: a tile's runs leave while the next is built
+inline size_t route_smem_bytes(uint32_t tile_q, uint32_t kw, int nshards, int depth) {
+    return (size_t)depth * route_stage_words(tile_q, kw, nshards) * 4u;     // `depth` staging areas: tiles' runs leave while the next are built
 }
 
 // Tile of BLOCK * kRouteQ queries per block iteration.  The tile is regrouped by owner in shared memory, every owner's run
@@ -983,7 +983,7 @@ template <int S, int KW, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags, uint64_t nq,
                                                       const uint64_t *__restrict__ splitters, int nshards, int my_rank, uint64_t cap,
                                                       PeerPtrs inbox, RouteState rs, unsigned long long *cursors, uint32_t stage_words,
-                                                      uint32_t k_bases) {
+                                                      uint32_t k_bases, uint32_t depth) {
     constexpr uint32_t kTile = BLOCK * kRouteQ;
     extern __shared__ __align__(128) uint32_t stage_all[];   // 2 x [stage_words] wire keys (double-buffered: see the copy-out)
     __shared__ uint32_t hist[kMaxShards], loc[kMaxShards + 1], locw[kMaxShards], endw[kMaxShards];
@@ -1018,11 +1018,15 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
     const uint64_t ntiles = route_tiles(nq, kTile);
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        uint32_t *stage = stage_all + (it & 1u) * stage_words;
+        uint32_t *stage = stage_all + (it % depth) * stage_words;
         for (int i = threadIdx.x; i < nshards; i += BLOCK) hist[i] = 0;
-        // this tile's staging area was last read by the bulk copies of tile it-2: their issuers wait for those reads here
-        // (at most the copies of tile it-1 stay pending); the barrier below publishes that to the whole CTA
-        if (threadIdx.x < (uint32_t)nshards) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // this tile's staging area was last read by the bulk copies of tile it-depth: their issuers wait for those reads here
+        // (the copies of the depth-1 tiles in between stay pending); the barrier below publishes that to the whole CTA
+        if (threadIdx.x < (uint32_t)nshards) {
+            if (depth == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else if (depth == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        }
         __syncthreads();
         uint64_t q[kRouteQ][S];
         uint32_t own[kRouteQ], rank_in[kRouteQ];
@@ -1877,13 +1881,14 @@ int launch_route(const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t n
         const RouteState rs = route_state_of(dev_route_state, max_q, nshards);
         const int block = route_block_for(nshards);
         const uint32_t tile_q = (uint32_t)block * kRouteQ, stage_words = route_stage_words(tile_q, kw, nshards);
-        const size_t smem = route_smem_bytes(tile_q, kw, nshards);
+        const int depth = std::min(4, std::max(2, options().route_stage_depth));
+        const size_t smem = route_smem_bytes(tile_q, kw, nshards, depth);
         const int per_sm = options().route_blocks_per_sm > 0 ? options().route_blocks_per_sm : 32;
 #define CC_ROUTE(BLOCK_) CC_DISPATCH_SKW(s, kw, {                                                                                   \
             CC_CUDA(cudaFuncSetAttribute(route_kernel<S_, KW_, BLOCK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
             const int grid = resident_grid(route_kernel<S_, KW_, BLOCK_>, BLOCK_, smem, route_tiles(nq, tile_q), sm_count_now(), per_sm); \
             route_kernel<S_, KW_, BLOCK_><<<grid, BLOCK_, smem, st>>>(dev_words, dev_flags, nq, dev_splitters, nshards, my_rank, cap, inbox, rs, \
-                                                                      cursors, stage_words, k); })
+                                                                      cursors, stage_words, k, (uint32_t)depth); })
         if (block == 256) { CC_ROUTE(256); } else { CC_ROUTE(128); }
 #undef CC_ROUTE
         count_launch();

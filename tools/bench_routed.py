@@ -42,8 +42,8 @@ for o in range(0, nq, 1 << 24):
 del words
 res = torch.empty(nq, dtype=torch.int64, device=dev)
 ref = None
-for name, opts in (("sequential", {}), ("sequential, line loads evict-first", {"lookup_l2_hints": 1}), ("sequential, route 2 CTAs/SM", {"route_blocks_per_sm": 2}),
-                   ("sequential, route 3 CTAs/SM", {"route_blocks_per_sm": 3})):
+for name, opts in (("sequential", {}), ("sequential, route staging 3 deep", {"route_stage_depth": 3}), ("sequential, route staging 4 deep", {"route_stage_depth": 4}),
+                   ("sequential, route staging 3 deep, 4 CTAs/SM", {"route_stage_depth": 3, "route_blocks_per_sm": 4})):
     for kname, v in opts.items():
         N.set_option(kname, v)
     rl = RoutedLookup(g, splitters, rank, world, dev, cap=int(nq / world * 1.25) + 4096, k=K, max_batch=nq)
@@ -64,6 +64,7 @@ for name, opts in (("sequential", {}), ("sequential, line loads evict-first", {"
     N.set_option("lookup_l2_hints", -1)
     N.set_option("routed_search_blocks_per_sm", 0)
     N.set_option("route_blocks_per_sm", 0)
+    N.set_option("route_stage_depth", 2)
     torch.cuda.empty_cache()
 if len(sys.argv) > 3 and sys.argv[3] == "pipelines":
     res2 = torch.empty_like(res)
