@@ -83,13 +83,17 @@ def peaks():
 
 
 def source_stamp() -> str:
-    """Hash of the CUDA sources: ncu-derived numbers under profiles/ carry it and are ignored when the kernels changed since."""
+    """Hash of what determines the profiled kernels -- the kernel sources and the default tuning options: ncu-derived numbers under
+    profiles/ carry it and are ignored once any of that has changed."""
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, "corticall_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".hpp")):
-            with open(os.path.join(d, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
+    for name in ("device_utils.cuh", "lookup.cu", "scan.cu"):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    with open(os.path.join(d, "cc_internal.hpp")) as f:
+        m = re.search(r"struct Options \{.*?\n\};", f.read(), flags=re.S)
+        h.update(m.group(0).encode() if m else b"?")
     return h.hexdigest()[:16]
 
 

@@ -240,6 +240,13 @@ void destroy(cc_graph *g) {
     if (g->novel_buf) cudaFree(g->novel_buf);
     if (g->novel_idx) cudaFree(g->novel_idx);
     if (g->small_host) cudaFreeHost(g->small_host);
+    for (int b = 0; b < 2; ++b) {
+        if (g->look_in[b]) cudaFree(g->look_in[b]);
+        if (g->look_flag[b]) cudaFree(g->look_flag[b]);
+        if (g->look_out[b]) cudaFree(g->look_out[b]);
+    }
+    if (g->look_stream) cudaStreamDestroy(g->look_stream);
+    if (g->look_done) cudaEventDestroy(g->look_done);
     if (g->dev_alloc) {
         if (g->dev_alloc_pooled && g->stream) { cudaFreeAsync(g->dev_alloc, g->stream); cudaStreamSynchronize(g->stream); }
         else cudaFree(g->dev_alloc);
@@ -838,6 +845,11 @@ int cc_find_packed_dev(cc_graph *g, const uint64_t *dev_words, const uint8_t *de
 }  // extern "C"
 
 namespace {
+struct StageView {
+    void *p;
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
 // Host-buffer lookups: the batch is streamed through the device in chunks on two alternating streams so that
 // (with page-locked caller buffers) the copies of one chunk overlap the search of the other.
 template <class Launch>
@@ -848,16 +860,32 @@ int chunked_lookup(cc_graph *g, const uint8_t *in, uint64_t in_bytes_per_q, uint
     g->stats = cc_stats{};
     const uint64_t launches0 = g_launches.load();
     const uint64_t chunk_q = std::max<uint64_t>(1, std::min<uint64_t>(nq, 1ull << 24));
-    cudaStream_t st[2] = {g->stream, nullptr};
-    CC_CUDA(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
-    struct Kill { cudaStream_t s; ~Kill() { cudaStreamDestroy(s); } } kill{st[1]};
-    DevBuf din[2], dflag[2], dout[2];
+    // the staging buffers, the second stream and its event live in the handle: a call allocates only when it needs more room
+    // than any call before it (per-call cudaMalloc / cudaFree of ~2 GB cost more than the copies of a 3e7-query batch)
+    if (!g->look_stream) CC_CUDA(cudaStreamCreateWithFlags(&g->look_stream, cudaStreamNonBlocking));
+    if (!g->look_done) CC_CUDA(cudaEventCreateWithFlags(&g->look_done, cudaEventDisableTiming));
+    cudaStream_t st[2] = {g->stream, g->look_stream};
     const int nb = nq > chunk_q ? 2 : 1;
-    for (int b = 0; b < nb; ++b) {
-        if (int rc = din[b].alloc(chunk_q * in_bytes_per_q + in_extra_bytes + 64)) return rc;
-        if (flags) if (int rc = dflag[b].alloc(chunk_q)) return rc;
-        if (int rc = dout[b].alloc(chunk_q * 8)) return rc;
+    const size_t need_in = chunk_q * in_bytes_per_q + in_extra_bytes + 64;
+    if (need_in > g->look_in_cap || chunk_q > g->look_q_cap || (nb == 2 && !g->look_in[1])) {
+        CC_CUDA(cudaStreamSynchronize(st[0]));
+        CC_CUDA(cudaStreamSynchronize(st[1]));
+        const size_t in_cap = std::max(need_in, g->look_in_cap), q_cap = std::max<size_t>(chunk_q, g->look_q_cap);
+        for (int b = 0; b < 2; ++b) {
+            if (g->look_in[b]) { cudaFree(g->look_in[b]); g->look_in[b] = nullptr; }
+            if (g->look_flag[b]) { cudaFree(g->look_flag[b]); g->look_flag[b] = nullptr; }
+            if (g->look_out[b]) { cudaFree(g->look_out[b]); g->look_out[b] = nullptr; }
+        }
+        g->look_in_cap = g->look_q_cap = 0;
+        for (int b = 0; b < nb; ++b) {
+            CC_CUDA(cudaMalloc(&g->look_in[b], in_cap));
+            CC_CUDA(cudaMalloc(&g->look_flag[b], q_cap + 64));
+            CC_CUDA(cudaMalloc(&g->look_out[b], q_cap * 8 + 64));
+        }
+        g->look_in_cap = in_cap;
+        g->look_q_cap = q_cap;
     }
+    StageView din[2] = {{g->look_in[0]}, {g->look_in[1]}}, dflag[2] = {{g->look_flag[0]}, {g->look_flag[1]}}, dout[2] = {{g->look_out[0]}, {g->look_out[1]}};
     CC_CUDA(cudaEventRecord(g->ev0, g->stream));
     CC_CUDA(cudaStreamWaitEvent(st[1], g->ev0, 0));
     int b = 0;
@@ -872,11 +900,8 @@ int chunked_lookup(cc_graph *g, const uint8_t *in, uint64_t in_bytes_per_q, uint
         g->stats.d2h_bytes += m * 8;
     }
     if (nb == 2) {
-        cudaEvent_t done;
-        CC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-        cudaEventRecord(done, st[1]);
-        cudaStreamWaitEvent(g->stream, done, 0);
-        cudaEventDestroy(done);
+        CC_CUDA(cudaEventRecord(g->look_done, st[1]));
+        CC_CUDA(cudaStreamWaitEvent(g->stream, g->look_done, 0));
     }
     CC_CUDA(cudaEventRecord(g->ev1, g->stream));
     if (int rc = sync_stream(g, g->stream)) return rc;

@@ -131,6 +131,11 @@ struct cc_graph {
     void *novel_idx = nullptr;
     uint64_t novel_cap = 0;
     std::vector<int32_t> parents_cached;   // what scan_ws.parents currently holds
+    // device staging of the host-buffer lookups (cc_find_ascii / windows / packed): two chunks in flight, kept across calls
+    void *look_in[2] = {nullptr, nullptr}, *look_flag[2] = {nullptr, nullptr}, *look_out[2] = {nullptr, nullptr};
+    size_t look_in_cap = 0, look_q_cap = 0;
+    cudaStream_t look_stream = nullptr;        // second stream: the copies of one chunk overlap the search of the other
+    cudaEvent_t look_done = nullptr;
     // mapped pinned staging of cc_find_records (the low-latency findRecord path): queries | indices | record bytes
     uint8_t *small_host = nullptr, *small_dev = nullptr;
     size_t small_bytes = 0;
