@@ -48,6 +48,7 @@ struct SeqTile {
     uint32_t codes[kStreamBases / 16 + 4];     // 2 bits per base, base b in word b/16, bits 31-2*(b%16)..
     uint32_t inval[kStreamBases / 32 + 4];     // 1 bit per base: byte outside ACGTacgt
     uint32_t lower[kStreamBases / 32 + 4];     // 1 bit per base: acgt
+    uint32_t dirty[kStreamBases / 32 + 4];     // inval | lower: one test clears the common window (upper-case ACGT only)
 };
 
 // ------------------------------------------------------------------ tile staging
@@ -69,30 +70,38 @@ __device__ __forceinline__ uint32_t stage_tile(SeqTile &t, const uint8_t *__rest
         for (uint32_t i = head + body + threadIdx.x; i < nb; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    // streams: group g covers stream positions [32g, 32g+32); position p holds tile byte p - kPadBases
+    // streams: group g covers stream positions [32g, 32g+32); position p holds tile byte p - kPadBases.  Four bases per 32-bit
+    // operation: code = ((u>>1)^(u>>2))&3 on the upper-cased byte u, the letter rebuilt from its code with PRMT (a byte that
+    // differs is not in ACGTacgt), the four 2-bit codes and the four flag bits gathered by one multiply each.
     const uint32_t ngroups = (nb + kPadBases + 31) / 32 + 2;
     for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-        uint32_t c0 = 0, c1 = 0, inv = 0, low = 0;
-#pragma unroll 8
-        for (uint32_t j = 0; j < 32; ++j) {
-            const int32_t pos = (int32_t)(g * 32 + j) - (int32_t)kPadBases;
-            uint32_t code = 0, bad = 0, lc = 0;
-            if (pos >= 0 && pos < (int32_t)nb) {
-                const uint32_t ch = dst[pos];
-                const uint32_t f = ch | 0x20u;
-                const bool ok = (f == 'a') | (f == 'c') | (f == 'g') | (f == 't');
-                code = ok ? base_code(ch) : 0u;
-                bad = ok ? 0u : 1u;
-                lc = (ok && (ch & 0x20u)) ? 1u : 0u;
-            }
-            if (j < 16) c0 |= code << (30 - 2 * j); else c1 |= code << (30 - 2 * (j - 16));
-            inv |= bad << (31 - j);
-            low |= lc << (31 - j);
+        uint32_t cw[2] = {0u, 0u}, inv = 0, low = 0;
+#pragma unroll
+        for (uint32_t kq = 0; kq < 8; ++kq) {
+            const int32_t pw = (int32_t)(g * 32 + 4 * kq) - (int32_t)kPadBases;       // tile byte of the word's first base (multiple of 4)
+            if (pw < 0 || pw >= (int32_t)nb) continue;                                 // outside the tile: clean zeros
+            uint32_t keep = 0x01010101u;                                               // bytes inside [0, nb)
+            if (pw + 4 > (int32_t)nb) keep = 0x01010101u >> (8 * (uint32_t)(pw + 4 - (int32_t)nb));
+            const uint32_t wv = lds_u32<false>(dst + pw);
+            const uint32_t u = wv & 0xdfdfdfdfu;
+            const uint32_t x = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+            const uint32_t y = x | (x >> 4);
+            const uint32_t z = y & 0x00ff00ffu;
+            const uint32_t sel = (z | (z >> 8)) & 0xffffu;
+            const uint32_t d = u ^ __byte_perm(0x54474341u, 0u, sel);
+            const uint32_t nzb = ((d | ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & keep;   // 1 per byte that is not a letter of ACGTacgt
+            const uint32_t okb = keep & ~nzb;
+            const uint32_t lcb = (wv >> 5) & okb;                                         // 1 per lower-case letter
+            const uint32_t code8 = ((x & (okb * 3u)) * 0x40100401u) >> 24;                // c0<<6 | c1<<4 | c2<<2 | c3
+            cw[kq >> 2] |= code8 << (24u - 8u * (kq & 3u));
+            inv |= ((nzb * 0x80402010u) >> 28) << (28u - 4u * kq);                        // first base = highest bit
+            low |= ((lcb * 0x80402010u) >> 28) << (28u - 4u * kq);
         }
-        t.codes[2 * g] = c0;
-        t.codes[2 * g + 1] = c1;
+        t.codes[2 * g] = cw[0];
+        t.codes[2 * g + 1] = cw[1];
         t.inval[g] = inv;
         t.lower[g] = low;
+        t.dirty[g] = inv | low;
     }
     __syncthreads();
     return off;
@@ -126,7 +135,8 @@ __device__ __forceinline__ uint64_t spread_bits(uint32_t x);
 template <int S>
 __device__ __forceinline__ uint32_t window_canonical(const SeqTile &t, uint32_t ascii_off, uint32_t start, uint32_t k, uint64_t (&out)[S]) {
     const uint32_t p0 = start + kPadBases;                   // stream position of the window's first base
-    if (any_bits(t.inval, p0, k)) {
+    const bool dirty = any_bits(t.dirty, p0, k);
+    if (dirty && any_bits(t.inval, p0, k)) {
 #pragma unroll
         for (int i = 0; i < S; ++i) out[i] = 0;
         return 2u;
@@ -143,7 +153,7 @@ __device__ __forceinline__ uint32_t window_canonical(const SeqTile &t, uint32_t 
     revcomp_words<S>(fw, rc, k);
     bool flip = words_less<S>(rc, fw);
     uint32_t flags = 0;
-    if (any_bits(t.lower, p0, k)) {
+    if (dirty) {
         // Mixed / lower case (soft-masked genomes are half lower case): the reference compares ASCII bytes, seq[i] against
         // complement(seq[k-1-i]), first difference decides (SequenceUtils.java:211-219).  For bytes in ACGTacgt that is the
         // lexicographic order of (case, code) per base -- every upper-case letter sorts before every lower-case one and the
@@ -1402,19 +1412,101 @@ __global__ void extract_word_kernel(const uint64_t *__restrict__ words, const ui
 __global__ void iota_kernel(uint32_t *p, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
-// Sorted pass: thread i resolves query perm[i]; neighbouring threads probe neighbouring keys.
-template <int S, int KW>
-__global__ void __launch_bounds__(kBlock) find_sorted_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
-                                                             const uint32_t *__restrict__ perm, uint64_t nq, IndexView ix,
-                                                             int64_t *__restrict__ out_index) {
-    const uint64_t pol = make_line_policy(0u);
-    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < nq; i += (uint64_t)gridDim.x * kBlock) {
-        const uint64_t src = perm[i];
+// ------------------------------------------------------------------ sorted-merge lookup (CC_ALGO_MERGE)
+// For a batch in ascending key order (the records of another graph: FindShared, RecoverExcludedKmers, Join-like callers; or any
+// batch after a radix sort) the lookup is a merge of two sorted arrays.  The batch is cut into tiles of kMergeTile queries; a
+// first kernel finds, by binary search, where each tile's first query falls in the key column (merge-path partition: one search
+// per tile instead of one per query); a tile's queries can then only match keys inside its window [b[t], b[t+1]], which is
+// staged in shared memory once and searched there (a batch denser than the table has windows of a few hundred keys), or searched
+// in place when it is too long to stage (a sparse batch: the window only narrows the binary search).  Queries and results
+// stream through once, coalesced when the batch arrived sorted: 8s + 8 bytes per query + the key column once.
+constexpr uint32_t kMergeTile = 1024;         // queries per tile (4 per thread)
+constexpr uint32_t kMergeWin = 2048;          // keys staged per window
+
+template <int S>
+__global__ void sorted_check_kernel(const uint64_t *__restrict__ words, uint64_t nq, unsigned int *unsorted) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < nq; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t a[S], b[S];
+        load_key<S>(words, i - 1, a);
+        load_key<S>(words, i, b);
+        if (words_less<S>(b, a)) *unsorted = 1u;
+    }
+}
+
+// bounds[t] = lower_bound(keys, first query of tile t) for t < ntiles; bounds[ntiles] = lower_bound(keys, last query).
+template <int S>
+__global__ void merge_bounds_kernel(const uint64_t *__restrict__ words, const uint32_t *__restrict__ perm, uint64_t nq, uint64_t ntiles,
+                                    const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ bounds) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = t < ntiles ? t * kMergeTile : nq - 1;
         uint64_t q[S];
-        load_key<S>(words, src, q);
-        int64_t r = -1;
-        if (!(flags && (flags[src] & 6u))) r = lookup_lines_thread<S, KW>(ix, ix.bins, pol, q);
-        out_index[src] = r;
+        load_key<S>(words, perm ? perm[j] : j, q);
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = lo + ((hi - lo) >> 1);
+            uint64_t km[S];
+            load_key<S>(keys, mid, km);
+            if (words_less<S>(km, q)) lo = mid + 1; else hi = mid;
+        }
+        bounds[t] = lo;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kBlock) find_merge_kernel(const uint64_t *__restrict__ words, const uint8_t *__restrict__ flags,
+                                                            const uint32_t *__restrict__ perm, uint64_t nq, uint64_t ntiles,
+                                                            const uint64_t *__restrict__ bounds, IndexView ix, int64_t *__restrict__ out_index) {
+    extern __shared__ __align__(16) uint64_t merge_win[];           // [kMergeWin][S]
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t lo = bounds[t], hi = min(bounds[t + 1] + 1, ix.n);
+        const uint32_t w = (uint32_t)min(hi - lo, (uint64_t)kMergeWin + 1);
+        const bool staged = w <= kMergeWin;
+        __syncthreads();                                            // the previous tile's window is no longer read
+        if (staged) {
+            for (uint32_t i = threadIdx.x; i < w * S; i += kBlock) merge_win[i] = __ldg(ix.keys + lo * S + i);
+        }
+        __syncthreads();
+        // thread i takes kMergeTile / kBlock CONSECUTIVE queries of the sorted order: one binary search for the first, the
+        // others continue from where their predecessor stopped (ascending queries only ever move forward in the window)
+        constexpr int PER = (int)(kMergeTile / kBlock);
+        uint32_t at = 0;
+        bool have_at = false;
+#pragma unroll
+        for (int h = 0; h < PER; ++h) {
+            const uint64_t j = t * kMergeTile + (uint64_t)threadIdx.x * PER + h;
+            if (j >= nq) continue;
+            const uint64_t src = perm ? perm[j] : j;
+            uint64_t q[S];
+            load_key<S>(words, src, q);
+            int64_t r = -1;
+            if (staged) {
+                if (!have_at) {
+                    uint32_t a = 0, b = w;                          // first window key >= q
+                    while (a < b) {
+                        const uint32_t mid = (a + b) >> 1;
+                        uint64_t km[S];
+#pragma unroll
+                        for (int x = 0; x < S; ++x) km[x] = merge_win[mid * S + x];
+                        if (words_less<S>(km, q)) a = mid + 1; else b = mid;
+                    }
+                    at = a;
+                    have_at = true;
+                }
+                uint64_t km[S];
+                while (at < w) {                                    // the merge step: advance to the first key >= q
+#pragma unroll
+                    for (int x = 0; x < S; ++x) km[x] = merge_win[at * S + x];
+                    if (!words_less<S>(km, q)) break;
+                    ++at;
+                }
+                if (at < w && words_equal<S>(km, q)) r = (int64_t)(lo + at + ix.first_index);
+            } else {
+                const int64_t f = search_range<S>(ix.keys, lo, hi, q);
+                r = f < 0 ? f : f + (int64_t)ix.first_index;
+            }
+            if (flags && (__ldg(flags + src) & 6u)) r = -1;
+            out_index[src] = r;
+        }
     }
 }
 
@@ -1711,11 +1803,32 @@ int launch_find_packed(cc_graph *g, const uint64_t *dev_words, const uint8_t *de
     const uint32_t s = g->h.s, kw = wire_words(g->h.k);
     const int grid = grid_for(nq, kBlock, g->sm_count, 8);
     if (algo == CC_ALGO_MERGE) {
-        uint32_t *perm = nullptr;
-        if (int rc = sort_permutation(dev_words, nq, s, g->h.k, st, &perm)) return rc;
-        CC_DISPATCH_SKW(s, kw, find_sorted_kernel<S_, KW_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, perm, nq, ix, dev_index));
+        // is the batch already in ascending order?  (one pass + one host round trip: this mode is synchronous up to here)
+        unsigned int *d_unsorted = nullptr, h_unsorted = 0;
+        CC_CUDA(cudaMallocAsync(&d_unsorted, sizeof(unsigned int), st));
+        CC_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(unsigned int), st));
+        CC_DISPATCH_S(s, sorted_check_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, nq, d_unsorted));
         count_launch();
-        cudaFreeAsync(perm, st);
+        CC_CUDA(cudaMemcpyAsync(&h_unsorted, d_unsorted, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaStreamSynchronize(st));
+        cudaFreeAsync(d_unsorted, st);
+        uint32_t *perm = nullptr;
+        if (h_unsorted)
+            if (int rc = sort_permutation(dev_words, nq, s, g->h.k, st, &perm)) return rc;
+        const uint64_t ntiles = (nq + kMergeTile - 1) / kMergeTile;
+        uint64_t *bounds = nullptr;
+        CC_CUDA(cudaMallocAsync(&bounds, (ntiles + 1) * sizeof(uint64_t), st));
+        const int bgrid = grid_for(ntiles + 1, kBlock, g->sm_count, 8);
+        const size_t msmem = (size_t)kMergeWin * s * sizeof(uint64_t);
+        CC_DISPATCH_S(s, {
+            merge_bounds_kernel<S_><<<bgrid, kBlock, 0, st>>>(dev_words, perm, nq, ntiles, ix.keys, ix.n, bounds);
+            if (msmem > 48 * 1024) CC_CUDA(cudaFuncSetAttribute(find_merge_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            const int mgrid = resident_grid(find_merge_kernel<S_>, kBlock, msmem, ntiles, g->sm_count);
+            find_merge_kernel<S_><<<mgrid, kBlock, msmem, st>>>(dev_words, dev_flags, perm, nq, ntiles, bounds, ix, dev_index);
+        });
+        count_launch(2);
+        cudaFreeAsync(bounds, st);
+        if (perm) cudaFreeAsync(perm, st);
     } else if (algo == CC_ALGO_BSEARCH) {
         CC_DISPATCH_S(s, find_bsearch_kernel<S_><<<grid, kBlock, 0, st>>>(dev_words, dev_flags, nq, ix, dev_index));
         count_launch();

@@ -157,7 +157,9 @@ CC_API int cc_pack_kmers_dev(int device, const uint8_t *dev_kmers, uint64_t nq, 
 
 /* ---------------------------------------------------------------- K4: batched lookups (findRecord) */
 /* algo: 0 = auto (the line index: one 64-byte bucket line per lookup), 1 = plain binary search over the key column,
- *       2 = sort the batch first, then probe the line index in key order (comparison mode). */
+ *       2 = sorted-merge: a batch in ascending key order (the records of another graph, or any batch after the radix sort this mode
+ *           runs when it finds the batch unsorted) is cut into tiles whose window of the key column is found by one binary search per
+ *           tile and searched through shared memory; queries and results stream through once.  Synchronises the stream once. */
 enum { CC_ALGO_AUTO = 0, CC_ALGO_BSEARCH = 1, CC_ALGO_MERGE = 2 };
 /* Build (or rebuild) the lookup index: key column + bucket lines (an order-preserving table of 64-byte lines over the
  * array's own key range); validates ascending order (CC_ERR_UNSORTED).  Called lazily by the first

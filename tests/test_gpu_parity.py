@@ -753,7 +753,14 @@ def test_line_index_on_clustered_keys(k):
                 g.buildIndex(bits)
                 assert (g.findPacked(q) == want).all(), (fill, bits)
         assert (g.findPacked(q, algo=cb.CC_ALGO_BSEARCH) == want).all()
-        assert (g.findPacked(q, algo=cb.CC_ALGO_MERGE) == want).all()
+        assert (g.findPacked(q, algo=cb.CC_ALGO_MERGE) == want).all()            # unsorted batch: radix sort, then the merge
+        qo = np.lexsort([q[:, w] for w in range(s - 1, -1, -1)])                   # the same batch in ascending order: merge only
+        assert (g.findPacked(q[qo], algo=cb.CC_ALGO_MERGE) == want[qo]).all()
+        sparse = q[qo][::997]                                                      # windows far longer than a tile can stage
+        assert (g.findPacked(sparse, algo=cb.CC_ALGO_MERGE) == want[qo][::997]).all()
+        fl = np.zeros(len(q), dtype=np.uint8)
+        fl[::5] = 2
+        assert (g.findPacked(q[qo], fl, algo=cb.CC_ALGO_MERGE) == np.where(fl == 0, want[qo], -1)).all()
     finally:
         N.set_option("index_fill_pct", 50)
     g.dispose()

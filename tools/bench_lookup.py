@@ -91,6 +91,22 @@ del pw, pf
 nm = min(nq, 1 << 25)
 ms = timeit(lambda: N.check(L.cc_find_packed_dev(g._h, qw.data_ptr(), qf.data_ptr(), nm, res.data_ptr(), cb.CC_ALGO_MERGE, st)), reps=2, warm=1)
 print("packed sort-then-probe        q=%.2e  %8.3f ms  %.3g lookups/s  agrees=%s" % (nm, ms, nm / ms * 1e3, bool(torch.equal(res[:nm], ref[:nm]))), flush=True)
+# a batch that arrives in ascending order (the records of another graph): sorted-merge against the line index on the same batch
+ns = min(nq, 1 << 27)
+srt = synth.sort_unique_words([qw[:ns, w].contiguous() for w in range(s)])
+qs = torch.stack(srt, dim=1).contiguous()
+ns = qs.shape[0]
+for name, algo in (("line index", cb.CC_ALGO_AUTO), ("sorted-merge", cb.CC_ALGO_MERGE)):
+    ms = timeit(lambda: N.check(L.cc_find_packed_dev(g._h, qs.data_ptr(), None, ns, res.data_ptr(), algo, st)))
+    if algo == cb.CC_ALGO_AUTO:
+        keep = res[:ns].clone()
+    print("sorted batch, %-13s q=%.2e  %8.3f ms  %.3g lookups/s  agrees=%s" % (name, ns, ms, ns / ms * 1e3, bool(torch.equal(res[:ns], keep))), flush=True)
+for frac in (16, 256):
+    sub = qs[::frac].contiguous()
+    for name, algo in (("line index", cb.CC_ALGO_AUTO), ("sorted-merge", cb.CC_ALGO_MERGE)):
+        ms = timeit(lambda: N.check(L.cc_find_packed_dev(g._h, sub.data_ptr(), None, sub.shape[0], res.data_ptr(), algo, st)))
+        print("sorted batch 1/%d, %-13s q=%.2e  %8.3f ms  %.3g lookups/s" % (frac, name, sub.shape[0], ms, sub.shape[0] / ms * 1e3), flush=True)
+del srt, qs
 seq = synth.random_genome(9, 1 << 27, device="cuda")
 nwin = seq.numel() - k + 1
 r2 = torch.empty(nwin, dtype=torch.int64, device="cuda")
