@@ -981,7 +981,7 @@ constexpr uint32_t kOwnerLutBits = 10;         // owner lookup: 2^10 key prefixe
 
 // Dynamic shared memory of route_kernel: two staging areas of wire keys (each owner's run padded to its destination's
 // 16-byte phase).
-inline uint32_t route_stage_words(uint32_t tile_q, uint32_t kw, int nshards) { return (tile_q * kw + 8u * (uint32_t)nshards + 3u) & ~3u; }
+inline uint32_t route_stage_words(uint32_t tile_q, uint32_t kw, int nshards) { return (tile_q * kw + 3u * kw * (uint32_t)nshards + 3u) & ~3u; }   // + up to 3 pad keys per owner
 inline size_t route_smem_bytes(uint32_t tile_q, uint32_t kw, int nshards, int depth) {
     return (size_t)depth * route_stage_words(tile_q, kw, nshards) * 4u;     // `depth` staging areas: tiles' runs leave while the next are built
 }
@@ -1092,7 +1092,10 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
         if (threadIdx.x >= 64 && threadIdx.x < 64u + (uint32_t)nshards) {
             const uint32_t o = threadIdx.x - 64;
             const uint32_t cnt = hist[o];
-            const unsigned long long b0 = cnt ? atomicAdd(&cursors[o], (unsigned long long)cnt) : 0ull;
+            // space is reserved in multiples of 4 keys: every run then starts AND ends on a 16-byte boundary of the owner's inbox
+            // (4 keys = KW 16-byte units) and leaves as one bulk copy; the up to 3 pad slots hold zero keys that the owner searches
+            // and nobody reads back (4-byte stores for ragged run ends doubled the number of NVLink packets)
+            const unsigned long long b0 = cnt ? atomicAdd(&cursors[o], (unsigned long long)((cnt + 3u) & ~3u)) : 0ull;
             base[o] = b0;
             rs.tile_base[tile * nshards + o] = (uint32_t)b0;
             rs.tile_cnt[tile * nshards + o] = cnt;
@@ -1107,22 +1110,23 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
             if (lane == 0) loc[nshards] = tot;
         }
         __syncthreads();
-        // staging layout: every owner's run starts in a fresh 16-byte slot, at the 16-byte phase of its destination
+        // staging layout: the owners' runs back to back, each padded to a multiple of 4 keys (16-byte aligned on both sides, in
+        // shared memory and in the destination: rank * cap + base is a multiple of 4 keys)
         if (threadIdx.x < 32) {
-            uint32_t len[2], phase[2], keepw[2];
+            uint32_t len[2], keepw[2];
             uint64_t dw[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const uint32_t o = 2 * lane + e;
-                len[e] = 0; phase[e] = 0; keepw[e] = 0; dw[e] = 0;
+                len[e] = 0; keepw[e] = 0; dw[e] = 0;
                 if (o < (uint32_t)nshards) {
                     const uint64_t b0 = base[o];
+                    const uint32_t padded = (hist[o] + 3u) & ~3u;
                     dw[e] = ((uint64_t)my_rank * cap + b0) * KW;                    // destination word index in the owner's inbox
                     // a segment holds `cap` keys; keys beyond it are dropped here and reported through sent[o] > cap
-                    const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)hist[o], (unsigned long long)(cap - b0));
-                    phase[e] = (uint32_t)(dw[e] & 3u);
+                    const uint32_t keep = b0 >= cap ? 0u : (uint32_t)min((unsigned long long)padded, (unsigned long long)(cap - b0));
                     keepw[e] = keep * KW;
-                    len[e] = (phase[e] + hist[o] * KW + 3u) & ~3u;                  // slots taken, in words
+                    len[e] = padded * KW;
                 }
             }
             uint32_t p[2], tot;
@@ -1131,9 +1135,10 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
             for (int e = 0; e < 2; ++e) {
                 const uint32_t o = 2 * lane + e;
                 if (o < (uint32_t)nshards) {
-                    locw[o] = p[e] + phase[e];
-                    endw[o] = locw[o] + keepw[e];
-                    dptr[o] = static_cast<uint32_t *>(inbox.p[o]) + dw[e] - locw[o];
+                    locw[o] = p[e];
+                    endw[o] = p[e] + keepw[e];
+                    dptr[o] = static_cast<uint32_t *>(inbox.p[o]) + dw[e] - p[e];
+                    for (uint32_t w = p[e] + hist[o] * KW; w < p[e] + len[e]; ++w) stage[w] = 0u;      // the pad keys
                 }
             }
         }
@@ -1153,25 +1158,15 @@ __global__ void __launch_bounds__(BLOCK) route_kernel(const uint64_t *__restrict
         // the staged keys are read by the async proxy (bulk copies): order the generic-proxy writes before it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        // copy-out: one thread per owner hands the 16-byte-aligned body of its run to the bulk-copy (TMA) engine -- shared
-        // memory -> the owner's inbox, over NVLink when the owner is a peer -- and stores the ragged head / tail words (at most
-        // three each) itself.  The copies are asynchronous: the CTA goes on to the next tile while the link drains this one,
+        // copy-out: one thread per owner hands its run to the bulk-copy (TMA) engine -- shared memory -> the owner's inbox, over
+        // NVLink when the owner is a peer.  The copies are asynchronous: the CTA goes on to the next tile while the link drains this one,
         // and no warp sits in a backed-up store queue (plain stores from all warps left the SMs stalled on the link: the leg
         // took compute + transfer instead of max(compute, transfer)).
         if (threadIdx.x < (uint32_t)nshards) {
-            const uint32_t o = threadIdx.x, lo = locw[o], hi = endw[o];
-            if (hi > lo) {
-                const uint32_t blo = (lo + 3u) & ~3u, bhi = hi & ~3u;
-                uint32_t *d = dptr[o];
-                if (bhi > blo) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(d + blo), "r"(smem_u32(stage + blo)), "r"((bhi - blo) * 4u) : "memory");
-                    for (uint32_t w = lo; w < blo; ++w) d[w] = stage[w];
-                    for (uint32_t w = bhi; w < hi; ++w) d[w] = stage[w];
-                } else {
-                    for (uint32_t w = lo; w < hi; ++w) d[w] = stage[w];
-                }
-            }
+            const uint32_t o = threadIdx.x, lo = locw[o], hi = endw[o];             // both multiples of 4 words
+            if (hi > lo)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(dptr[o] + lo), "r"(smem_u32(stage + lo)), "r"((hi - lo) * 4u) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // one group per tile, empty or not: wait_group counts tiles
         }
     }

@@ -216,7 +216,8 @@ CC_API int cc_scatter_results_dev(int device, const int64_t *dev_values, const u
  * arrays of nshards DEVICE pointers (entry v = the [world][cap][kw] / [world] block of owner v on its rank); peer_res is a
  * HOST array of nshards DEVICE pointers (entry v = the [cap] result segment (owner v, source = this rank) on owner v's rank).  With cap >= the batch size no segment can
  * overflow; with a smaller cap the caller must check sent[v] <= cap after the batch (keys beyond cap are dropped and
- * their queries report -1). */
+ * their queries report -1).  Segment space is reserved in multiples of 4 keys per tile and owner (runs leave as 16-byte aligned bulk
+ * copies); the pad slots hold zero keys, are counted in sent[] / counts_in and are never read back. */
 CC_API int cc_route_state_bytes(uint64_t max_queries, int nshards, uint64_t *out_bytes);
 CC_API int cc_route_queries_dev(int device, const uint64_t *dev_words, const uint8_t *dev_flags, uint64_t nq, uint32_t k,
                                 const uint64_t *dev_splitters, int nshards, int my_rank, uint64_t cap,

@@ -526,7 +526,8 @@ def test_routed_lookup_emulated_ranks(world, k, vsub):
     for r in range(world):
         want = og.find_batch(qs[r][0].numpy())
         assert (qs[r][3].cpu().numpy() == want).all(), r
-        assert int(rls[r].sent[:world * vsub].sum()) == int((qs[r][2] == 0).sum())
+        routed, valid = int(rls[r].sent[:world * vsub].sum()), int((qs[r][2] == 0).sum())
+        assert valid <= routed <= valid + 3 * world * vsub * (nq_per[r] // 1024 + 1)      # runs are padded to multiples of 4 keys
     # a second batch through the same buffers (stale segment contents must not leak)
     for r in range(world):
         rls[r].route(qs[r][1][:100], qs[r][2][:100])
@@ -578,7 +579,8 @@ def test_routed_lookup_reports_segment_overflow():
     with pytest.raises(OverflowError):
         rls[0].check_overflow()
     got = out[:skew.shape[0]].cpu().numpy()
-    assert (got >= 0).sum() == cap and ((got >= 0) | (got == -1)).all()
+    # the segment holds `cap` slots; a few of them are the pad keys of the runs (multiples of 4 keys per tile and owner)
+    assert cap - 3 * (nq // 1024 + 1) <= (got >= 0).sum() <= cap and ((got >= 0) | (got == -1)).all()
     for g in shards:
         g.dispose()
     whole.dispose()
