@@ -602,7 +602,22 @@ def bench_lookup(args, env):
         del pw, pf
         nm = min(nq, 1 << 25)
         ms = env.timeit(lambda: N.check(L.cc_find_packed_dev(g._h, qwords.data_ptr(), qflags.data_ptr(), nm, res.data_ptr(), cb.CC_ALGO_MERGE, stream)), steps=2, warm=1)
-        out["packed_sort_then_probe_lookups_per_s"] = nm / (ms / 1000.0)
+        out["packed_merge_path_unsorted_batch_lookups_per_s"] = nm / (ms / 1000.0)      # CC_ALGO_MERGE: radix sort + merge-path + un-permute
+        # the same mode on a batch that arrives in key order (the case a merge is made for), beside the line index on that batch
+        cw = qwords[:nm][qflags[:nm] == 0]                         # packable queries only: the words of a flagged query are not a key
+        ns = cw.shape[0]
+        o1 = torch.sort(cw[:, S_WORDS - 1] ^ (-(1 << 63)), stable=True).indices       # unsigned order, least significant word first
+        for wcol in range(S_WORDS - 2, -1, -1):
+            o1 = o1[torch.sort(cw[:, wcol][o1] ^ (-(1 << 63)), stable=True).indices]
+        sw, sf = cw[o1].contiguous(), torch.zeros(ns, dtype=torch.uint8, device=dev)
+        del o1, cw
+        rm, ra = torch.empty(ns, dtype=torch.int64, device=dev), torch.empty(ns, dtype=torch.int64, device=dev)
+        ms = env.timeit(lambda: N.check(L.cc_find_packed_dev(g._h, sw.data_ptr(), sf.data_ptr(), ns, rm.data_ptr(), cb.CC_ALGO_MERGE, stream)), steps=3, warm=1)
+        out["packed_merge_path_sorted_batch_lookups_per_s"] = ns / (ms / 1000.0)
+        ms = env.timeit(lambda: N.check(L.cc_find_packed_dev(g._h, sw.data_ptr(), sf.data_ptr(), ns, ra.data_ptr(), cb.CC_ALGO_AUTO, stream)), steps=3, warm=1)
+        out["packed_line_index_sorted_batch_lookups_per_s"] = ns / (ms / 1000.0)
+        out["parity"]["merge_path_equals_line_index_on"] = ns if bool(torch.equal(rm, ra)) else 0
+        del sw, sf, rm, ra
         # ---- e2e through the host-buffer entry point: pinned host ASCII in, host indices out
         ne = min(n_ascii, 1 << 25)
         h_in = torch.empty((ne, K), dtype=torch.uint8, pin_memory=True)
@@ -988,18 +1003,26 @@ def bench_composite(args, env):
     torch.cuda.empty_cache()
     try:
         def gpu_run():
+            t = [time.perf_counter()]
             g = cb.CortexGraph(path, device=env.local_rank)
+            t.append(time.perf_counter())
             cnt = g.writeRois(0, [1, 2, 3], roi_path)
+            t.append(time.perf_counter())
             hits = 0
             for sq in contigs:
                 hits += int((g.findWindows(sq) >= 0).sum())
+            t.append(time.perf_counter())
             g.dispose()
-            return cnt, hits
+            t.append(time.perf_counter())
+            return cnt, hits, [b - a for a, b in zip(t[:-1], t[1:])]
 
         gpu_run()
-        t0 = time.perf_counter()
-        cnt, hits = gpu_run()
-        gpu_s = time.perf_counter() - t0
+        runs = []
+        for _ in range(3):          # wall-clock with file I/O inside: report the median of three and list all of them
+            cnt, hits, phases = gpu_run()
+            runs.append((sum(phases), phases))
+        runs.sort(key=lambda r: r[0])
+        gpu_s, phases = runs[1]
         with open(roi_path, "rb") as f:
             roi_bytes = f.read()
         # the CPU port: same steps; the lookups on a bounded sample of the windows, scaled
@@ -1020,7 +1043,8 @@ def bench_composite(args, env):
         g.dispose()
         return {"workload": "open %d-record .ctx (%.2f GB, /dev/shm) -> FindROIs to a file -> findRecord for all %d windows of %d contigs; graph resident across calls"
                             % (n, len(image) / 1e9, windows, ncontig),
-                "gpu_seconds": gpu_s, "cpu_port_seconds": cpu_scan_s + cpu_find_s, "cpu_port_scan_seconds": cpu_scan_s,
+                "gpu_seconds": gpu_s, "gpu_seconds_runs": [r[0] for r in runs],
+                "gpu_phase_seconds": dict(zip(("open", "find_rois_to_file", "find_windows", "dispose"), phases)), "cpu_port_seconds": cpu_scan_s + cpu_find_s, "cpu_port_scan_seconds": cpu_scan_s,
                 "cpu_port_lookup_seconds_extrapolated": cpu_find_s, "cpu_port_threads": threads, "speedup": (cpu_scan_s + cpu_find_s) / gpu_s,
                 "novel_records": cnt, "window_hits": hits,
                 "parity": {"roi_file_equals_oracle": bool(cnt == ocnt and roi_bytes == orc.roi_header(K, S_WORDS, "child") + o_rec.tobytes()),
