@@ -379,6 +379,7 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "index_fill_pct")) o.index_fill_pct = (int)value;
     else if (!strcmp(name, "find_bins_smem")) o.find_bins_smem = (int)value;
     else if (!strcmp(name, "rows_fused")) o.rows_fused = (int)value;
+    else if (!strcmp(name, "rows_warp")) o.rows_warp = (int)value;
     else if (!strcmp(name, "rows_rpt2_max_k")) o.rows_rpt2_max_k = (int)value;
     else if (!strcmp(name, "route_blocks_per_sm")) o.route_blocks_per_sm = (int)value;
     else if (!strcmp(name, "route_stage_depth")) o.route_stage_depth = (int)value;

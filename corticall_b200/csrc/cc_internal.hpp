@@ -36,6 +36,7 @@ struct Options {
     int rows_rpt2_max_k = 32;    // cc_pack_kmers: two rows per thread (512-row tiles) up to this k, else one
     int lookup_l2_hints = -1;    // line loads: -1 = auto (plain up to 1 GB of lines, evict-first beyond), 0 plain, 1 evict-first, 2 evict-normal, 3 evict-last
     int find_bins_smem = 1;      // packed / routed search: stage the bin table in shared memory
+    int rows_warp = 2;           // cc_pack_kmers on independent rows: 2 / 3 = warp-autonomous kernel with that many raw buffers per warp, 0 = CTA tiles
     int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
     int route_stage_depth = 2;            // staging areas per route CTA (2..4): tiles whose bulk copies may still be reading shared memory
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1

@@ -130,6 +130,30 @@ __device__ __forceinline__ bool any_bits(const uint32_t *w, uint32_t P, uint32_t
 
 __device__ __forceinline__ uint64_t spread_bits(uint32_t x);
 
+// rc < fw for the canonical choice, as the borrow of the 64*S-bit subtraction rc - fw: one subtract-with-carry chain
+// instead of a compare / branch ladder per word (words_less costs ~27 instructions at S = 2, this 5).
+template <int S>
+__device__ __forceinline__ bool less_by_borrow(const uint64_t (&a)[S], const uint64_t (&b)[S]) {
+    uint64_t r;
+    if constexpr (S == 1) {
+        return a[0] < b[0];
+    } else if constexpr (S == 2) {
+        asm("{\n .reg .u64 t;\n sub.cc.u64 t, %1, %3;\n subc.cc.u64 t, %2, %4;\n subc.u64 %0, 0, 0;\n}"
+            : "=l"(r) : "l"(a[1]), "l"(a[0]), "l"(b[1]), "l"(b[0]));
+        return r != 0;
+    } else if constexpr (S == 3) {
+        asm("{\n .reg .u64 t;\n sub.cc.u64 t, %1, %4;\n subc.cc.u64 t, %2, %5;\n subc.cc.u64 t, %3, %6;\n subc.u64 %0, 0, 0;\n}"
+            : "=l"(r) : "l"(a[2]), "l"(a[1]), "l"(a[0]), "l"(b[2]), "l"(b[1]), "l"(b[0]));
+        return r != 0;
+    } else if constexpr (S == 4) {
+        asm("{\n .reg .u64 t;\n sub.cc.u64 t, %1, %5;\n subc.cc.u64 t, %2, %6;\n subc.cc.u64 t, %3, %7;\n subc.cc.u64 t, %4, %8;\n subc.u64 %0, 0, 0;\n}"
+            : "=l"(r) : "l"(a[3]), "l"(a[2]), "l"(a[1]), "l"(a[0]), "l"(b[3]), "l"(b[2]), "l"(b[1]), "l"(b[0]));
+        return r != 0;
+    } else {
+        return words_less<S>(a, b);
+    }
+}
+
 // Canonical packed k-mer of the window starting at tile byte `start`.  Returns flags
 // (bit0 flipped, bit1 not ACGTacgt, bit2 has lower case); words zeroed when bit1.
 template <int S>
@@ -151,7 +175,7 @@ __device__ __forceinline__ uint32_t window_canonical(const SeqTile &t, uint32_t 
     const uint32_t top_bits = 2u * k - 64u * (S - 1);
     if (top_bits < 64) fw[0] &= (1ull << top_bits) - 1ull;
     revcomp_words<S>(fw, rc, k);
-    bool flip = words_less<S>(rc, fw);
+    bool flip = less_by_borrow<S>(rc, fw);
     uint32_t flags = 0;
     if (dirty) {
         // Mixed / lower case (soft-masked genomes are half lower case): the reference compares ASCII bytes, seq[i] against
@@ -685,7 +709,7 @@ __device__ __forceinline__ uint32_t row_canonical_warp(const uint8_t *a, uint32_
         fw[i] = v;
     }
     revcomp_words<S>(fw, rc, k);
-    bool flip = words_less<S>(rc, fw);
+    bool flip = less_by_borrow<S>(rc, fw);
     uint32_t flags = 0;
     if (low) {                                                // mixed / lower case: ASCII bytes decide, not 2-bit codes
         flags |= 4u;
@@ -835,7 +859,7 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
                 }
                 if (top_bits < 64) fw[0] &= (1ull << top_bits) - 1ull;
                 revcomp_words<S>(fw, rc, k);
-                const bool flip = words_less<S>(rc, fw);
+                const bool flip = less_by_borrow<S>(rc, fw);
 #pragma unroll
                 for (int w = 0; w < S; ++w) q[h][w] = flip ? rc[w] : fw[w];
                 flags[h] = flip ? 1u : 0u;
@@ -861,6 +885,188 @@ __global__ void __launch_bounds__(kBlock, (FIND && S <= 2) ? 3 : 1) rows_kernel(
                 out_flags[row] = (uint8_t)flags[h];
             }
         }
+    }
+}
+
+// rows_warp_kernel: the pack-only form of rows_kernel with WARPS as the unit instead of CTAs.  A warp owns 32 consecutive
+// rows: lane 0 fetches their bytes with one bulk copy into the warp's private ring (NRAW buffers, one mbarrier each), the
+// warp converts its ~32k/16 chunks (three rounds at k = 47) into its private code stream, and lane r cuts row r out of it.
+// Nothing is shared between warps, so there is no CTA barrier in the loop: rows_kernel lost 36 % of its stall samples at
+// the one __syncthreads per 256-row tile (profiles/r1_rows_kernel_hotspots.txt).  Suspect rows are a 32-bit mask in a
+// register (REDUX over the lanes' chunk findings) instead of shared-memory atomics.  Validity costs 3 instructions per
+// 4 bases here (codes_good_4) instead of the 8 of rebuilding the letters with PRMT; the per-tile bookkeeping runs on
+// pointers advanced by a constant and on 32-bit shared addresses computed once.
+inline size_t rows_warp_smem_bytes(uint32_t k, uint32_t nraw) {
+    return (size_t)(kBlock / 32) * (nraw * (size_t)rows_tile_bytes(32, k) + (size_t)rows_stream_words(32, k) * 4u);
+}
+
+// Four bases -> byte 3 = c0 | c1<<2 | c2<<4 | c3<<6 (first base lowest: the warp kernel's stream is little-endian), and
+// `good` keeps bit 4 of every byte set only while the byte's low five bits are those of an upper-case A, C, G or T:
+// (b2 b1 b0) in {001, 011, 111, 100} and b4 == !b0 (T is the one letter with b0 = 0, and the one with b4 = 1).  Bits 7, 6,
+// 5, 3 are checked once per 16 bytes by the caller.  Written with LEFT shifts only, and those as multiplications by
+// factors the compiler cannot see (kernel arguments): the integer ALU pipe (LOP3 / SHF / PRMT, one warp instruction per
+// two cycles) is what limits this kernel, the FMA pipe (IMAD) is idle -- 5 IMAD + 3 LOP3 per four bases.
+struct RowsMul { uint32_t m2, m4, m8, m16, pack; };
+constexpr RowsMul kRowsMul{2u, 4u, 8u, 16u, 0x00410410u};
+__device__ __forceinline__ uint32_t codes_good_4(uint32_t w, uint32_t &good, const RowsMul &mu) {
+    const uint32_t l1 = w * mu.m2, l2 = w * mu.m4, l3 = w * mu.m8, l4 = w * mu.m16;
+    const uint32_t h = (l4 & (l3 | ~l2)) | (~l4 & ~l3 & l2);            // bit 4: b0 (b1 | !b2) | !b0 !b1 b2
+    good &= h & (w ^ l4);
+    return ((l1 ^ w) & 0x0c0c0c0cu) * mu.pack;                           // codes (b2^b3, b1^b2) at bits 3:2 of every byte
+}
+
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int S, int KW, bool FIND, int NRAW>
+__global__ void __launch_bounds__(kBlock) rows_warp_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
+                                                           uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags, const RowsMul mu,
+                                                           IndexView ix, int64_t *__restrict__ out_index) {
+    constexpr uint32_t kWarps = kBlock / 32;
+    extern __shared__ __align__(128) uint8_t rows_smem[];
+    __shared__ __align__(8) uint64_t full[kWarps][NRAW];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t raw_cap = rows_tile_bytes(32, k), stream_cap = rows_stream_words(32, k);
+    uint8_t *const raw0 = rows_smem + (size_t)warp * (NRAW * raw_cap + stream_cap * 4u);
+    uint32_t *const stream = reinterpret_cast<uint32_t *>(raw0 + NRAW * raw_cap);
+    const uint32_t raw_s = smem_u32(raw0), bar_s = smem_u32(&full[warp][0]);
+    const uint64_t ntiles = (nq + 31u) / 32u, last = ntiles - 1;
+    const uint64_t gw = (uint64_t)blockIdx.x * kWarps + warp, nw = (uint64_t)gridDim.x * kWarps;
+    const uint64_t step = nw * 32u * k;                             // bytes between consecutive tiles of this warp
+    const uint32_t tail_rows = (uint32_t)(nq - last * 32u);
+    const uint32_t top_bits = 2u * k - 64u * (S - 1);
+    const uint64_t policy = make_evict_first_policy();
+    const uint64_t pol = make_line_policy(FIND ? ix.hints : 0u);
+
+    auto issue = [&](const uint8_t *src, uint32_t rows, uint32_t buf) {
+        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint32_t bytes = (off + rows * k + 15u) & ~15u;
+        const uint32_t bar = bar_s + 8u * buf;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(raw_s + buf * raw_cap), "l"(src - off), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+    };
+
+    if (lane == 0) {
+        for (uint32_t b = 0; b < NRAW; ++b) mbar_init(&full[warp][b], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint8_t *src = kmers + gw * 32u * k;
+    if (lane == 0) {
+#pragma unroll
+        for (uint32_t b = 0; b < NRAW; ++b) {
+            const uint64_t t = gw + b * nw;
+            if (t < ntiles) issue(src + b * step, t == last ? tail_rows : 32u, b);
+        }
+    }
+    uint32_t rb = 0, par = 0;
+    for (uint64_t tile = gw; tile < ntiles; tile += nw, src += step) {
+        const uint32_t rows = tile == last ? tail_rows : 32u;
+        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint32_t nbytes = rows * k;
+        const uint32_t nchunks = (off + nbytes + 15u) >> 4;
+        if (!mbar_try_wait_s(bar_s + 8u * rb, par)) mbar_wait(&full[warp][rb], par, nullptr, DEV_TIMEOUT_FULL);
+        // ---- phase 1: the warp's 16-byte chunks -> code words
+        const uint8_t *const rawb = raw0 + rb * raw_cap;
+        const uint4 *raw = reinterpret_cast<const uint4 *>(rawb);
+        uint32_t sus = 0;
+        for (uint32_t j = lane; j < nchunks; j += 32u) {
+            const uint4 v = raw[j];
+            uint32_t good = 0xffffffffu;
+            const uint32_t m0 = codes_good_4(v.x, good, mu), m1 = codes_good_4(v.y, good, mu);
+            const uint32_t m2 = codes_good_4(v.z, good, mu), m3 = codes_good_4(v.w, good, mu);
+            const uint32_t lo = __byte_perm(m0, m1, 0x7373u), hi = __byte_perm(m2, m3, 0x7373u);
+            stream[j] = __byte_perm(lo, hi, 0x5410u);            // base i of the chunk at bits 2i+1:2i
+            // bits 7, 5, 3 clear (5 = lower case) and bit 6 set in all 16 bytes; the low bits as collected in `good`
+            const uint32_t diff = ((v.x | v.y | v.z | v.w) & 0xa8a8a8a8u) | (~(v.x & v.y & v.z & v.w) & 0x40404040u) | (~good & 0x10101010u);
+            if (diff) {                                          // rare: every row this chunk overlaps is suspect
+                const int32_t b_lo = max((int32_t)(16u * j) - (int32_t)off, 0);
+                const int32_t b_hi = min((int32_t)(16u * j + 16u) - (int32_t)off, (int32_t)nbytes);
+                if (b_lo < b_hi) {
+                    const uint32_t r0 = (uint32_t)b_lo / k, r1 = (uint32_t)(b_hi - 1) / k;
+                    sus |= ((2u << r1) - 1u) & ~((1u << r0) - 1u);
+                }
+            }
+        }
+        if (lane < 3) stream[nchunks + lane] = 0;
+        sus = __reduce_or_sync(0xffffffffu, sus);
+        __syncwarp();                                            // stream complete
+        // ---- phase 2: lane r = row r
+        uint64_t q[S];
+        uint32_t flags = 2u;
+#pragma unroll
+        for (int w = 0; w < S; ++w) q[w] = 0;
+        for (uint32_t todo = sus; todo;) {                      // suspect rows (rare): exact, one at a time, by the whole warp
+            const uint32_t sl = __ffs(todo) - 1u;
+            todo &= todo - 1u;
+            uint64_t exact[S];
+            const uint32_t fl = row_canonical_warp<S>(rawb + off + sl * k, k, lane, exact);
+            if (lane == sl) {
+                flags = fl;
+#pragma unroll
+                for (int w = 0; w < S; ++w) q[w] = exact[w];
+            }
+        }
+        if (lane < rows) {
+            if (!((sus >> lane) & 1u)) {
+                // the row's 2k bits, first base lowest, cut out of the little-endian stream; E[j] = bits [64j, 64j + 64)
+                const uint32_t P = 2u * (off + lane * k), idx = P >> 5, sh = P & 31u;
+                uint64_t E[S];
+                uint32_t prev = stream[idx];
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const uint32_t w1 = stream[idx + 2 * j + 1], w2 = stream[idx + 2 * j + 2];
+                    E[j] = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(prev, w1, sh);
+                    prev = w2;
+                }
+                if (top_bits < 64) E[S - 1] &= (1ull << top_bits) - 1ull;
+                // reverse complement = the complement read in this order; forward = the 2-bit groups reversed, right-aligned
+                uint64_t fw[S], rc[S], t[S];
+#pragma unroll
+                for (int i = 0; i < S; ++i) { rc[i] = ~E[S - 1 - i]; t[i] = rev2(E[i]); }
+                if (top_bits < 64) rc[0] &= (1ull << top_bits) - 1ull;
+                const uint32_t rs = 64u * S - 2u * k;                           // 0..62, even
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    uint64_t v = t[i] >> rs;
+                    if (i > 0 && rs) v |= t[i - 1] << (64u - rs);
+                    fw[i] = v;
+                }
+                const bool flip = less_by_borrow<S>(rc, fw);
+#pragma unroll
+                for (int w = 0; w < S; ++w) q[w] = flip ? rc[w] : fw[w];
+                flags = flip ? 1u : 0u;
+            }
+            if (!FIND) {
+                const uint64_t row = tile * 32u + lane;
+                if (S == 2) reinterpret_cast<ulonglong2 *>(out_words)[row] = make_ulonglong2(q[0], q[1 % S]);
+                else {
+#pragma unroll
+                    for (int w = 0; w < S; ++w) out_words[row * S + w] = q[w];
+                }
+                out_flags[row] = (uint8_t)flags;
+            }
+        }
+        if (FIND) {                                              // warp-collective: every lane gets here
+            const int64_t res = lookup_lines_warp<S, KW>(ix, ix.bins, pol, q, lane < rows && (flags & 6u) == 0);
+            if (lane < rows) out_index[tile * 32u + lane] = res;
+        }
+        __syncwarp();                                            // every lane is done with this tile's bytes and stream
+        if (lane == 0) {
+            const uint64_t t = tile + NRAW * nw;
+            if (t < ntiles) issue(src + NRAW * step, t == last ? tail_rows : 32u, rb);
+        }
+        if (++rb == NRAW) { rb = 0; par ^= 1u; }
     }
 }
 
@@ -1661,7 +1867,15 @@ int launch_pack_windows(const uint8_t *dev_seq, uint64_t /*len*/, uint32_t k, ui
             CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, 2 * S_, false, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
             const int grid = resident_grid(rows_kernel<S_, 2 * S_, false, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), sm_count_now()); \
             rows_kernel<S_, 2 * S_, false, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags, none, nullptr); })
-        if (k <= (uint32_t)options().rows_rpt2_max_k) { CC_ROWS_PACK(2); } else { CC_ROWS_PACK(1); }
+        if (options().rows_warp) {
+#define CC_ROWS_WARP(NRAW_) CC_DISPATCH_S(s, {                                                                                 \
+                const size_t smem = rows_warp_smem_bytes(k, NRAW_);                                                                 \
+                CC_CUDA(cudaFuncSetAttribute(rows_warp_kernel<S_, 2 * S_, false, NRAW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                const int grid = resident_grid(rows_warp_kernel<S_, 2 * S_, false, NRAW_>, kBlock, smem, (nq + kBlock - 1) / kBlock, sm_count_now()); \
+                rows_warp_kernel<S_, 2 * S_, false, NRAW_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, dev_words, dev_flags, kRowsMul, none, nullptr); })
+            if (options().rows_warp == 3) { CC_ROWS_WARP(3); } else { CC_ROWS_WARP(2); }
+#undef CC_ROWS_WARP
+        } else if (k <= (uint32_t)options().rows_rpt2_max_k) { CC_ROWS_PACK(2); } else { CC_ROWS_PACK(1); }
 #undef CC_ROWS_PACK
         count_launch();
         CC_CUDA(cudaGetLastError());
@@ -1703,7 +1917,15 @@ int launch_find_seq(cc_graph *g, const uint8_t *dev_seq, uint64_t /*len*/, uint6
                 CC_CUDA(cudaFuncSetAttribute(rows_kernel<S_, KW_, true, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
                 const int grid = resident_grid(rows_kernel<S_, KW_, true, RPT_>, kBlock, smem, (nq + RPT_ * kBlock - 1) / (RPT_ * kBlock), g->sm_count); \
                 rows_kernel<S_, KW_, true, RPT_><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, nullptr, nullptr, ix, dev_index); })
-            if (k <= 64) { CC_ROWS_FIND(2); } else { CC_ROWS_FIND(1); }     // two lookups in flight per thread when the tile fits
+            if (options().rows_warp) {
+                // warp-autonomous form: no CTA barrier between the conversion and the searches, the occupancy hides the line loads
+                CC_DISPATCH_SKW(g->h.s, wire_words(k), {
+                    const size_t smem = rows_warp_smem_bytes(k, 2);
+                    CC_CUDA(cudaFuncSetAttribute(rows_warp_kernel<S_, KW_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const int grid = resident_grid(rows_warp_kernel<S_, KW_, true, 2>, kBlock, smem, (nq + kBlock - 1) / kBlock, g->sm_count);
+                    rows_warp_kernel<S_, KW_, true, 2><<<grid, kBlock, smem, st>>>(dev_seq, nq, k, nullptr, nullptr, kRowsMul, ix, dev_index);
+                });
+            } else if (k <= 64) { CC_ROWS_FIND(2); } else { CC_ROWS_FIND(1); }     // two lookups in flight per thread when the tile fits
 #undef CC_ROWS_FIND
             count_launch();
             CC_CUDA(cudaGetLastError());
