@@ -380,6 +380,9 @@ int cc_set_option(const char *name, int64_t value) {
     else if (!strcmp(name, "find_bins_smem")) o.find_bins_smem = (int)value;
     else if (!strcmp(name, "rows_fused")) o.rows_fused = (int)value;
     else if (!strcmp(name, "rows_warp")) o.rows_warp = (int)value;
+    else if (!strcmp(name, "covstats_fused")) o.covstats_fused = (int)value;
+    else if (!strcmp(name, "join_tiled")) o.join_tiled = (int)value;
+    else if (!strcmp(name, "join_tile_kb")) o.join_tile_kb = (int)value;
     else if (!strcmp(name, "rows_rpt2_max_k")) o.rows_rpt2_max_k = (int)value;
     else if (!strcmp(name, "route_blocks_per_sm")) o.route_blocks_per_sm = (int)value;
     else if (!strcmp(name, "route_stage_depth")) o.route_stage_depth = (int)value;
@@ -1095,8 +1098,9 @@ int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out) {
     for (int i = 1; i < ngraphs; ++i) {
         void *nb = nullptr;
         uint64_t nn = 0;
+        uint64_t *nk = nullptr;        // key column of the intermediate for the next union (written by the tiled emit pass)
         if (int rc = join_pair(body, keys, n, c, graphs[i]->dev_body, graphs[i]->index.keys, graphs[i]->h.num_records, graphs[i]->h.c, s,
-                               g->stream, &nb, &nn)) return rc;
+                               g->stream, &nb, &nn, i + 1 < ngraphs ? &nk : nullptr)) { if (nb) cudaFree(nb); if (nk) cudaFree(nk); return rc; }
         if (cur_body) cudaFree(cur_body);
         if (cur_keys) { cudaFree(cur_keys); cur_keys = nullptr; }
         cur_body = nb;
@@ -1104,17 +1108,22 @@ int cc_join(cc_graph *const *graphs, int ngraphs, cc_graph **out) {
         n = nn;
         c += graphs[i]->h.c;
         for (const ColorMeta &cm : graphs[i]->h.colors) g->h.colors.push_back(cm);
-        if (i + 1 < ngraphs) {         // key column of the intermediate for the next union
-            CC_CUDA(cudaMalloc(&cur_keys, std::max<uint64_t>(n * s, 2) * 8 + 64));
-            if (int rc = g->scan_ws.ensure(0, 0)) return rc;
-            if (int rc = launch_decode_columns(body, n, s, c, cur_keys, nullptr, nullptr, g->scan_ws, g->sm_count, g->stream)) return rc;
-            CC_CUDA(cudaStreamSynchronize(g->stream));
+        if (i + 1 < ngraphs) {
+            cur_keys = nk;
+            if (!cur_keys) {           // the untiled union does not produce it: decode it from the records
+                CC_CUDA(cudaMalloc(&cur_keys, std::max<uint64_t>(n * s, 2) * 8 + 64));
+                if (int rc = g->scan_ws.ensure(0, 0)) return rc;
+                if (int rc = launch_decode_columns(body, n, s, c, cur_keys, nullptr, nullptr, g->scan_ws, g->sm_count, g->stream)) return rc;
+                CC_CUDA(cudaStreamSynchronize(g->stream));
+            }
             keys = cur_keys;
         }
     }
     if (!cur_body) {                   // a single graph: copy it
         CC_CUDA(cudaMalloc(&cur_body, n * graphs[0]->h.record_size + 256));
-        CC_CUDA(cudaMemcpy(cur_body, body, n * graphs[0]->h.record_size, cudaMemcpyDeviceToDevice));
+        CC_CUDA(cudaMemcpyAsync(cur_body, body, n * graphs[0]->h.record_size, cudaMemcpyDeviceToDevice, g->stream));
+        CC_CUDA(cudaMemsetAsync(static_cast<uint8_t *>(cur_body) + n * graphs[0]->h.record_size, 0, 256, g->stream));
+        CC_CUDA(cudaStreamSynchronize(g->stream));
     }
     g->h.c = c;
     g->h.record_size = 8ull * s + 5ull * c;
@@ -1379,16 +1388,22 @@ int cc_cov_stats(cc_graph *g, int32_t child, const int32_t *parents, int nparent
     cudaStream_t st = g->stream;
     const uint64_t n = g->h.num_records;
     StreamBuf sb(st);
-    int32_t *cov = nullptr; uint32_t *dmask = nullptr;
-    if (int rc = CC_SB_ALLOC(sb, cov, n * g->h.c)) return rc;
+    uint32_t *dmask = nullptr;
     std::vector<uint32_t> mask = color_mask(g, parents, nparents);
     if (int rc = CC_SB_ALLOC(sb, dmask, mask.size())) return rc;
     CC_CUDA(cudaMemcpyAsync(dmask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, st));
-    if (int rc = g->scan_ws.ensure(0, 0)) return rc;
-    if (int rc = launch_decode_columns(g->dev_body, n, g->h.s, g->h.c, nullptr, cov, nullptr, g->scan_ws, g->sm_count, st)) return rc;
     std::vector<int32_t> hc;
     std::vector<long long> hn;
-    if (int rc = cov_stats(cov, n, g->h.c, child, dmask, g->sm_count, st, hc, hn)) return rc;
+    bool fell_back = !options().covstats_fused;
+    if (!fell_back)
+        if (int rc = cov_stats_fused(g->dev_body, n, g->h.s, g->h.c, child, dmask, g->sm_count, st, hc, hn, &fell_back)) return rc;
+    if (fell_back) {          // more huge coverages than the overflow list holds: decode the coverage matrix, sort, reduce by key
+        int32_t *cov = nullptr;
+        if (int rc = CC_SB_ALLOC(sb, cov, n * g->h.c)) return rc;
+        if (int rc = g->scan_ws.ensure(0, 0)) return rc;
+        if (int rc = launch_decode_columns(g->dev_body, n, g->h.s, g->h.c, nullptr, cov, nullptr, g->scan_ws, g->sm_count, st)) return rc;
+        if (int rc = cov_stats(cov, n, g->h.c, child, dmask, g->sm_count, st, hc, hn)) return rc;
+    }
     *out_n = hc.size();
     for (uint64_t i = 0; i < hc.size() && i < cap; ++i) {
         out_cov[i] = hc[i];

@@ -37,6 +37,9 @@ struct Options {
     int lookup_l2_hints = -1;    // line loads: -1 = auto (plain up to 1 GB of lines, evict-first beyond), 0 plain, 1 evict-first, 2 evict-normal, 3 evict-last
     int find_bins_smem = 1;      // packed / routed search: stage the bin table in shared memory
     int rows_warp = 2;           // cc_pack_kmers on independent rows: 2 / 3 = warp-autonomous kernel with that many raw buffers per warp, 0 = CTA tiles
+    int join_tiled = 1;          // Join / Remove: 1 = tiled union through shared memory, 0 = one global merge-path search per thread (round-1 form)
+    int join_tile_kb = 48;       // tiled union: shared-memory budget per CTA in KB for the key slices (decides the tile size: 2048 elements at k <= 64)
+    int covstats_fused = 1;      // CovStats: 1 = one histogram pass over the records, 0 = coverage matrix + radix sort + reduce by key (the fallback)
     int rows_fused = 1;          // ASCII query lists: 1 = pack + search in one kernel, 0 = pack, then search
     int route_stage_depth = 2;            // staging areas per route CTA (2..4): tiles whose bulk copies may still be reading shared memory
     int route_blocks_per_sm = 0;          // 0 = as many as fit; the overlapped pipeline uses 1
@@ -179,7 +182,7 @@ int launch_bucket_by_owner(const uint64_t *dev_words, const uint8_t *dev_flags, 
                            uint32_t *dev_slots, cudaStream_t st);
 int launch_scatter_results(const int64_t *dev_values, const uint32_t *dev_slots, uint64_t n, int64_t *dev_out, cudaStream_t st);
 int join_pair(const uint8_t *body_a, const uint64_t *keys_a, uint64_t na, uint32_t ca, const uint8_t *body_b, const uint64_t *keys_b,
-              uint64_t nb, uint32_t cb, uint32_t s, cudaStream_t st, void **out_body, uint64_t *out_n);
+              uint64_t nb, uint32_t cb, uint32_t s, cudaStream_t st, void **out_body, uint64_t *out_n, uint64_t **out_keys = nullptr);
 int sort_permutation(const uint64_t *dev_words, uint64_t n, uint32_t s, uint32_t k, cudaStream_t st, uint32_t **perm_out);
 int launch_gather_records(const uint8_t *body, const uint32_t *perm, uint64_t n, uint32_t S, uint8_t *out, cudaStream_t st);
 // prefilter.cu
@@ -194,6 +197,8 @@ int launch_shared_flags(const int64_t *idx, const uint8_t *graph_body, uint32_t 
 int select_flagged(const uint8_t *flags, uint64_t n, uint32_t **sel_out, uint64_t *m_out, cudaStream_t st);
 int launch_project_records(const uint8_t *body, uint32_t s, uint32_t c_in, const uint32_t *sel, uint64_t m, uint32_t c_out,
                            const uint8_t *flags, const int32_t *patch, uint32_t patch_color, uint8_t *out, int sm_count, cudaStream_t st);
+int cov_stats_fused(const uint8_t *body, uint64_t n, uint32_t s, uint32_t c, int32_t child, const uint32_t *dev_parent_mask, int sm_count,
+                    cudaStream_t st, std::vector<int32_t> &out_cov, std::vector<long long> &out_count, bool *fell_back);
 int cov_stats(const int32_t *cov, uint64_t n, uint32_t c, int32_t child, const uint32_t *dev_parent_mask, int sm_count, cudaStream_t st,
               std::vector<int32_t> &out_cov, std::vector<long long> &out_count);
 uint64_t route_state_size(uint64_t max_q, int nshards);

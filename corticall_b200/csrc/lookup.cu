@@ -928,7 +928,7 @@ __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
 }
 
 template <int S, int KW, bool FIND, int NRAW>
-__global__ void __launch_bounds__(kBlock) rows_warp_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
+__global__ void __launch_bounds__(kBlock, FIND ? 4 : 0) rows_warp_kernel(const uint8_t *__restrict__ kmers, uint64_t nq, uint32_t k,
                                                            uint64_t *__restrict__ out_words, uint8_t *__restrict__ out_flags, const RowsMul mu,
                                                            IndexView ix, int64_t *__restrict__ out_index) {
     constexpr uint32_t kWarps = kBlock / 32;

@@ -13,6 +13,8 @@
 // into a coalesced int32 coverage matrix (and the key column where lookups follow); the predicates below then run as
 // fully coalesced column kernels, the selection is an index list (cub::DeviceSelect, plumbing), and one gather kernel
 // writes the projected records.  The lookups inside FindShared / RecoverExcludedKmers are the K4 kernels of lookup.cu.
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_select.cuh>
@@ -118,6 +120,43 @@ __global__ void covstats_pairs_kernel(const int32_t *__restrict__ cov, uint64_t 
         key[i] = counts ? (uint32_t)row[child] : 0u;
         weight[i] = counts ? (long long)(np + nc) : 0ll;
     }
+}
+
+// CovStats as ONE pass over the record array: no coverage matrix, no sort.  Child coverages below kCovHistSmem go to a
+// per-CTA shared-memory histogram (flushed once), below kCovHistGlobal to a global table of 64-bit counters, anything
+// larger (never seen in a real graph; possible in a file) to a short overflow list the host aggregates.  Weights are
+// summed exactly; the shared counters are 32-bit and the launcher bounds what one CTA can add.
+constexpr uint32_t kCovHistSmem = 4096, kCovHistGlobal = 65536, kCovOverflowCap = 1u << 20;
+
+__global__ void __launch_bounds__(kPBlock) covstats_hist_kernel(const uint8_t *__restrict__ body, uint64_t n, uint32_t s, uint32_t c, uint32_t child,
+                                                                const uint32_t *__restrict__ parents, unsigned long long *__restrict__ hist_global,
+                                                                uint2 *__restrict__ overflow, unsigned int *__restrict__ overflow_n) {
+    __shared__ uint32_t hist[kCovHistSmem];
+    for (uint32_t b = threadIdx.x; b < kCovHistSmem; b += kPBlock) hist[b] = 0;
+    __syncthreads();
+    const uint32_t S = 8u * s + 5u * c;
+    for (uint64_t i = (uint64_t)blockIdx.x * kPBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kPBlock) {
+        const uint8_t *rec = body + i * S;
+        const int32_t cc_child = read_cov(rec, s, child);
+        if (cc_child <= 0) continue;
+        uint32_t np = 0, nc = 0;
+        for (uint32_t cc = 0; cc < c; ++cc) {
+            if (cc != child && read_cov(rec, s, cc) > 0) {
+                if (in_mask(parents, cc)) ++np; else ++nc;
+            }
+        }
+        if (np == 0 || nc == 0) continue;
+        const uint32_t w = np + nc, v = (uint32_t)cc_child;
+        if (v < kCovHistSmem) atomicAdd(&hist[v], w);
+        else if (v < kCovHistGlobal) atomicAdd(&hist_global[v], (unsigned long long)w);
+        else {
+            const unsigned int slot = atomicAdd(overflow_n, 1u);
+            if (slot < kCovOverflowCap) overflow[slot] = make_uint2(v, w);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < kCovHistSmem; b += kPBlock)
+        if (hist[b]) atomicAdd(&hist_global[b], (unsigned long long)hist[b]);
 }
 
 // Output record j = the first c_out colours of input record sel[j] (CortexGraphWriter.addRecord :106-138 writes
@@ -285,6 +324,57 @@ int cov_stats(const int32_t *cov, uint64_t n, uint32_t c, int32_t child, const u
         if (hk[i] == 0) continue;
         out_cov.push_back((int32_t)hk[i]);
         out_count.push_back(hs[i]);
+    }
+    return CC_OK;
+}
+
+// CovStats straight from the record array (covstats_hist_kernel).  *fell_back = true when the overflow list did not hold
+// every outlier (or the 32-bit shared counters could wrap): the caller then takes the sort-based path.
+int cov_stats_fused(const uint8_t *body, uint64_t n, uint32_t s, uint32_t c, int32_t child, const uint32_t *dev_parent_mask, int sm_count,
+                    cudaStream_t st, std::vector<int32_t> &out_cov, std::vector<long long> &out_count, bool *fell_back) {
+    out_cov.clear();
+    out_count.clear();
+    *fell_back = false;
+    if (n == 0) return CC_OK;
+    const int grid = grid_of(n, sm_count);
+    if (((n + (uint64_t)grid * kPBlock - 1) / ((uint64_t)grid * kPBlock)) * kPBlock * (uint64_t)c >= (1ull << 32)) { *fell_back = true; return CC_OK; }
+    unsigned long long *hist = nullptr;
+    uint2 *overflow = nullptr;
+    unsigned int *d_n = nullptr;
+    struct Free {
+        cudaStream_t st; unsigned long long *&h; uint2 *&o; unsigned int *&n;
+        ~Free() { cudaFreeAsync(h, st); cudaFreeAsync(o, st); cudaFreeAsync(n, st); }
+    } fr{st, hist, overflow, d_n};
+    CC_CUDA(cudaMallocAsync(&hist, kCovHistGlobal * sizeof(unsigned long long), st));
+    CC_CUDA(cudaMallocAsync(&overflow, (size_t)kCovOverflowCap * sizeof(uint2), st));
+    CC_CUDA(cudaMallocAsync(&d_n, sizeof(unsigned int), st));
+    CC_CUDA(cudaMemsetAsync(hist, 0, kCovHistGlobal * sizeof(unsigned long long), st));
+    CC_CUDA(cudaMemsetAsync(d_n, 0, sizeof(unsigned int), st));
+    covstats_hist_kernel<<<grid, kPBlock, 0, st>>>(body, n, s, c, (uint32_t)child, dev_parent_mask, hist, overflow, d_n);
+    count_launch();
+    CC_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> h(kCovHistGlobal);
+    unsigned int nover = 0;
+    CC_CUDA(cudaMemcpyAsync(h.data(), hist, kCovHistGlobal * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CC_CUDA(cudaMemcpyAsync(&nover, d_n, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CC_CUDA(cudaStreamSynchronize(st));
+    if (nover > kCovOverflowCap) { *fell_back = true; return CC_OK; }
+    for (uint32_t v = 1; v < kCovHistGlobal; ++v) {
+        if (h[v]) { out_cov.push_back((int32_t)v); out_count.push_back((long long)h[v]); }
+    }
+    if (nover) {
+        std::vector<uint2> ov(nover);
+        CC_CUDA(cudaMemcpyAsync(ov.data(), overflow, (size_t)nover * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaStreamSynchronize(st));
+        std::sort(ov.begin(), ov.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
+        for (size_t i = 0; i < ov.size();) {
+            size_t j = i;
+            long long sum = 0;
+            for (; j < ov.size() && ov[j].x == ov[i].x; ++j) sum += ov[j].y;
+            out_cov.push_back((int32_t)ov[i].x);
+            out_count.push_back(sum);
+            i = j;
+        }
     }
     return CC_OK;
 }

@@ -324,6 +324,9 @@ CC_API int cc_device_keys(cc_graph *g, const uint64_t **dev_keys, uint64_t *n);
  *   index:   "index_bits" (log2 of the number of bins, 0 = auto), "index_fill_pct" (average fill of a bucket line, default 50)
  *   lookups: "lookup_l2_hints" (line loads: -1 auto, 0 plain, 1 evict-first in L2, 2 evict-normal, 3 evict-last), "find_bins_smem" (1 = bin table staged in shared memory),
  *            "rows_fused" (ASCII lists: 1 = pack + search in one kernel), "rows_warp" (pack rows: 2 / 3 = warp-autonomous kernel with that many buffers per warp, 0 = CTA tiles), "rows_rpt2_max_k"
+ *   prefilters: "covstats_fused" (1 = CovStats as one histogram pass, 0 = coverage matrix + sort + reduce by key),
+ *            "join_tiled" (Join / Remove: 1 = tiled union through shared memory, 0 = one global merge-path search per thread),
+ *            "join_tile_kb" (shared-memory budget per CTA of the tiled union)
  *   routed:  "route_stage_depth" (2..4 staging areas per route CTA), "route_blocks_per_sm", "routed_search_blocks_per_sm", "gather_blocks_per_sm"
  * Unknown names fail with CC_ERR_ARG. */
 CC_API int cc_set_option(const char *name, int64_t value);

@@ -772,11 +772,15 @@ def test_line_index_on_clustered_keys(k):
 
 @pytest.mark.parametrize("k,colors,sizes", [(31, (1, 1), (5000, 7000)), (47, (1, 1, 1, 1), (20000, 30000, 25000, 9000)),
                                             (63, (2, 3), (4000, 4001)), (47, (4, 1), (50000, 3)), (31, (1, 2), (0, 500)),
-                                            (95, (1, 1, 1), (3000, 1, 2999))])
-def test_join_vs_oracle(tmp_path, k, colors, sizes):
+                                            (95, (1, 1, 1), (3000, 1, 2999)), (47, (21, 5), (3000, 2500)), (127, (1, 2, 1), (2000, 3000, 10)),
+                                            (31, (1, 1), (40000, 40000))])
+@pytest.mark.parametrize("tiled", [1, 0])
+def test_join_vs_oracle(tmp_path, k, colors, sizes, tiled):
     """cc_join / Join.execute against the oracle's union (CortexCollection.next semantics): overlapping key sets
-    (every graph draws from one pool so many k-mers are shared), colour remap, absent k-mers zero-filled, header."""
+    (every graph draws from one pool so many k-mers are shared), colour remap, absent k-mers zero-filled, header.
+    tiled = 1: the shared-memory tiled union; 0: the per-thread merge-path form it falls back to for very wide records."""
     from oracle import oracle_np as onp
+    N.set_option("join_tiled", tiled)
     pool = synth.random_canonical_keys(123 + k, int(max(sizes) * 1.5) + 10, k, "cpu")
     ctxs, graphs = [], []
     for gi, (c, n) in enumerate(zip(colors, sizes)):
@@ -793,7 +797,10 @@ def test_join_vs_oracle(tmp_path, k, colors, sizes):
         graphs.append(cb.CortexGraph(p))
     want = onp.join(ctxs)
     out = tmp_path / "joined.ctx"
-    n = cb.Join(graphs, out).execute()
+    try:
+        n = cb.Join(graphs, out).execute()
+    finally:
+        N.set_option("join_tiled", 1)
     got = out.read_bytes()
     hw = onp.parse_header(want)
     assert n == hw["num_records"]
@@ -972,14 +979,54 @@ def test_prefilters_vs_oracle(tmp_path, k, c, n):
 
     # CovStats
     import io
+    from corticall_b200 import _native as N
     for child_name, pnames in ((names[0], parents), (names[1], [names[0]]), (names[0], ["no-such-sample"])):
-        buf = io.StringIO()
-        rows = cb.CovStats(graph, child_name, pnames, buf).execute()
         ccol = graph.getColorForSampleName(child_name)
         want = onp.cov_stats(ctx, ccol, [graph.getColorForSampleName(p) for p in pnames])
-        assert rows == want and buf.getvalue() == "".join("%d\t%d\n" % r for r in want)
+        for fused in (1, 0):                     # the histogram pass, and the sort-based path it falls back to
+            N.set_option("covstats_fused", fused)
+            try:
+                buf = io.StringIO()
+                rows = cb.CovStats(graph, child_name, pnames, buf).execute()
+            finally:
+                N.set_option("covstats_fused", 1)
+            assert rows == want and buf.getvalue() == "".join("%d\t%d\n" % r for r in want), fused
     assert len(onp.cov_stats(ctx, 0, graph.getColorsForSampleNames(parents))) > 0 or c < 4
     roi.dispose(); graph.dispose()
+
+
+@pytest.mark.parametrize("k,c", [(47, 4), (31, 5)])
+def test_covstats_huge_coverages(k, c):
+    """CovStats is one histogram pass with three levels (shared memory < 4096, global table < 65536, overflow list beyond):
+    child coverages placed in every level, on and around the boundaries, still give the oracle's table."""
+    import io
+    from oracle import oracle_np as onp
+    n = 30_000
+    names = ["kid", "mom", "dad", "ref", "other"][:c]
+    ctx = bytearray(synth.make_ctx_file(77 + k, n, k, c, novel_permille=40, adv_period=53, names=names))
+    hdr = len(synth.header_bytes(k, c, names))
+    s_words = (k + 31) // 32
+    S = 8 * s_words + 5 * c
+    body = np.frombuffer(ctx, dtype=np.uint8, offset=hdr).reshape(n, S)
+    cov = body[:, 8 * s_words:8 * s_words + 4 * c].copy().view("<u4").reshape(n, c)
+    rng = np.random.default_rng(k)
+    special = np.array([4095, 4096, 4097, 65535, 65536, 65537, 1 << 20, (1 << 30) + 7, (1 << 31) - 1, 1 << 31, 0xFFFFFFFF, 5000, 5000, 70000, 70000, 70000],
+                       dtype=np.uint32)
+    rows = rng.choice(n, size=len(special) * 20, replace=False)
+    cov[rows, 0] = np.tile(special, 20)
+    cov[rows[::2], 1] = 3          # a parent ...
+    cov[rows[::3], c - 1] = 2      # ... and another sample for some of them
+    body[:, 8 * s_words:8 * s_words + 4 * c] = cov.astype("<u4").view(np.uint8).reshape(n, 4 * c)
+    ctx = bytes(ctx)
+    graph = cb.CortexGraph(ctx)
+    for child_name, pnames in (("kid", ["mom", "dad"][:max(1, c - 3)]), ("mom", ["kid"])):
+        buf = io.StringIO()
+        got = cb.CovStats(graph, child_name, pnames, buf).execute()
+        want = onp.cov_stats(ctx, graph.getColorForSampleName(child_name), [graph.getColorForSampleName(p) for p in pnames])
+        assert got == want
+        if child_name == "kid":
+            assert any(v >= 65536 for v, _ in want) and any(4096 <= v < 65536 for v, _ in want)
+    graph.dispose()
 
 
 def test_prefilters_empty_graph(tmp_path):
