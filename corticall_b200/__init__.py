@@ -8,9 +8,9 @@ from ._native import (CC_ALGO_AUTO, CC_ALGO_BSEARCH, CC_ALGO_MERGE, CortexJDKExc
                       set_option)
 from .host.commands import (CallHelpers, CortexCollection, CortexVertex, CovStats, FindLowCoverage, FindROIs, FindShared, Join,
                             RecoverExcludedKmers, Remove, Sort)
-from .host.cortex import CortexColor, CortexGraph, CortexHeader, CortexRecord, ShardedCortexGraph, packCanonical
+from .host.cortex import CortexColor, CortexGraph, CortexHeader, CortexMap, CortexRecord, ShardedCortexGraph, packCanonical
 from .host.kmer import CanonicalKmer, CortexBinaryKmer, CortexByteKmer, SequenceUtils
 
-__all__ = ["CortexGraph", "ShardedCortexGraph", "CortexRecord", "CortexHeader", "CortexColor", "CanonicalKmer", "CortexByteKmer",
+__all__ = ["CortexGraph", "ShardedCortexGraph", "CortexMap", "CortexRecord", "CortexHeader", "CortexColor", "CanonicalKmer", "CortexByteKmer",
            "CortexBinaryKmer", "SequenceUtils", "FindROIs", "Join", "Remove", "Sort", "FindLowCoverage", "FindShared", "RecoverExcludedKmers", "CovStats", "CortexCollection", "CallHelpers", "CortexVertex", "CortexJDKException", "packCanonical", "lib", "launch_count",
            "set_option", "device_count", "CC_ALGO_AUTO", "CC_ALGO_BSEARCH", "CC_ALGO_MERGE"]

@@ -570,6 +570,37 @@ class CortexGraph:
     __str__ = toString
 
 
+class CortexMap:
+    """CortexMap (S/utils/io/graph/cortex/CortexMap.java:14-160).  The reference pre-loads every record into a
+    HashMap<CortexBinaryKmer, CortexRecord> (:22-36) and answers findRecord from it; the key of a query is
+    CortexBinaryKmer(byte[]) (:77-99), which -- unlike CortexGraph.findRecord -- first takes the alphanumerically lowest
+    orientation (CortexBinaryKmer.java:15-17) and compares packed words, not bytes.  Here the graph's device-resident index
+    is the map: the packed key goes to cc_find_packed.  Everything else delegates to the wrapped graph, as in the reference.
+    (A HashMap does not need sorted input; the index does: an unsorted file raises CC_ERR_UNSORTED -- Sort repairs it.)"""
+
+    def __init__(self, cortexFile, device: int = 0):
+        self.graph = cortexFile if isinstance(cortexFile, CortexGraph) else CortexGraph(cortexFile, device=device)
+
+    def _get(self, cbk: CortexBinaryKmer):
+        if len(cbk.binaryKmer) != self.graph.getKmerBits():      # a long[] of another length equals no key of the map
+            return None
+        from .kmer import _swap64
+        words = np.array([_swap64(int(x) & 0xFFFFFFFFFFFFFFFF) for x in cbk.binaryKmer], dtype=np.uint64)
+        idx = int(self.graph.findPacked(words.reshape(1, -1))[0])
+        return self.graph.getRecord(idx) if idx >= 0 else None
+
+    def findRecord(self, kmer):                                         # :77-99
+        if isinstance(kmer, CortexBinaryKmer):
+            return self._get(kmer)
+        return self._get(CortexBinaryKmer(self.graph._as_kmer_bytes(kmer)))
+
+    def __getattr__(self, name):                                        # position / iterator / getRecord / header getters: :38-75,101-160
+        return getattr(self.graph, name)
+
+    def __iter__(self):
+        return iter(self.graph)
+
+
 class ShardedCortexGraph:
     """One graph over several GPUs of this process (cc_open_sharded): the record array is cut into k-mer-range shards, one
     per entry of `devices`; lookups are routed to the owning shard over peer memory and the novelty scan returns one

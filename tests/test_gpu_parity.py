@@ -83,6 +83,33 @@ def test_find_non_existent_record(graph, kats):                          # testF
     assert graph.findRecord("A" * 30) is None
 
 
+def test_cortex_map(graph, fixture_ctx, kats):                           # CortexMap.java:14-160
+    """CortexMap = the reference's HashMap<CortexBinaryKmer, CortexRecord> view: built here the way the reference builds it
+    (a dict over the iterated records) and compared with the mirror, whose map is the device index."""
+    want = {cr.getCortexBinaryKmer(): cr for cr in cb.CortexGraph(fixture_ctx)}
+    m = cb.CortexMap(fixture_ctx)
+    assert m.getNumRecords() == len(want) and m.getKmerSize() == 31 and sum(1 for _ in m) == len(want)
+    queries = []
+    for row in kats["fixture_records"]:
+        rc = cb.SequenceUtils.reverseComplement(row["kmer"])
+        rc = rc.decode() if isinstance(rc, bytes) else rc
+        queries += [row["kmer"], rc, row["kmer"].lower(), rc[:15] + rc[15:].lower(), row["kmer"][1:], "A" + row["kmer"][:-1]]
+    queries += [kats["missing_query"].replace("N", "A"), "A" * 31, "T" * 31, "ACGT" * 7 + "ACG", "C" * 33]
+    hits = 0
+    for q in queries:
+        key = cb.CortexBinaryKmer(q)
+        got = m.findRecord(q)
+        assert got == want.get(key), q
+        assert m.findRecord(q.encode()) == got and m.findRecord(key) == got
+        hits += got is not None
+    assert hits >= 2 * len(kats["fixture_records"])
+    cr = graph.getRecord(7)
+    assert m.findRecord(cb.CanonicalKmer(cr.getKmerAsString())) == cr and m.findRecord(cb.CortexByteKmer(cr.getKmerAsBytes())) == cr
+    with pytest.raises(RuntimeError):                                    # charToBinaryNucleotide: 'N' is not a valid nucleotide
+        m.findRecord(kats["missing_query"])
+    m.graph.dispose()
+
+
 def test_all_fasta_windows_hit(graph, fixture_ctx, fixture_fa):          # BASELINE.json configs[0]
     og = orc.Graph(fixture_ctx)
     seen = set()

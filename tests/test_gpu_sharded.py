@@ -132,6 +132,13 @@ def test_sharded_rejects_bad_input(tmp_path):
     cnt, _, _ = sh.findNovel(0, [1])
     assert cnt == g.findNovel(0, [1])[0]
     sh.dispose(); g.dispose()
+    # the routed kernels keep their owner tables in shared memory: at most 64 owners (world x virtual shards)
+    import torch as _t
+    buf = _t.zeros(4096, dtype=_t.int64, device="cuda")
+    ptrs = (N._P * 65)(*([buf.data_ptr()] * 65))
+    rc = N.lib().cc_route_queries_dev(0, buf.data_ptr(), buf.data_ptr(), 16, 31, buf.data_ptr(), 65, 0, 64, ptrs, ptrs, buf.data_ptr(), 16,
+                                      buf.data_ptr(), None)
+    assert rc == N.CC_ERR_ARG and "1..64" in N.last_error()
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two or more GPUs")
