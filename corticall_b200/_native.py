@@ -90,6 +90,9 @@ SIGNATURES = {
     "cc_gather_routed_dev": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_uint64, _P, C.c_int, C.c_uint64, _P, _P]),
     "cc_open_sharded": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     "cc_open_sharded_memory": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "cc_open_sharded_placed": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_P)]),
+    "cc_open_sharded_memory_placed": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_P)]),
+    "cc_sharded_placement": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "cc_open_sharded_device": (C.c_int, [C.POINTER(_P), _U64P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     "cc_dispose_sharded": (None, [_P]),
     "cc_sharded_info": (C.c_int, [_P, C.POINTER(C.c_int), _U64P, _U32P, _U32P]),

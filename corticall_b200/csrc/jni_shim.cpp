@@ -293,13 +293,13 @@ JFN(jlongArray, remove)(JNIEnv *env, jclass, jlong primary, jlongArray secondari
 }
 
 // ---- one graph over several GPUs of this process
-JFN(jlong, openSharded)(JNIEnv *env, jclass, jstring path, jintArray devices) {
+JFN(jlong, openSharded)(JNIEnv *env, jclass, jstring path, jintArray devices, jint placement) {
     const char *p = path ? env->GetStringUTFChars(path, nullptr) : nullptr;
     if (!p || !devices) { if (p) env->ReleaseStringUTFChars(path, p); fail_arg(env, "null path or device list"); return 0; }
     const jsize n = env->GetArrayLength(devices);
     jint *d = env->GetIntArrayElements(devices, nullptr);
     cc_sharded *sh = nullptr;
-    const int rc = d ? cc_open_sharded(p, reinterpret_cast<int *>(d), (int)n, &sh) : CC_ERR_ARG;
+    const int rc = d ? cc_open_sharded_placed(p, reinterpret_cast<int *>(d), (int)n, (int)placement, &sh) : CC_ERR_ARG;
     if (d) env->ReleaseIntArrayElements(devices, d, JNI_ABORT);
     env->ReleaseStringUTFChars(path, p);
     return check(env, rc) ? reinterpret_cast<jlong>(sh) : 0;

@@ -34,6 +34,8 @@ struct cc_sharded {
     cc::Header h;                             // the whole graph's header (num_records = all shards)
     uint32_t kw = 0;
     bool boundaries_checked = false;
+    bool replicated = false;                  // every device holds the WHOLE graph (shard[r] = full copy, first = 0); lookups need no exchange
+    std::vector<cc_graph *> scan_view;        // replicated only: device r's view of records [n r / world, n (r+1) / world) of its copy, for the scan
     void *map_base = nullptr;
     uint64_t map_len = 0;
     // ---- routed-lookup state, per rank (allocated on first use, grown on demand)
@@ -79,6 +81,7 @@ void destroy_sharded(cc_sharded *sh) {
         if (r < (int)sh->shard.size() && sh->shard[r] && sh->shard[r]->stream) cudaStreamSynchronize(sh->shard[r]->stream);
         free_rank(sh->rank[r]);
     }
+    for (cc_graph *g : sh->scan_view) if (g) cc_dispose(g);
     for (cc_graph *g : sh->shard) if (g) cc_dispose(g);
     for (int r = 0; r < (int)sh->owned_body.size(); ++r)
         if (sh->owned_body[r]) { cudaSetDevice(sh->dev[r]); cudaFree(sh->owned_body[r]); }
@@ -125,6 +128,18 @@ int finish_sharded(cc_sharded *sh, const void *const *bodies, const uint64_t *co
     sh->shard.assign(sh->world, nullptr);
     sh->first.assign(sh->world, 0);
     sh->rank.assign(sh->world, cc_sharded::Rank());
+    if (sh->replicated) {
+        // bodies[r] = device r's copy of all records; counts[r] = the slice of it device r scans
+        sh->scan_view.assign(sh->world, nullptr);
+        for (int r = 0; r < sh->world; ++r) {
+            if (int rc = cc_open_device(bodies[r], h.k, h.s, h.c, h.num_records, 0, sh->dev[r], &sh->shard[r])) return rc;
+            if (int rc = cc_open_device(static_cast<const uint8_t *>(bodies[r]) + at * h.record_size, h.k, h.s, h.c, counts[r], at, sh->dev[r], &sh->scan_view[r])) return rc;
+            sh->shard[r]->h.colors = h.colors.size() == h.c ? h.colors : sh->shard[r]->h.colors;
+            sh->shard[r]->h.version = 6;
+            at += counts[r];
+        }
+        return CC_OK;
+    }
     for (int r = 0; r < sh->world; ++r) {
         sh->first[r] = at;
         if (int rc = cc_open_device(bodies[r], h.k, h.s, h.c, counts[r], at, sh->dev[r], &sh->shard[r])) return rc;
@@ -147,8 +162,8 @@ int ensure_indices(cc_sharded *sh) {
             return fail(CC_ERR_UNSORTED, "Records are not sorted (record %llu sorts before its predecessor)",
                         (unsigned long long)(sh->first[r] + g->index.unsorted_at));
     }
-    // the order must also hold ACROSS the shard boundaries (checked once)
-    if (!sh->boundaries_checked) {
+    // the order must also hold ACROSS the shard boundaries (checked once; replicas hold the whole array)
+    if (!sh->boundaries_checked && !sh->replicated) {
         const uint32_t s = sh->h.s;
         std::vector<uint64_t> prev_last(s), cur(s);
         bool have_prev = false;
@@ -331,7 +346,19 @@ int routed_all(cc_sharded *sh, const uint64_t *const *words, const uint8_t *cons
     return CC_OK;
 }
 
+// Replicated placement: every device answers its own queries from its own copy -- no exchange, global indices directly.
+int local_all(cc_sharded *sh, const uint64_t *const *words, const uint8_t *const *flags, const uint64_t *nq, int64_t *const *out) {
+    for (int r = 0; r < sh->world; ++r) {
+        if (!nq[r]) continue;
+        CC_CUDA(cudaSetDevice(sh->dev[r]));
+        cc_graph *g = sh->shard[r];
+        if (int rc = launch_find_packed(g, words[r], flags && flags[r] ? flags[r] : nullptr, nq[r], out[r], CC_ALGO_AUTO, g->stream)) return rc;
+    }
+    return CC_OK;
+}
+
 void collect_stats(cc_sharded *sh) {
+    if (sh->replicated) return;
     float route = 0, search = 0, gather = 0, total = 0;
     for (int r = 0; r < sh->world; ++r) {
         cudaSetDevice(sh->dev[r]);
@@ -379,7 +406,8 @@ int cc_open_sharded_device(const void *const *dev_bodies, const uint64_t *counts
 }
 
 static int open_sharded_image(std::unique_ptr<cc_sharded, void (*)(cc_sharded *)> &sh, const uint8_t *image, uint64_t size, const char *path,
-                              const int *devices, int ndev, cc_sharded **out) {
+                              const int *devices, int ndev, int placement, cc_sharded **out) {
+    if (placement < CC_PLACE_RANGE || placement > CC_PLACE_AUTO) return fail(CC_ERR_ARG, "unknown placement %d", placement);
     if (int rc = parse_header(image, size, size, path, sh->h)) return rc;
     if (sh->h.s != (sh->h.k + 31) / 32) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': kmer_bits %u does not match kmer_size %u", path, sh->h.s, sh->h.k);
     if (int rc = check_devices(devices, ndev)) return rc;
@@ -390,6 +418,36 @@ static int open_sharded_image(std::unique_ptr<cc_sharded, void (*)(cc_sharded *)
     const uint64_t n = sh->h.num_records, S = sh->h.record_size;
     std::vector<const void *> bodies(ndev);
     std::vector<uint64_t> counts(ndev);
+    if (placement == CC_PLACE_AUTO) {
+        // replicas when a lookup-ready copy (records + key column + bucket lines, <= 32 bytes per record) takes at most a quarter of
+        // every device's free memory: lookups then need no exchange and scale with the device count; k-mer ranges otherwise
+        const uint64_t need = n * (S + 8ull * sh->h.s + 32) + (64ull << 20);
+        placement = CC_PLACE_REPLICATE;
+        for (int r = 0; r < ndev && placement == CC_PLACE_REPLICATE; ++r) {
+            size_t free_b = 0, total_b = 0;
+            CC_CUDA(cudaSetDevice(devices[r]));
+            CC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            if (need > free_b / 4) placement = CC_PLACE_RANGE;
+        }
+    }
+    sh->replicated = placement == CC_PLACE_REPLICATE && ndev > 1;
+    if (sh->replicated) {
+        for (int r = 0; r < ndev; ++r) {
+            counts[r] = n * (r + 1) / ndev - n * r / ndev;
+            CC_CUDA(cudaSetDevice(devices[r]));
+            CC_CUDA(cudaMalloc(&sh->owned_body[r], n * S + 256));
+            CC_CUDA(cudaMemcpyAsync(sh->owned_body[r], image + sh->h.data_offset, n * S, cudaMemcpyHostToDevice, nullptr));
+            CC_CUDA(cudaMemsetAsync(static_cast<uint8_t *>(sh->owned_body[r]) + n * S, 0, 256, nullptr));
+            bodies[r] = sh->owned_body[r];
+        }
+        for (int r = 0; r < ndev; ++r) {
+            CC_CUDA(cudaSetDevice(devices[r]));
+            CC_CUDA(cudaDeviceSynchronize());
+        }
+        if (int rc = finish_sharded(sh.get(), bodies.data(), counts.data())) return rc;
+        *out = sh.release();
+        return CC_OK;
+    }
     for (int r = 0; r < ndev; ++r) {
         const uint64_t lo = n * r / ndev, hi = n * (r + 1) / ndev;
         counts[r] = hi - lo;
@@ -405,6 +463,10 @@ static int open_sharded_image(std::unique_ptr<cc_sharded, void (*)(cc_sharded *)
 }
 
 int cc_open_sharded(const char *path, const int *devices, int ndev, cc_sharded **out) {
+    return cc_open_sharded_placed(path, devices, ndev, CC_PLACE_RANGE, out);
+}
+
+int cc_open_sharded_placed(const char *path, const int *devices, int ndev, int placement, cc_sharded **out) {
     if (!path || !out) return fail(CC_ERR_ARG, "null argument");
     *out = nullptr;
     std::unique_ptr<cc_sharded, void (*)(cc_sharded *)> sh(new cc_sharded(), destroy_sharded);
@@ -419,14 +481,18 @@ int cc_open_sharded(const char *path, const int *devices, int ndev, cc_sharded *
     if (m == MAP_FAILED) return fail(CC_ERR_IO, "Error while parsing Cortex graph file '%s': mmap: %s", path, strerror(errno));
     sh->map_base = m;
     sh->map_len = size;
-    return open_sharded_image(sh, static_cast<const uint8_t *>(m), size, path, devices, ndev, out);
+    return open_sharded_image(sh, static_cast<const uint8_t *>(m), size, path, devices, ndev, placement, out);
 }
 
 int cc_open_sharded_memory(const void *file_image, uint64_t size, const int *devices, int ndev, cc_sharded **out) {
+    return cc_open_sharded_memory_placed(file_image, size, devices, ndev, CC_PLACE_RANGE, out);
+}
+
+int cc_open_sharded_memory_placed(const void *file_image, uint64_t size, const int *devices, int ndev, int placement, cc_sharded **out) {
     if (!file_image || !out) return fail(CC_ERR_ARG, "null argument");
     *out = nullptr;
     std::unique_ptr<cc_sharded, void (*)(cc_sharded *)> sh(new cc_sharded(), destroy_sharded);
-    return open_sharded_image(sh, static_cast<const uint8_t *>(file_image), size, "<memory>", devices, ndev, out);
+    return open_sharded_image(sh, static_cast<const uint8_t *>(file_image), size, "<memory>", devices, ndev, placement, out);
 }
 
 void cc_dispose_sharded(cc_sharded *sh) { destroy_sharded(sh); }
@@ -437,6 +503,12 @@ int cc_sharded_info(const cc_sharded *sh, int *ndev, uint64_t *num_records, uint
     if (num_records) *num_records = sh->h.num_records;
     if (kmer_size) *kmer_size = sh->h.k;
     if (num_colors) *num_colors = sh->h.c;
+    return CC_OK;
+}
+
+int cc_sharded_placement(const cc_sharded *sh, int *placement) {
+    if (!sh || !placement) return fail(CC_ERR_ARG, "null argument");
+    *placement = sh->replicated ? CC_PLACE_REPLICATE : CC_PLACE_RANGE;
     return CC_OK;
 }
 
@@ -465,10 +537,12 @@ int cc_find_packed_sharded_dev(cc_sharded *sh, const uint64_t *const *dev_words,
     }
     if (longest == 0) return CC_OK;
     if (int rc = ensure_indices(sh)) return rc;
-    if (int rc = ensure_exchange(sh, pick_batch(sh, longest))) return rc;
+    if (!sh->replicated)
+        if (int rc = ensure_exchange(sh, pick_batch(sh, longest))) return rc;
     sh->stats = cc_sharded_stats{};
     const uint64_t launches0 = g_launches.load();
-    if (int rc = routed_all(sh, dev_words, dev_flags, nq, dev_out, sh->max_batch)) return rc;
+    if (sh->replicated) { if (int rc = local_all(sh, dev_words, dev_flags, nq, dev_out)) return rc; }
+    else if (int rc = routed_all(sh, dev_words, dev_flags, nq, dev_out, sh->max_batch)) return rc;
     if (int rc = sync_all(sh)) return rc;
     collect_stats(sh);
     sh->stats.launches = (uint32_t)(g_launches.load() - launches0);
@@ -522,7 +596,8 @@ int host_lookup(cc_sharded *sh, HostIn kind, const void *in, const uint8_t *flag
         const uint64_t per = (m + world - 1) / world;
         const uint64_t ascii_bytes = kind == HostIn::Ascii ? per * k : kind == HostIn::Windows ? per + k : 0;
         if (int rc = ensure_staging(sh, per, ascii_bytes)) return rc;
-        if (int rc = ensure_exchange(sh, pick_batch(sh, per))) return rc;
+        if (!sh->replicated)
+            if (int rc = ensure_exchange(sh, pick_batch(sh, per))) return rc;
         std::vector<const uint64_t *> w(world);
         std::vector<const uint8_t *> f(world);
         std::vector<int64_t *> o(world);
@@ -551,7 +626,8 @@ int host_lookup(cc_sharded *sh, HostIn kind, const void *in, const uint8_t *flag
             f[r] = (kind != HostIn::Packed || flags) ? rk.q_flags : nullptr;
             o[r] = rk.q_out;
         }
-        if (int rc = routed_all(sh, w.data(), (kind != HostIn::Packed || flags) ? f.data() : nullptr, cnt.data(), o.data(), sh->max_batch)) return rc;
+        if (sh->replicated) { if (int rc = local_all(sh, w.data(), (kind != HostIn::Packed || flags) ? f.data() : nullptr, cnt.data(), o.data())) return rc; }
+        else if (int rc = routed_all(sh, w.data(), (kind != HostIn::Packed || flags) ? f.data() : nullptr, cnt.data(), o.data(), sh->max_batch)) return rc;
         for (int r = 0; r < world; ++r) {
             CC_CUDA(cudaSetDevice(sh->dev[r]));
             CC_CUDA(cudaMemcpyAsync(out + lo[r], sh->rank[r].q_out, cnt[r] * 8, cudaMemcpyDeviceToHost, sh->shard[r]->stream));
@@ -615,7 +691,7 @@ int cc_find_novel_sharded(cc_sharded *sh, int32_t child, const int32_t *parents,
     for (int attempt = 0; attempt < 2; ++attempt) {
         bool again = false;
         for (int r = 0; r < world; ++r) {
-            cc_graph *g = sh->shard[r];
+            cc_graph *g = sh->replicated ? sh->scan_view[r] : sh->shard[r];
             const uint64_t n = g->h.num_records;
             if (attempt == 0) dcap[r] = std::min<uint64_t>(n, std::max<uint64_t>(65536, n / 32));
             else if (count[r] <= dcap[r]) continue;

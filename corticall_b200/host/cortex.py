@@ -607,16 +607,21 @@ class ShardedCortexGraph:
     globally ordered list.  The batch surface is CortexGraph's (findRecordIndices / findWindows / findPacked / findNovel /
     writeRois) and so are the answers; per-record access goes through `shard(r)`."""
 
-    def __init__(self, source, devices):
+    PLACEMENTS = {"range": 0, "replicate": 1, "auto": 2}
+
+    def __init__(self, source, devices, placement: str = "range"):
+        """placement: "range" = k-mer-range shards (graphs larger than one GPU), "replicate" = a full copy per device (no
+        exchange: lookups scale with the device count), "auto" = replicas when they fit (cc_open_sharded_placed)."""
         devs = (C.c_int * len(devices))(*[int(d) for d in devices])
         h = N._P()
+        place = self.PLACEMENTS[placement]
         if isinstance(source, (bytes, bytearray, memoryview)):
             buf = bytes(source)
-            N.check(N.lib().cc_open_sharded_memory(buf, len(buf), devs, len(devices), C.byref(h)))
+            N.check(N.lib().cc_open_sharded_memory_placed(buf, len(buf), devs, len(devices), place, C.byref(h)))
             self.cortexFile = None
         else:
             self.cortexFile = os.fspath(source)
-            N.check(N.lib().cc_open_sharded(self.cortexFile.encode(), devs, len(devices), C.byref(h)))
+            N.check(N.lib().cc_open_sharded_placed(self.cortexFile.encode(), devs, len(devices), place, C.byref(h)))
         self._h, self._keep = h, None
         self._info()
 
@@ -639,6 +644,9 @@ class ShardedCortexGraph:
         N.check(N.lib().cc_sharded_info(self._h, C.byref(nd), C.byref(nr), C.byref(k), C.byref(c)))
         self.numShards, self.numRecords, self.kmerSize, self.numColors = nd.value, nr.value, k.value, c.value
         self.kmerBits = getKmerBits(k.value)
+        pl = C.c_int(0)
+        N.check(N.lib().cc_sharded_placement(self._h, C.byref(pl)))
+        self.placement = "replicate" if pl.value == 1 else "range"
 
     def getNumRecords(self): return self.numRecords
     def getKmerSize(self): return self.kmerSize

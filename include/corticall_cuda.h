@@ -253,6 +253,16 @@ typedef struct {
 } cc_sharded_stats;
 CC_API int cc_open_sharded(const char *path, const int *devices, int ndev, cc_sharded **out);
 CC_API int cc_open_sharded_memory(const void *file_image, uint64_t size, const int *devices, int ndev, cc_sharded **out);
+/* Placement of the record array over the devices.  CC_PLACE_RANGE (what cc_open_sharded does): contiguous k-mer ranges, one per
+ * device -- for graphs larger than one GPU (BASELINE configs[3]); lookups are routed to the owning device.  CC_PLACE_REPLICATE:
+ * every device holds the whole array and its own index; a batch is split evenly and every device answers its share from its own
+ * copy -- no exchange, lookups scale with the device count; the scan still gives every device 1/ndev of the records.
+ * CC_PLACE_AUTO: replicas when a lookup-ready copy takes at most a quarter of every device's free memory, ranges otherwise.
+ * Results are identical under every placement (the reference has one CortexGraph per file: ArgumentHandler.java:271-274). */
+enum { CC_PLACE_RANGE = 0, CC_PLACE_REPLICATE = 1, CC_PLACE_AUTO = 2 };
+CC_API int cc_open_sharded_placed(const char *path, const int *devices, int ndev, int placement, cc_sharded **out);
+CC_API int cc_open_sharded_memory_placed(const void *file_image, uint64_t size, const int *devices, int ndev, int placement, cc_sharded **out);
+CC_API int cc_sharded_placement(const cc_sharded *sh, int *placement);   /* CC_PLACE_RANGE or CC_PLACE_REPLICATE: what the handle uses */
 /* Wrap slices that are already resident: dev_bodies[r] = counts[r] records (on-disk layout) on devices[r], ascending across r. */
 CC_API int cc_open_sharded_device(const void *const *dev_bodies, const uint64_t *counts, uint32_t k, uint32_t s, uint32_t c,
                                   const int *devices, int ndev, cc_sharded **out);

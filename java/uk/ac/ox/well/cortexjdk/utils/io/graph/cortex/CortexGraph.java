@@ -68,14 +68,16 @@ public class CortexGraph implements DeBruijnGraph {
         this(cortexFile, openNative(cortexFile));
     }
 
-    /** {cc_graph handle, cc_sharded handle or 0}: one device unless -Dcorticall.cuda.devices lists several. */
+    /** {cc_graph handle, cc_sharded handle or 0}: one device unless -Dcorticall.cuda.devices lists several
+     *  (-Dcorticall.cuda.placement=auto|range|replicate: replicas of a graph that fits every device, k-mer ranges otherwise). */
     private static long[] openNative(File f) {
         String devs = System.getProperty("corticall.cuda.devices");
         if (devs != null && devs.contains(",")) {
             String[] parts = devs.split(",");
             int[] ids = new int[parts.length];
             for (int i = 0; i < ids.length; i++) { ids[i] = Integer.parseInt(parts[i].trim()); }
-            long sh = NativeCortex.openSharded(f.getAbsolutePath(), ids);
+            String place = System.getProperty("corticall.cuda.placement", "auto");
+            long sh = NativeCortex.openSharded(f.getAbsolutePath(), ids, place.equals("range") ? 0 : place.equals("replicate") ? 1 : 2);
             return new long[] { NativeCortex.shardedShard(sh, 0)[0], sh };
         }
         return new long[] { NativeCortex.open(f.getAbsolutePath(), Integer.getInteger("corticall.cuda.device", 0)), 0 };

@@ -97,8 +97,9 @@ public final class NativeCortex {
     static native int[] covStats(long handle, int child, int[] parents);
 
     // one graph over several GPUs ---------------------------------------------------------------- cc_open_sharded / cc_*_sharded
-    /** The record array cut into k-mer-range shards, one per device id (ArgumentHandler.java:271-274 constructs ONE graph per file). */
-    static native long openSharded(String path, int[] devices);
+    /** One graph over several devices (ArgumentHandler.java:271-274 constructs ONE graph per file).  placement: 0 = k-mer-range shards,
+     *  1 = a replica per device (lookups need no exchange), 2 = replicas when they fit, ranges otherwise (cc_open_sharded_placed). */
+    static native long openSharded(String path, int[] devices, int placement);
     static native void disposeSharded(long shardedHandle);
     /** {numShards, numRecords, kmerSize, numColors} */
     static native long[] shardedInfo(long shardedHandle);

@@ -48,8 +48,10 @@ def test_sharded_matches_oracle_and_single_gpu(tmp_path, k, c, n):
     assert want_recs.tobytes() == o_recs and want_idx.tolist() == o_idx.tolist()
     single.writeRois(0, list(range(1, c)), tmp_path / "single.ctx")
     for devs in device_lists():
-        for source in (path, ctx):
-            sh = cb.ShardedCortexGraph(source, devs)
+        for source, placement in ((path, "range"), (ctx, "range"), (path, "replicate"), (ctx, "auto")):
+            sh = cb.ShardedCortexGraph(source, devs, placement)
+            # a replica per device when asked for (or when the graph fits: "auto" on these sizes), unless there is one device
+            assert sh.placement == ("range" if placement == "range" or len(devs) == 1 else "replicate")
             assert sh.getNumRecords() == n and sh.numShards == len(devs) and sh.getKmerSize() == k
             assert sh.findRecordIndices(qa).tolist() == want.tolist(), devs
             assert sh.findPacked(pw, flags).tolist() == want.tolist(), devs
@@ -61,9 +63,14 @@ def test_sharded_matches_oracle_and_single_gpu(tmp_path, k, c, n):
             assert cnt == want_cnt and recs.tobytes() == o_recs[:min(7, want_cnt) * (8 * s + 5)]
             assert sh.writeRois(0, list(range(1, c)), tmp_path / "sharded.ctx") == want_cnt
             assert (tmp_path / "sharded.ctx").read_bytes() == (tmp_path / "single.ctx").read_bytes()
-            # shards are ordinary graphs over their slices
+            # shards are ordinary graphs over their slices (a replica is the whole graph)
             g1, dev, first = sh.shard(len(devs) - 1)
-            assert first == n * (len(devs) - 1) // len(devs) and g1.getNumRecords() == n - first
+            if sh.placement == "range":
+                assert first == n * (len(devs) - 1) // len(devs) and g1.getNumRecords() == n - first
+            else:
+                assert first == 0 and g1.getNumRecords() == n
+                if n > 10:
+                    assert g1.getRecord(n - 3) == single.getRecord(n - 3)
             assert g1.getColor(0).getSampleName() == single.getColor(0).getSampleName()
             sh.dispose()
     single.dispose()
@@ -105,7 +112,16 @@ def test_sharded_device_resident_batches_and_skew():
     sh.findPackedDevice([q[0] for q in qs], [q[1] for q in qs], outs)
     for r in range(4):
         assert outs[r].cpu().numpy().tolist() == wants[r].tolist(), r
-    sh.dispose(); single.dispose()
+    sh.dispose()
+    # the same batches against replicas: no exchange, no overflow to handle, same answers
+    rep = cb.ShardedCortexGraph(ctx, devs, "replicate")
+    for o in outs:
+        o.fill_(-9)
+    rep.findPackedDevice([q[0] for q in qs], [q[1] for q in qs], outs)
+    for r in range(4):
+        assert outs[r].cpu().numpy().tolist() == wants[r].tolist(), r
+    assert rep.findPacked(qw.numpy().view(np.uint64)).tolist() == pick.tolist() and rep.lastStats().overflow_retries == 0
+    rep.dispose(); single.dispose()
 
 
 def test_sharded_rejects_bad_input(tmp_path):

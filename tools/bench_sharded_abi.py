@@ -60,3 +60,39 @@ print(json.dumps({"api": "cc_open_sharded_device + cc_find_packed_sharded_dev (o
                   "queries_per_call": nq * world, "lookups_per_s": nq * world / ms * 1e3, "ms_per_call_wall": ms,
                   "device_ms_first_chunk": {"route": st.route_ms, "search": st.search_ms, "gather": st.gather_ms, "route_to_gather_end": st.chunk_ms},
                   "launches": st.launches, "overflow_retries": st.overflow_retries, "device0_equals_whole_table_graph": bool(torch.equal(outs[0], ref))}))
+
+# ---- the same batch against REPLICAS (cc_open_sharded_memory_placed, CC_PLACE_REPLICATE / AUTO): a full copy and index per device,
+# every device answers its own queries -- what the library picks by itself ("auto") for a graph of this size
+sh.dispose()
+del bodies
+import numpy as np
+hdr = synth.header_bytes(K, C_)
+image = np.empty(len(hdr) + whole_body.numel(), dtype=np.uint8)
+image[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
+torch.from_numpy(image[len(hdr):]).copy_(whole_body.reshape(-1))
+t0 = time.perf_counter()
+rep = cb.ShardedCortexGraph(memoryview(image), list(range(world)), "auto")
+open_s = time.perf_counter() - t0
+for o in outs:
+    o.fill_(-7)
+t0 = time.perf_counter()
+rep.findPackedDevice(qws, qfs, outs)           # first call builds the per-device indices
+first_s = time.perf_counter() - t0
+times = []
+for _ in range(5):
+    t0 = time.perf_counter()
+    rep.findPackedDevice(qws, qfs, outs)
+    times.append(time.perf_counter() - t0)
+ms = sorted(times)[len(times) // 2] * 1e3
+same = bool(torch.equal(outs[0], ref))
+last = outs[world - 1].to("cuda:0")
+# the last device's answers against the whole-table graph too (its queries copied to device 0)
+torch.cuda.set_device(0)
+q_last, f_last = qws[world - 1].to("cuda:0"), qfs[world - 1].to("cuda:0")
+torch.cuda.synchronize()
+N.check(N.lib().cc_find_packed_dev(whole._h, q_last.data_ptr(), f_last.data_ptr(), nq, ref.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+print(json.dumps({"api": "cc_open_sharded_memory_placed(CC_PLACE_AUTO) + cc_find_packed_sharded_dev (one process, one host thread)", "placement": rep.placement,
+                  "n_gpus": world, "table_records": nt, "queries_per_call": nq * world, "lookups_per_s": nq * world / ms * 1e3, "ms_per_call_wall": ms,
+                  "open_seconds_upload_to_all_devices": open_s, "first_call_seconds_with_index_build": first_s,
+                  "device0_equals_whole_table_graph": same, "last_device_equals_whole_table_graph": bool(torch.equal(last, ref))}))
