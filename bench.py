@@ -740,6 +740,18 @@ def bench_lookup(args, env):
                 msr = env.timeit(lambda: N.check(L.cc_find_packed_dev(gfull._h, qwords.data_ptr(), qflags.data_ptr(), nq, res4.data_ptr(), cb.CC_ALGO_AUTO, stream)))
                 out["replicated_table_lookups_per_s"] = nq * world / (msr / 1000.0)
                 out["replicated_agrees"] = bool(torch.equal(res, res4))
+                # what cc_open_sharded_placed(CC_PLACE_AUTO) picks for this table: replicas when a lookup-ready copy (records + key column +
+                # <= 32 B of bucket lines per record) takes at most a quarter of a device's memory, k-mer ranges otherwise
+                need = nt * (REC_BYTES + 8 * S_WORDS + 32) + (64 << 20)
+                fits = need <= torch.cuda.get_device_properties(dev).total_memory // 4
+                out["placement"] = {"range_sharded_lookups_per_s": out["lookups_per_s"], "replicated_lookups_per_s": out["replicated_table_lookups_per_s"],
+                                    "auto_picks": "replicate" if fits else "range",
+                                    "auto_lookups_per_s": out["replicated_table_lookups_per_s"] if fits else out["lookups_per_s"],
+                                    "lookup_ready_copy_gb": need / 1e9,
+                                    "range_sharded_fraction_of_replicated": out["lookups_per_s"] / out["replicated_table_lookups_per_s"],
+                                    "note": "lookups_per_s above is the k-mer-range-sharded path the north star names (the only one possible for "
+                                            "configs[3]); a graph that fits every GPU is replicated by default and needs no exchange "
+                                            "(one process: profiles/r2_sharded_abi_n8.json)"}
                 gfull.dispose()
                 del full_body, res4
             except Exception as e:          # comparison mode only
