@@ -48,6 +48,16 @@ def test_no_cpu_fallback(fixture_ctx):
     par = np.array([1], dtype=np.int32)
     rc = N.lib().cc_find_novel_host(0, seq.ctypes.data, 31, 1, 2, 1, 0, par.ctypes.data, 1, None, None, 0, C.byref(cnt), None)
     assert rc == N.CC_ERR_CUDA
+    # the multi-GPU handle: every placement needs devices too; a bad placement is an argument error before anything else
+    buf = np.frombuffer(fixture_ctx, dtype=np.uint8)
+    devs = (C.c_int * 2)(0, 0)
+    for place in (0, 1, 2):
+        h = N._P()
+        assert N.lib().cc_open_sharded_memory_placed(buf.ctypes.data, buf.size, devs, 2, place, C.byref(h)) == N.CC_ERR_CUDA
+        assert "no CPU fallback" in N.last_error() and not h.value
+    h = N._P()
+    assert N.lib().cc_open_sharded_memory_placed(buf.ctypes.data, buf.size, devs, 2, 7, C.byref(h)) == N.CC_ERR_ARG
+    assert N.lib().cc_open_sharded_memory(buf.ctypes.data, buf.size, devs, 2, C.byref(h)) == N.CC_ERR_CUDA
 
 
 def open_status(image: bytes):
